@@ -1,0 +1,75 @@
+// Test-infrastructure stand-in for the handful of OpenCV declarations that the
+// reference's image operators touch.  NOT OpenCV, NOT product
+// code: it exists only so that /root/reference/src/{FOVUndistorter,
+// PhotometricUndistorter}.cpp and the compat headers can be compiled in a
+// container without OpenCV.  Pixel decode is delegated to a registry the test
+// harness fills (with pixels decoded by the real cv2 wheel) or to a PGM reader.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cassert>
+#include <cmath>
+#ifdef MDC_SHIM_WITH_MATH_H
+#include <math.h>   // pulls the float overloads of tan/sqrt into the global namespace (g++ >= 6)
+#endif
+#include <string>
+#include <vector>
+#include <memory>
+#include <iostream>
+
+#define CV_8U 0
+#define CV_16U 2
+#define CV_32F 5
+#define CV_LOAD_IMAGE_UNCHANGED (-1)
+#define CV_LOAD_IMAGE_GRAYSCALE 0
+
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+
+namespace cv {
+
+inline int shim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : 4); }
+
+class Mat {
+public:
+    int rows, cols;
+    unsigned char* data;
+
+    Mat() : rows(0), cols(0), data(0), type_(CV_8U) {}
+    Mat(int r, int c, int t) : rows(r), cols(c), data(0), type_(t) {
+        own_.reset(new std::vector<unsigned char>((size_t)r * c * shim_elem_size(t)));
+        data = own_->empty() ? 0 : &(*own_)[0];
+    }
+    Mat(int r, int c, int t, void* ext) : rows(r), cols(c), data((unsigned char*)ext), type_(t) {}
+
+    int type() const { return type_; }
+    bool empty() const { return rows == 0 || cols == 0; }
+    template <typename T> T& at(int i) { return ((T*)data)[i]; }
+    template <typename T> const T& at(int i) const { return ((const T*)data)[i]; }
+    template <typename T> T& at(int r, int c) { return ((T*)data)[(size_t)r * cols + c]; }
+
+    Mat operator*(double s) const {
+        Mat m(rows, cols, type_);
+        if (type_ == CV_32F)
+            for (size_t i = 0; i < (size_t)rows * cols; i++) m.at<float>((int)i) = (float)(at<float>((int)i) * s);
+        return m;
+    }
+
+private:
+    int type_;
+    std::shared_ptr<std::vector<unsigned char> > own_;
+};
+
+// implemented in oracle/shim/shim_impl.cpp
+Mat imread(const std::string& path, int flags);
+Mat imdecode(const Mat& buf, int flags);
+bool imwrite(const std::string& path, const Mat& m);
+void imshow(const std::string& name, const Mat& m);
+int waitKey(int ms);
+
+}  // namespace cv
+
+// registry used by the test harness: pixels decoded elsewhere (cv2) for `path`
+extern "C" void mdc_shim_register_image(const char* path, int rows, int cols, int type, const void* pixels);
+extern "C" void mdc_shim_clear_images();
