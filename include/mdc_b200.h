@@ -1,0 +1,181 @@
+/*
+ * mdc_b200.h — C ABI of the B200-native frame-preparation library (libmdc_b200.so).
+ *
+ * The reference (tum-vision/mono_dataset_code) has no FFI/plugin layer: its boundary
+ * is the C++ class surface of four headers.  This ABI is what those
+ * classes are re-implemented on (the headers under include/compat) and what any other host
+ * language binds.  Each entry point names the reference interface it
+ * replaces; paths are relative to the reference's src/ directory.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (MDC_OK = 0) and never throws; mdc_last_error() gives a thread-local message.  The
+ * reference's "print + early return + validity flag" error style is
+ * reproduced by the compat classes on top of these statuses.  There is NO CPU
+ * fallback: per-frame work always runs in the sm_100a kernels of this library and
+ * fails with MDC_ERR_CUDA when no device is usable.
+ */
+#ifndef MDC_B200_H
+#define MDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---------------------------------------------------------------- */
+#define MDC_OK 0
+#define MDC_ERR_INVALID_ARG 1   /* null pointer, bad size, wrong pixel count            */
+#define MDC_ERR_IO 2            /* file missing / unreadable                            */
+#define MDC_ERR_FORMAT 3        /* file present but not in the reference's format       */
+#define MDC_ERR_INVALID_OBJECT 4 /* operating on an object the reference would flag !valid */
+#define MDC_ERR_CUDA 5          /* CUDA runtime/driver failure (message has the detail) */
+#define MDC_ERR_UNSUPPORTED 6
+
+/* ---- per-frame mode flags (DatasetReader::getImage arguments, BenchmarkDatasetReader.h:188) */
+#define MDC_RECTIFY 1u          /* rectify                                              */
+#define MDC_REMOVE_GAMMA 2u     /* removeGamma     -> unMapImage undoGamma              */
+#define MDC_REMOVE_VIGNETTE 4u  /* removeVignette  -> unMapImage undoVignette           */
+#define MDC_NAN_OVEREXPOSED 8u  /* nanOverexposed  -> unMapImage killOverexposed        */
+
+/* output-camera modes of camera.txt line 3 (FOVUndistorter.cpp:86-110) */
+#define MDC_FOV_CROP (-1)
+#define MDC_FOV_FULL (-2)
+#define MDC_FOV_EXPLICIT 0
+
+#define MDC_MAX_PYR_LEVELS 8
+
+typedef struct mdc_fov mdc_fov;     /* host-side FOV rectifier model  (UndistorterFOV state)          */
+typedef struct mdc_photo mdc_photo; /* host-side photometric model    (PhotometricUndistorter state)  */
+typedef struct mdc_ctx mdc_ctx;     /* device context: tables resident in HBM + tile plan + streams   */
+typedef void* mdc_stream;           /* cudaStream_t (NULL = the context's own stream, synchronous API) */
+
+const char* mdc_last_error(void);
+const char* mdc_version(void);
+
+/* =====================================================================================
+ * FOV rectifier model — replaces UndistorterFOV's constructor and getters
+ * (FOVUndistorter.h:40-83, FOVUndistorter.cpp:48-269).  Tables are built on the HOST in
+ * strict IEEE float so they are bit-identical to the reference's.
+ * ===================================================================================== */
+
+/* UndistorterFOV(const char* configFileName), FOVUndistorter.cpp:48.  Always returns an
+ * object in *out (like the reference's constructor); status is MDC_OK only if the
+ * object is valid.  float_math: 0 = unqualified tan()/sqrt() are the double functions
+ * (canonical), 1 = the float overloads. */
+int mdc_fov_create(const char* camera_txt, mdc_fov** out);
+int mdc_fov_create_ex(const char* camera_txt, int float_math, mdc_fov** out);
+/* Same model from numbers instead of a file (lines 1-4 of camera.txt). */
+int mdc_fov_create_from_params(const float in_calib[5], int in_w, int in_h, int mode,
+                               const float out_calib[5], int out_w, int out_h, int float_math,
+                               mdc_fov** out);
+void mdc_fov_destroy(mdc_fov* f);
+int mdc_fov_is_valid(const mdc_fov* f);                              /* isValid(),  FOVUndistorter.h:80 */
+int mdc_fov_dims(const mdc_fov* f, int* in_w, int* in_h, int* out_w, int* out_h); /* getInputDims/getOutputDims, :71-78 */
+int mdc_fov_get_K(const mdc_fov* f, float k_rect[9], float k_org[9]);/* getK_rect/getK_org (row-major 3x3), :49-56 */
+float mdc_fov_omega(const mdc_fov* f);                               /* getOmega(), :57 */
+int mdc_fov_original_calibration(const mdc_fov* f, float v[5]);      /* getOriginalCalibration(), :61-70 */
+/* distortCoordinates(float*, float*, int), FOVUndistorter.cpp:280-319 (host, in place). */
+int mdc_fov_distort_coordinates(const mdc_fov* f, float* x, float* y, int n);
+/* remapX / remapY (out_w*out_h floats each; NULL for an invalid object) — private in the
+ * reference (FOVUndistorter.h:92-93); exposed for bit-compare and for NCCL broadcast. */
+const float* mdc_fov_remap_x(const mdc_fov* f);
+const float* mdc_fov_remap_y(const mdc_fov* f);
+
+/* =====================================================================================
+ * Photometric model — replaces PhotometricUndistorter's constructor and getters
+ * (PhotometricUndistorter.h:40-45, PhotometricUndistorter.cpp:42-157).
+ * ===================================================================================== */
+
+/* PhotometricUndistorter(std::string file, std::string vignetteImage, int w, int h).
+ * vignette: 8/16-bit greyscale PNG (non-interlaced) or binary PGM.  Always returns an
+ * object; status MDC_OK only if both gamma and vignette loaded. */
+int mdc_photo_create(const char* pcalib_txt, const char* vignette_image, int w, int h, mdc_photo** out);
+/* Same model from arrays: raw 256-entry inverse response (NULL = none) and decoded
+ * vignette pixels (depth 8 or 16; NULL = none; rows x cols must equal h x w). */
+int mdc_photo_create_from_arrays(const float* ginv_raw256, const void* vignette_pixels, int depth,
+                                 int rows, int cols, int w, int h, mdc_photo** out);
+void mdc_photo_destroy(mdc_photo* p);
+int mdc_photo_valid_gamma(const mdc_photo* p);
+int mdc_photo_valid_vignette(const mdc_photo* p);
+float* mdc_photo_ginv(mdc_photo* p);            /* getGInv(): NULL if !validGamma, PhotometricUndistorter.h:44 */
+float* mdc_photo_g(mdc_photo* p);               /* getG(),    PhotometricUndistorter.h:45 */
+const float* mdc_photo_vignette_map(const mdc_photo* p);     /* vignetteMap    (w*h) or NULL */
+const float* mdc_photo_vignette_map_inv(const mdc_photo* p); /* vignetteMapInv (w*h) or NULL */
+
+/* =====================================================================================
+ * Device context — tables uploaded once, resident in HBM; tile plan + TMA descriptors.
+ * One context per GPU (one process per GPU).  fov and/or photo may be NULL/invalid:
+ * operations needing the missing half then fail with MDC_ERR_INVALID_OBJECT.
+ * ===================================================================================== */
+int mdc_ctx_create(int device, const mdc_fov* fov, const mdc_photo* photo, mdc_ctx** out);
+/* Multi-GPU init: rank 0 builds the host models, broadcasts the four tables over NCCL
+ * (the host language's NCCL binding, e.g. torch.distributed) into DEVICE buffers the
+ * caller owns, and every rank adopts them here.  Pointers may be NULL for a missing
+ * half (d_remap_* NULL = no rectifier; d_ginv / d_vinv NULL = not loaded).  The buffers
+ * must outlive the context. */
+int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h, int out_w, int out_h,
+                                      const float* d_remap_x, const float* d_remap_y,
+                                      const float* d_ginv256, const float* d_vinv, mdc_ctx** out);
+void mdc_ctx_destroy(mdc_ctx* c);
+int mdc_ctx_device_tables(const mdc_ctx* c, const float** d_remap_x, const float** d_remap_y,
+                          const float** d_ginv256, const float** d_vinv);
+/* Pyramid geometry: level l has (out_w >> l) x (out_h >> l) pixels (odd trailing row/column dropped). */
+int mdc_ctx_level_dims(const mdc_ctx* c, int level, int* w, int* h);
+/* Number of kernel launches issued through this context so far (bench bookkeeping). */
+long long mdc_ctx_launch_count(const mdc_ctx* c);
+/* Tuning knobs (0 keeps the default): use_tma = -1 auto / 0 off / 1 on. */
+int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm);
+
+/* -------------------------------------------------------------------------------------
+ * Device-resident per-frame operators (all pointers are DEVICE pointers; `stream` is a
+ * cudaStream_t, NULL = the context's stream followed by a synchronize).
+ * ------------------------------------------------------------------------------------- */
+
+/* PhotometricUndistorter::unMapImage, PhotometricUndistorter.cpp:165-212, batched:
+ * in  [n_frames][n] u8, out [n_frames][n] f32; n must equal w*h of the photometric model.
+ * flags: MDC_REMOVE_GAMMA | MDC_REMOVE_VIGNETTE | MDC_NAN_OVEREXPOSED (sanitised as in :173-189). */
+int mdc_unmap_u8(mdc_ctx* c, const uint8_t* d_in, float* d_out, int n, int n_frames, unsigned flags, mdc_stream stream);
+
+/* UndistorterFOV::undistort<unsigned char> / <float>, FOVUndistorter.cpp:322-370, batched.
+ * Pixel-count mismatch leaves the output untouched and returns MDC_ERR_INVALID_ARG (the
+ * reference prints and returns, :327-338); an invalid rectifier returns MDC_ERR_INVALID_OBJECT (:325). */
+int mdc_undistort_u8(mdc_ctx* c, const uint8_t* d_in, float* d_out, int n_pix_in, int n_pix_out, int n_frames, mdc_stream stream);
+int mdc_undistort_f32(mdc_ctx* c, const float* d_in, float* d_out, int n_pix_in, int n_pix_out, int n_frames, mdc_stream stream);
+
+/* DatasetReader::getImage mode switch (BenchmarkDatasetReader.h:210-241) fused into one
+ * pass, batched, plus the consumer-side box-filter pyramid:
+ *   d_frames      [n_frames][in_w*in_h] u8
+ *   d_out_levels  array of `levels` device pointers; level l: [n_frames][w_l*h_l] f32.
+ *                 Level 0 is the getImage result (out_w x out_h if MDC_RECTIFY else in_w x in_h).
+ * levels = 1 gives exactly getImage.  This is the hot path (kernel K1). */
+int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_frames, unsigned flags,
+                      float* const* d_out_levels, int levels, mdc_stream stream);
+
+/* Stand-alone pyramid level (kernel K2): dst[x,y] = 0.25f*(((a+b)+c)+d) over the 2x2 block. */
+int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_dst, int n_frames, mdc_stream stream);
+
+/* responseCalib E-step, main_responseCalib.cpp:317-346 (kernel K3):
+ *   d_data [n][npix] u8 image-major, d_t [n] f64 exposure times, d_G [256] f64 -> d_E [npix] f64.
+ * Bit-exact with the reference's loop (sequential fp64 accumulation per pixel, no FMA). */
+int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, double* d_E, mdc_stream stream);
+
+/* -------------------------------------------------------------------------------------
+ * Host-buffer entry points (what the compat classes call): H2D copy, kernels, D2H copy.
+ * Host pointers may be pageable; pinned memory (mdc_host_alloc) makes the copies async.
+ * ------------------------------------------------------------------------------------- */
+int mdc_unmap_u8_host(mdc_ctx* c, const uint8_t* in, float* out, int n, unsigned flags);
+int mdc_undistort_u8_host(mdc_ctx* c, const uint8_t* in, float* out, int n_pix_in, int n_pix_out);
+int mdc_undistort_f32_host(mdc_ctx* c, const float* in, float* out, int n_pix_in, int n_pix_out);
+/* getImage for n_frames host frames; out_levels[l] host buffers laid out as in mdc_prepare_batch.
+ * Internally chunked and double-buffered so H2D, kernel and D2H overlap. */
+int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_frames, unsigned flags,
+                           float* const* out_levels, int levels);
+int mdc_host_alloc(void** p, size_t bytes);   /* pinned host memory */
+void mdc_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDC_B200_H */

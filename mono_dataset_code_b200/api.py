@@ -1,0 +1,350 @@
+"""Python host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the reference's C++ classes
+(/root/reference/src/FOVUndistorter.h:36-83, PhotometricUndistorter.h:37-45,
+BenchmarkDatasetReader.h:83-243), implemented on the C ABI of libmdc_b200.so.  The C++ mirror
+lives in include/compat/*.h; this module exists so tests and bench.py read like the
+reference's call sites.  torch is used for device memory, streams and torch.distributed only.
+
+Host arrays (numpy) go through the library's host-buffer entry points (H2D + kernel + D2H);
+CUDA tensors are processed in place on the device with no copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, MdcError, RECTIFY, REMOVE_GAMMA, REMOVE_VIGNETTE, NAN_OVEREXPOSED  # noqa: F401
+
+_f32p = C.POINTER(C.c_float)
+
+
+def _np_f32(ptr, n):
+    return np.ctypeslib.as_array(ptr, (n,)).copy() if ptr else None
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _flags(rectify, gamma, vignette, nan_over) -> int:
+    return (RECTIFY if rectify else 0) | (REMOVE_GAMMA if gamma else 0) | (REMOVE_VIGNETTE if vignette else 0) | \
+        (NAN_OVEREXPOSED if nan_over else 0)
+
+
+class UndistorterFOV:
+    """FOV-model rectifier (FOVUndistorter.h:36).  Invalid objects behave like the reference's:
+    isValid() is False and undistort() leaves the output untouched."""
+
+    def __init__(self, configFileName: str | None = None, *, float_math: bool = False, params=None):
+        h = C.c_void_p()
+        self.status = 0
+        if params is not None:   # (in_calib5, in_w, in_h, mode, out_calib5, out_w, out_h)
+            ic, iw, ih, mode, oc, ow, oh = params
+            ic = np.asarray(ic, np.float32)
+            oc = np.asarray(oc if oc is not None else [0] * 5, np.float32)
+            self.status = lib.mdc_fov_create_from_params(ic.ctypes.data_as(_f32p), iw, ih, mode, oc.ctypes.data_as(_f32p),
+                                                         ow, oh, int(float_math), C.byref(h))
+        elif configFileName is not None:
+            self.status = lib.mdc_fov_create_ex(str(configFileName).encode(), int(float_math), C.byref(h))
+        self._h = h if h.value else None
+        self._ctx = None
+
+    def __del__(self):
+        if getattr(self, "_ctx", None) is not None:
+            self._ctx.close()
+        if getattr(self, "_h", None):
+            lib.mdc_fov_destroy(self._h)
+            self._h = None
+
+    # ---- getters (FOVUndistorter.h:49-83)
+    def isValid(self) -> bool:
+        return bool(self._h) and bool(lib.mdc_fov_is_valid(self._h))
+
+    def _dims(self):
+        d = [C.c_int() for _ in range(4)]
+        if self._h:
+            lib.mdc_fov_dims(self._h, *[C.byref(x) for x in d])
+        return [x.value for x in d]
+
+    def getInputDims(self):
+        return tuple(self._dims()[:2])
+
+    def getOutputDims(self):
+        return tuple(self._dims()[2:])
+
+    def _K(self):
+        a, b = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        if self._h:
+            lib.mdc_fov_get_K(self._h, a.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p))
+        return a.reshape(3, 3), b.reshape(3, 3)
+
+    def getK_rect(self):
+        return self._K()[0]
+
+    def getK_org(self):
+        return self._K()[1]
+
+    def getOmega(self) -> float:
+        return float(lib.mdc_fov_omega(self._h)) if self._h else 0.0
+
+    def getOriginalCalibration(self):
+        v = np.zeros(5, np.float32)
+        if self._h:
+            lib.mdc_fov_original_calibration(self._h, v.ctypes.data_as(_f32p))
+        return v
+
+    def remap_tables(self):
+        """(remapX, remapY) copies — private in the reference; exposed for bit-compare / broadcast."""
+        if not self.isValid():
+            return None, None
+        n = self.getOutputDims()[0] * self.getOutputDims()[1]
+        return _np_f32(lib.mdc_fov_remap_x(self._h), n), _np_f32(lib.mdc_fov_remap_y(self._h), n)
+
+    def distortCoordinates(self, in_x: np.ndarray, in_y: np.ndarray, n: int | None = None) -> None:
+        """In place, like FOVUndistorter.cpp:280.  Prints and returns on an invalid object."""
+        assert in_x.dtype == np.float32 and in_y.dtype == np.float32 and in_x.flags.c_contiguous and in_y.flags.c_contiguous
+        n = in_x.size if n is None else n
+        if not self._h:
+            print("ERROR: invalid UndistorterFOV!")
+            return
+        lib.mdc_fov_distort_coordinates(self._h, in_x.ctypes.data_as(_f32p), in_y.ctypes.data_as(_f32p), n)
+
+    # ---- per-frame operator (FOVUndistorter.cpp:322-370)
+    def _context(self, device=0):
+        if self._ctx is None:
+            self._ctx = Context(self, None, device)
+        return self._ctx
+
+    def undistort(self, input, output, nPixIn: int | None = None, nPixOut: int | None = None) -> None:
+        """undistort<T>(input, output, nPixIn, nPixOut); T from input dtype (uint8 / float32).
+        numpy arrays = host buffers; CUDA tensors = device buffers.  Error behaviour as the
+        reference: invalid object or wrong pixel counts -> message, output untouched."""
+        if not self.isValid():
+            return
+        nPixIn = int(np.prod(input.shape)) if nPixIn is None else nPixIn
+        nPixOut = int(np.prod(output.shape)) if nPixOut is None else nPixOut
+        try:
+            if _is_torch(input):
+                ctx = self._context(input.device.index or 0)
+                ctx.undistort_device(input, output, nPixIn, nPixOut)
+            else:
+                self._context().undistort_host(input, output, nPixIn, nPixOut)
+        except MdcError as e:
+            if e.code == 5:   # CUDA failure is not a reference-style soft error
+                raise
+
+
+class PhotometricUndistorter:
+    """Photometric un-mapper (PhotometricUndistorter.h:37)."""
+
+    def __init__(self, file: str, vignetteImage: str, w_: int, h_: int, *, arrays=None):
+        h = C.c_void_p()
+        self.w, self.h = w_, h_
+        if arrays is not None:   # (ginv_raw256 or None, vignette pixel array or None)
+            raw, vig = arrays
+            rawp = np.ascontiguousarray(raw, np.float32).ctypes.data_as(_f32p) if raw is not None else None
+            if vig is not None:
+                vig = np.ascontiguousarray(vig)
+                self.status = lib.mdc_photo_create_from_arrays(rawp, vig.ctypes.data_as(C.c_void_p), 8 if vig.dtype == np.uint8 else 16,
+                                                               vig.shape[0], vig.shape[1], w_, h_, C.byref(h))
+            else:
+                self.status = lib.mdc_photo_create_from_arrays(rawp, None, 0, 0, 0, w_, h_, C.byref(h))
+        else:
+            self.status = lib.mdc_photo_create(str(file).encode(), str(vignetteImage).encode(), w_, h_, C.byref(h))
+        self._h = h if h.value else None
+        self._ctx = None
+
+    def __del__(self):
+        if getattr(self, "_ctx", None) is not None:
+            self._ctx.close()
+        if getattr(self, "_h", None):
+            lib.mdc_photo_destroy(self._h)
+            self._h = None
+
+    @property
+    def validGamma(self) -> bool:
+        return bool(self._h) and bool(lib.mdc_photo_valid_gamma(self._h))
+
+    @property
+    def validVignette(self) -> bool:
+        return bool(self._h) and bool(lib.mdc_photo_valid_vignette(self._h))
+
+    def getGInv(self):
+        return _np_f32(lib.mdc_photo_ginv(self._h), 256) if self._h else None
+
+    def getG(self):
+        return _np_f32(lib.mdc_photo_g(self._h), 256) if self._h else None
+
+    def vignette_maps(self):
+        if not self.validVignette:
+            return None, None
+        n = self.w * self.h
+        return _np_f32(lib.mdc_photo_vignette_map(self._h), n), _np_f32(lib.mdc_photo_vignette_map_inv(self._h), n)
+
+    def _context(self, device=0):
+        if self._ctx is None:
+            self._ctx = Context(None, self, device)
+        return self._ctx
+
+    def unMapImage(self, image_in, image_out, n: int, undoGamma: bool, undoVignette: bool, killOverexposed: bool) -> None:
+        flags = _flags(False, undoGamma, undoVignette, killOverexposed)
+        if _is_torch(image_in):
+            self._context(image_in.device.index or 0).unmap_device(image_in, image_out, n, flags)
+        else:
+            self._context().unmap_host(image_in, image_out, n, flags)
+
+
+class Context:
+    """Device context: calibration tables resident in HBM + tile plan (mdc_ctx)."""
+
+    def __init__(self, fov: UndistorterFOV | None, photo: PhotometricUndistorter | None, device: int = 0, *, _adopt=None):
+        h = C.c_void_p()
+        self._keep = None
+        if _adopt is not None:
+            dims, tensors = _adopt   # (in_w, in_h, out_w, out_h), (rx, ry, ginv, vinv) CUDA tensors or None
+            self._keep = tensors
+            ptrs = [C.c_void_p(t.data_ptr()) if t is not None else None for t in tensors]
+            check(lib.mdc_ctx_create_from_device_tables(device, *dims, *ptrs, C.byref(h)), "mdc_ctx_create_from_device_tables")
+        else:
+            check(lib.mdc_ctx_create(device, fov._h if fov is not None else None, photo._h if photo is not None else None,
+                                     C.byref(h)), "mdc_ctx_create")
+        self._h = h
+        self.device = device
+        self.fov, self.photo = fov, photo
+
+    @classmethod
+    def from_device_tables(cls, device, in_w, in_h, out_w, out_h, rx, ry, ginv, vinv):
+        """Adopt tables that were broadcast over NCCL into CUDA tensors (multi-GPU init)."""
+        return cls(None, None, device, _adopt=((in_w, in_h, out_w, out_h), (rx, ry, ginv, vinv)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.mdc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def configure(self, use_tma: int = -1, ctas_per_sm: int = 0):
+        check(lib.mdc_ctx_configure(self._h, use_tma, ctas_per_sm), "mdc_ctx_configure")
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.mdc_ctx_launch_count(self._h))
+
+    def level_dims(self, level: int):
+        w, h = C.c_int(), C.c_int()
+        check(lib.mdc_ctx_level_dims(self._h, level, C.byref(w), C.byref(h)), "mdc_ctx_level_dims")
+        return w.value, h.value
+
+    @staticmethod
+    def _stream(t):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    # ---- device-resident operators (CUDA tensors, asynchronous on torch's current stream)
+    def prepare_batch(self, frames, flags: int, out_levels):
+        """frames: uint8 CUDA tensor [n, H*W] (or [n,H,W]); out_levels: list of float32 CUDA tensors."""
+        n = frames.shape[0]
+        arr = (C.c_void_p * len(out_levels))(*[t.data_ptr() for t in out_levels])
+        check(lib.mdc_prepare_batch(self._h, C.c_void_p(frames.data_ptr()), n, flags, arr, len(out_levels), self._stream(frames)),
+              "mdc_prepare_batch")
+
+    def unmap_device(self, image_in, image_out, n, flags, n_frames=1):
+        check(lib.mdc_unmap_u8(self._h, C.c_void_p(image_in.data_ptr()), C.c_void_p(image_out.data_ptr()), n, n_frames, flags,
+                               self._stream(image_in)), "mdc_unmap_u8")
+
+    def undistort_device(self, inp, out, n_in, n_out, n_frames=1):
+        import torch
+        fn = lib.mdc_undistort_u8 if inp.dtype == torch.uint8 else lib.mdc_undistort_f32
+        check(fn(self._h, C.c_void_p(inp.data_ptr()), C.c_void_p(out.data_ptr()), n_in, n_out, n_frames, self._stream(inp)),
+              "mdc_undistort")
+
+    def pyr_down(self, src, sw, sh, dst, n_frames=1):
+        check(lib.mdc_pyr_down(self._h, C.c_void_p(src.data_ptr()), sw, sh, C.c_void_p(dst.data_ptr()), n_frames, self._stream(src)),
+              "mdc_pyr_down")
+
+    def estep(self, data, t, G, E):
+        """data uint8 [n, npix], t float64 [n], G float64 [256] -> E float64 [npix] (all CUDA tensors)."""
+        check(lib.mdc_estep(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                            C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), self._stream(data)), "mdc_estep")
+
+    # ---- host-buffer operators (numpy)
+    def unmap_host(self, image_in: np.ndarray, image_out: np.ndarray, n, flags):
+        assert image_in.dtype == np.uint8 and image_out.dtype == np.float32
+        check(lib.mdc_unmap_u8_host(self._h, image_in.ctypes.data_as(C.c_void_p), image_out.ctypes.data_as(C.c_void_p), n, flags),
+              "mdc_unmap_u8_host")
+
+    def undistort_host(self, inp: np.ndarray, out: np.ndarray, n_in, n_out):
+        assert out.dtype == np.float32 and inp.dtype in (np.uint8, np.float32)
+        fn = lib.mdc_undistort_u8_host if inp.dtype == np.uint8 else lib.mdc_undistort_f32_host
+        check(fn(self._h, inp.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n_in, n_out), "mdc_undistort_host")
+
+    def prepare_batch_host(self, frames, flags: int, out_levels):
+        """frames / out_levels: numpy arrays or raw integer addresses of (pinned) host memory."""
+        def addr(x):
+            return x if isinstance(x, int) else x.ctypes.data
+        n = frames.shape[0] if hasattr(frames, "shape") else None
+        raise_if = n is None
+        if raise_if:
+            raise ValueError("frames must be an array")
+        arr = (C.c_void_p * len(out_levels))(*[addr(t) for t in out_levels])
+        check(lib.mdc_prepare_batch_host(self._h, C.c_void_p(addr(frames)), n, flags, arr, len(out_levels)), "mdc_prepare_batch_host")
+
+
+class ExposureImage:
+    """ExposureImage.h:33 — float image + metadata (numpy-owned)."""
+
+    def __init__(self, w_, h_, timestamp_, exposure_, id_):
+        self.w, self.h, self.timestamp, self.exposure_time, self.id = w_, h_, timestamp_, exposure_, id_
+        self.image = np.empty(w_ * h_, np.float32)
+
+
+class FramePreparer:
+    """The getImage composition of DatasetReader (BenchmarkDatasetReader.h:188-243) over frames
+    that are already decoded (decode/zip is out of scope)."""
+
+    def __init__(self, undistorter: UndistorterFOV, photoUndistorter: PhotometricUndistorter, device: int = 0):
+        self.undistorter, self.photoUndistorter = undistorter, photoUndistorter
+        self.widthOrg, self.heightOrg = undistorter.getInputDims()
+        self.width, self.height = undistorter.getOutputDims()
+        self.ctx = Context(undistorter, photoUndistorter, device)
+
+    def getUndistorter(self):
+        return self.undistorter
+
+    def getPhotoUndistorter(self):
+        return self.photoUndistorter
+
+    def getImage(self, imageRaw: np.ndarray, id_: int, rectify: bool, removeGamma: bool, removeVignette: bool,
+                 nanOverexposed: bool, timestamp: float = 0.0, exposure: float = 0.0):
+        """One decoded 8-bit frame -> ExposureImage, or None on a dimension/type mismatch (:194-205)."""
+        if imageRaw.ndim != 2 or imageRaw.shape != (self.heightOrg, self.widthOrg):
+            shp = imageRaw.shape if imageRaw.ndim == 2 else (0, 0)
+            print("ERROR: expected cv-mat to have dimensions %d x %d; found %d x %d (image %d)!" %
+                  (self.widthOrg, self.heightOrg, shp[1], shp[0], id_))
+            return None
+        if imageRaw.dtype != np.uint8:
+            print("ERROR: expected cv-mat to have type 8U!")
+            return None
+        w, h = (self.width, self.height) if rectify else (self.widthOrg, self.heightOrg)
+        ret = ExposureImage(w, h, timestamp, exposure, id_)
+        raw = np.ascontiguousarray(imageRaw).reshape(1, -1)
+        self.ctx.prepare_batch_host(raw, _flags(rectify, removeGamma, removeVignette, nanOverexposed), [ret.image])
+        return ret
+
+    def level_shapes(self, rectify: bool, levels: int):
+        w, h = (self.width, self.height) if rectify else (self.widthOrg, self.heightOrg)
+        return [(w >> l, h >> l) for l in range(levels)]
+
+    def prepare_device(self, frames, rectify, removeGamma, removeVignette, nanOverexposed, levels: int = 1, out=None):
+        """Batched, device-resident getImage (+ pyramid): frames uint8 CUDA tensor [n, H*W]."""
+        import torch
+        n = frames.shape[0]
+        if out is None:
+            out = [torch.empty((n, w * h), dtype=torch.float32, device=frames.device) for (w, h) in self.level_shapes(rectify, levels)]
+        self.ctx.prepare_batch(frames, _flags(rectify, removeGamma, removeVignette, nanOverexposed), out)
+        return out

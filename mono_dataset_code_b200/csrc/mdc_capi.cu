@@ -1,0 +1,609 @@
+// C-ABI glue: device context (tables in HBM, tile plan, TMA descriptors), the getImage mode
+// switch, and the host-buffer pipeline.  See include/mdc_b200.h for the contract of each entry.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "mdc_internal.h"
+#include "mdc_kernels.cuh"
+
+using namespace mdc;
+
+#define CU_CHECK(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            mdc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return MDC_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+constexpr int kMapSlots = 8;        // host-side cache of encoded descriptor sets, keyed by (frames ptr, n_frames)
+constexpr int kHostPipeDepth = 3;   // host-buffer pipeline: chunks in flight
+constexpr int kMaxStagedPx = 8192;  // largest staged box (pixels, height rounded to 8): 32 KB float tile
+
+}  // namespace
+
+struct mdc_ctx {
+    int device = 0, sm_count = 148;
+    int in_w = 0, in_h = 0, out_w = 0, out_h = 0;
+    bool have_fov = false, have_gamma = false, have_vig = false;
+    // device tables (owned unless adopted)
+    bool owns_tables = true;
+    float *d_rx = nullptr, *d_ry = nullptr, *d_ginv = nullptr, *d_vinv = nullptr;
+    // tile plan
+    std::vector<TileDesc> tiles;
+    std::vector<uint32_t> cost_prefix;
+    std::vector<std::pair<int, int>> classes;   // (bw, bh rounded to 8) of every TMA box class
+    int tiles_x = 0, tiles_y = 0, box_px_max = 128;
+    bool plan_tma_ok = false;
+    TileDesc* d_tiles = nullptr;
+    uint32_t* d_cost_prefix = nullptr;
+    // TMA descriptor cache (host memory; descriptors are passed to the kernel by value)
+    TmaMaps* maps[kMapSlots] = {};
+    const void* map_key_ptr[kMapSlots] = {};
+    int map_key_frames[kMapSlots] = {};
+    int map_next = 0;
+    // knobs
+    int use_tma = -1, ctas_per_sm = 0;
+    // streams + host pipeline scratch
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe_stream[kHostPipeDepth] = {nullptr, nullptr, nullptr};
+    uint8_t* pipe_in[kHostPipeDepth] = {nullptr, nullptr, nullptr};
+    float* pipe_out[kHostPipeDepth] = {nullptr, nullptr, nullptr};
+    size_t pipe_in_bytes = 0, pipe_out_bytes = 0;
+    // scratch for the single-op host entry points
+    void* scratch_a = nullptr; size_t scratch_a_bytes = 0;
+    void* scratch_b = nullptr; size_t scratch_b_bytes = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int ensure_bytes(void** p, size_t* have, size_t need) {
+    if (*have >= need) return MDC_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    CU_CHECK(cudaMalloc(p, need));
+    *have = need;
+    return MDC_OK;
+}
+
+// Build the tile plan from HOST copies of the remap tables.
+void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
+    const int OW = c->out_w, OH = c->out_h, W = c->in_w, H = c->in_h;
+    c->tiles_x = (OW + kTile - 1) / kTile;
+    c->tiles_y = (OH + kTile - 1) / kTile;
+    const int n_tiles = c->tiles_x * c->tiles_y;
+    c->tiles.assign(n_tiles, TileDesc{0, 0, 0, TILE_EMPTY});
+    c->cost_prefix.assign(n_tiles + 1, 0);
+    const bool tma_geom_ok = (W % 16 == 0) && (static_cast<long long>(W) * H % 16 == 0);
+    // relative per-frame cost of a tile (pixel-equivalents), used to balance the static schedule
+    const char* e;
+    const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 1;       // per staged input pixel (LUT pass)
+    const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 4;     // per output pixel (gather + blend + store)
+    const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 12;
+    // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
+    for (int gran = 8; gran <= 256; gran *= 2) {
+    c->classes.clear();
+    c->box_px_max = 128;
+    std::map<std::pair<int, int>, int> class_index;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int tx0 = (t % c->tiles_x) * kTile, ty0 = (t / c->tiles_x) * kTile;
+        int xlo = 1 << 30, xhi = -1, ylo = 1 << 30, yhi = -1;
+        for (int y = ty0; y < std::min(ty0 + kTile, OH); ++y)
+            for (int x = tx0; x < std::min(tx0 + kTile, OW); ++x) {
+                const float sx = rx[static_cast<size_t>(y) * OW + x], sy = ry[static_cast<size_t>(y) * OW + x];
+                if (sx < 0) continue;
+                const int xi = static_cast<int>(sx), yi = static_cast<int>(sy);
+                xlo = std::min(xlo, xi); xhi = std::max(xhi, xi + 1);
+                ylo = std::min(ylo, yi); yhi = std::max(yhi, yi + 1);
+            }
+        TileDesc td{0, 0, 0, TILE_EMPTY};
+        uint32_t cost = kTile * kTile;   // an empty tile still writes zeros
+        if (xhi >= 0) {
+            // defensive: a table that violates the reference's in-bounds guarantee would read outside the frame
+            xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
+            xhi = std::min(xhi, W - 1); yhi = std::min(yhi, H - 1);
+            const int x0 = xlo & ~15;
+            const int bw = ((xhi - x0 + 1) + 15) & ~15;
+            const int bh = yhi - ylo + 1, bh8 = (bh + gran - 1) / gran * gran;
+            int lg = 2;
+            while ((4 << lg) < bw) ++lg;
+            const int rstep = std::max(1, kThreads >> lg);
+            const bool staged = bw <= 256 && bh8 <= 256 && bw * bh8 <= kMaxStagedPx &&
+                                (bh + rstep - 1) / rstep <= kMaxBoxWordsPerThread;
+            td.x0 = x0; td.y0 = ylo; td.bw_bh = bw | (bh << 16);
+            if (staged) {
+                int cls = 0;
+                if (tma_geom_ok) {
+                    auto key = std::make_pair(bw, bh8);
+                    auto it = class_index.find(key);
+                    if (it == class_index.end()) {
+                        cls = static_cast<int>(c->classes.size());
+                        class_index[key] = cls;
+                        c->classes.push_back(key);
+                    } else cls = it->second;
+                }
+                td.mode_map = TILE_STAGED | (cls << 8) | (bh8 << 16);
+                c->box_px_max = std::max(c->box_px_max, bw * bh8);
+                cost = static_cast<uint32_t>(cost_in * bw * bh + cost_out * kTile * kTile);
+            } else {
+                td.mode_map = TILE_DIRECT;
+                cost = static_cast<uint32_t>(cost_direct * kTile * kTile);
+            }
+        }
+        c->tiles[t] = td;
+        c->cost_prefix[t + 1] = c->cost_prefix[t] + std::max<uint32_t>(cost, 1u);
+    }
+    if (static_cast<int>(c->classes.size()) <= kMaxClasses) break;
+    }
+    c->plan_tma_ok = tma_geom_ok && !c->classes.empty() && static_cast<int>(c->classes.size()) <= kMaxClasses && encode_tiled_fn() != nullptr;
+}
+
+int upload_plan(mdc_ctx* c) {
+    const size_t n = c->tiles.size();
+    CU_CHECK(cudaMalloc(&c->d_tiles, std::max<size_t>(n, 1) * sizeof(TileDesc)));
+    CU_CHECK(cudaMalloc(&c->d_cost_prefix, (n + 1) * sizeof(uint32_t)));
+    CU_CHECK(cudaMemcpy(c->d_tiles, c->tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMemcpy(c->d_cost_prefix, c->cost_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return MDC_OK;
+}
+
+int ctx_common_init(mdc_ctx* c, int device) {
+    c->device = device;
+    CU_CHECK(cudaSetDevice(device));
+    int v = 0;
+    CU_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    c->sm_count = v;
+    CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const char* e = getenv("MDC_USE_TMA");
+    if (e) c->use_tma = atoi(e);
+    e = getenv("MDC_CTAS_PER_SM");
+    if (e) c->ctas_per_sm = atoi(e);
+    return MDC_OK;
+}
+
+// descriptors for `frames` ([n_frames][H][W] u8): one per box class; encoded sets are cached on the host
+int get_tensor_maps(mdc_ctx* c, const uint8_t* frames, int n_frames, const TmaMaps** out) {
+    for (int s = 0; s < kMapSlots; ++s)
+        if (c->maps[s] && c->map_key_ptr[s] == frames && c->map_key_frames[s] == n_frames) { *out = c->maps[s]; return MDC_OK; }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { mdc_set_error("cuTensorMapEncodeTiled unavailable"); return MDC_ERR_CUDA; }
+    const int slot = c->map_next;
+    c->map_next = (c->map_next + 1) % kMapSlots;
+    if (!c->maps[slot]) {
+        void* mem = nullptr;
+        if (posix_memalign(&mem, 64, sizeof(TmaMaps)) != 0) { mdc_set_error("out of memory"); return MDC_ERR_CUDA; }
+        memset(mem, 0, sizeof(TmaMaps));
+        c->maps[slot] = static_cast<TmaMaps*>(mem);
+    }
+    c->map_key_ptr[slot] = nullptr;
+    for (size_t i = 0; i < c->classes.size(); ++i) {
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(c->in_w), static_cast<cuuint64_t>(c->in_h), static_cast<cuuint64_t>(n_frames)};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(c->in_w), static_cast<cuuint64_t>(c->in_w) * c->in_h};
+        const cuuint32_t box[3] = {static_cast<cuuint32_t>(c->classes[i].first), static_cast<cuuint32_t>(c->classes[i].second), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult r = enc(&c->maps[slot]->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(frames), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mdc_set_error("cuTensorMapEncodeTiled failed (%d) for box %u x %u", (int)r, box[0], box[1]); return MDC_ERR_CUDA; }
+    }
+    c->map_key_ptr[slot] = frames;
+    c->map_key_frames[slot] = n_frames;
+    *out = c->maps[slot];
+    return MDC_OK;
+}
+
+struct UnmapFlags { bool gamma, vig, kill; };
+
+// flag sanitising of unMapImage, PhotometricUndistorter.cpp:173-189
+UnmapFlags sanitise(const mdc_ctx* c, unsigned flags) {
+    UnmapFlags u{(flags & MDC_REMOVE_GAMMA) != 0, (flags & MDC_REMOVE_VIGNETTE) != 0, (flags & MDC_NAN_OVEREXPOSED) != 0};
+    if (!c->have_gamma && u.gamma) {
+        printf("Photometric Undistorter did not load Gamma correctly. correctly. Not undoing gamma!\n");
+        u.gamma = false;
+    }
+    if (!c->have_vig && u.vig) {
+        printf("Photometric Undistorter did not load Vignette correctly. correctly. Not undoing Vignette!\n");
+        u.vig = false;
+    }
+    if (!u.gamma && u.vig) {
+        printf("it doesn't make sense to undo vignette without undoing gamma! not doing neither.\n");
+        u.vig = false; u.gamma = false;
+    }
+    return u;
+}
+
+int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, float* const* d_out_levels, int levels,
+              cudaStream_t stream) {
+    FusedParams p;
+    memset(&p, 0, sizeof p);
+    p.frames = d_frames; p.n_frames = n_frames;
+    p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h;
+    p.remap_x = c->d_rx; p.remap_y = c->d_ry; p.vinv = c->d_vinv; p.ginv = c->d_ginv;
+    p.tiles = c->d_tiles; p.tile_cost_prefix = c->d_cost_prefix;
+    p.tiles_x = c->tiles_x; p.n_tiles = static_cast<int>(c->tiles.size());
+    const int in_kernel = std::min(levels, kInKernelLevels);
+    p.levels = in_kernel;
+    for (int l = 0; l < in_kernel; ++l) { p.out[l] = d_out_levels[l]; p.lw[l] = c->out_w >> l; p.lh[l] = c->out_h >> l; }
+    for (int l = in_kernel; l < MDC_MAX_PYR_LEVELS; ++l) { p.lw[l] = p.lh[l] = 0; }
+    p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
+    p.box_px_max = c->box_px_max;
+    p.vec2_ok = (c->out_w % 2 == 0) && (reinterpret_cast<uintptr_t>(d_out_levels[0]) % 8 == 0);
+    bool tma = c->plan_tma_ok && c->use_tma != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
+    if (c->use_tma == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
+    const TmaMaps* maps = nullptr;
+    if (tma) {
+        int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
+        if (rc != MDC_OK) return rc;
+    }
+    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma);
+    if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
+    if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
+    long long units = static_cast<long long>(p.n_tiles) * n_frames;
+    int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(units, 1)));
+    CU_CHECK(launch_fused(p, maps, grid, stream));
+    c->launches++;
+    // levels beyond the fused epilogue: stand-alone K2 chain
+    for (int l = in_kernel; l < levels; ++l) {
+        CU_CHECK(launch_pyr_down(d_out_levels[l - 1], c->out_w >> (l - 1), c->out_h >> (l - 1), d_out_levels[l], n_frames, stream));
+        c->launches++;
+    }
+    return MDC_OK;
+}
+
+int finish(mdc_ctx* c, mdc_stream user_stream, cudaStream_t s) {
+    if (!user_stream) CU_CHECK(cudaStreamSynchronize(s));
+    (void)c;
+    return MDC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ context
+extern "C" int mdc_ctx_create(int device, const mdc_fov* fov, const mdc_photo* photo, mdc_ctx** out) {
+    if (!out) { mdc_set_error("mdc_ctx_create: out is NULL"); return MDC_ERR_INVALID_ARG; }
+    *out = nullptr;
+    mdc_ctx* c = new mdc_ctx();
+    int rc = ctx_common_init(c, device);
+    if (rc != MDC_OK) { delete c; return rc; }
+    c->have_fov = fov && fov->valid;
+    if (fov && fov->dims_known) { c->in_w = fov->in_w; c->in_h = fov->in_h; }
+    if (c->have_fov) { c->out_w = fov->out_w; c->out_h = fov->out_h; }
+    if (photo && (photo->valid_gamma || photo->valid_vignette)) {
+        if (c->in_w == 0) { c->in_w = photo->w; c->in_h = photo->h; }
+        if (photo->w != c->in_w || photo->h != c->in_h) {
+            mdc_set_error("photometric model is %d x %d but the rectifier input is %d x %d", photo->w, photo->h, c->in_w, c->in_h);
+            mdc_ctx_destroy(c);
+            return MDC_ERR_INVALID_ARG;
+        }
+    } else if (photo && c->in_w == 0) { c->in_w = photo->w; c->in_h = photo->h; }
+    c->have_gamma = photo && photo->valid_gamma;
+    c->have_vig = photo && photo->valid_vignette;
+    auto fail = [&](int code) { mdc_ctx_destroy(c); return code; };
+#define CTX_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { mdc_set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); return fail(MDC_ERR_CUDA); } } while (0)
+    if (c->have_fov) {
+        const size_t nb = static_cast<size_t>(c->out_w) * c->out_h * sizeof(float);
+        CTX_CHECK(cudaMalloc(&c->d_rx, nb));
+        CTX_CHECK(cudaMalloc(&c->d_ry, nb));
+        CTX_CHECK(cudaMemcpy(c->d_rx, fov->remap_x.data(), nb, cudaMemcpyHostToDevice));
+        CTX_CHECK(cudaMemcpy(c->d_ry, fov->remap_y.data(), nb, cudaMemcpyHostToDevice));
+        build_plan(c, fov->remap_x.data(), fov->remap_y.data());
+        if ((rc = upload_plan(c)) != MDC_OK) return fail(rc);
+    }
+    if (c->have_gamma) {
+        CTX_CHECK(cudaMalloc(&c->d_ginv, 256 * sizeof(float)));
+        CTX_CHECK(cudaMemcpy(c->d_ginv, photo->GInv, 256 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (c->have_vig) {
+        const size_t nb = static_cast<size_t>(c->in_w) * c->in_h * sizeof(float);
+        CTX_CHECK(cudaMalloc(&c->d_vinv, nb));
+        CTX_CHECK(cudaMemcpy(c->d_vinv, photo->vinv.data(), nb, cudaMemcpyHostToDevice));
+    }
+#undef CTX_CHECK
+    *out = c;
+    return MDC_OK;
+}
+
+extern "C" int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h, int out_w, int out_h,
+                                                 const float* d_remap_x, const float* d_remap_y,
+                                                 const float* d_ginv256, const float* d_vinv, mdc_ctx** out) {
+    if (!out) { mdc_set_error("mdc_ctx_create_from_device_tables: out is NULL"); return MDC_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (in_w < 2 || in_h < 2) { mdc_set_error("bad input size"); return MDC_ERR_INVALID_ARG; }
+    if ((d_remap_x == nullptr) != (d_remap_y == nullptr)) { mdc_set_error("remap tables must come as a pair"); return MDC_ERR_INVALID_ARG; }
+    mdc_ctx* c = new mdc_ctx();
+    int rc = ctx_common_init(c, device);
+    if (rc != MDC_OK) { delete c; return rc; }
+    c->owns_tables = false;
+    c->in_w = in_w; c->in_h = in_h;
+    c->have_fov = d_remap_x != nullptr;
+    c->have_gamma = d_ginv256 != nullptr;
+    c->have_vig = d_vinv != nullptr;
+    c->d_rx = const_cast<float*>(d_remap_x); c->d_ry = const_cast<float*>(d_remap_y);
+    c->d_ginv = const_cast<float*>(d_ginv256); c->d_vinv = const_cast<float*>(d_vinv);
+    if (c->have_fov) {
+        if (out_w < 1 || out_h < 1) { mdc_set_error("bad output size"); mdc_ctx_destroy(c); return MDC_ERR_INVALID_ARG; }
+        c->out_w = out_w; c->out_h = out_h;
+        const size_t n = static_cast<size_t>(out_w) * out_h;
+        std::vector<float> hx(n), hy(n);
+        cudaError_t e = cudaMemcpy(hx.data(), d_remap_x, n * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hy.data(), d_remap_y, n * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { mdc_set_error("reading back remap tables failed: %s", cudaGetErrorString(e)); mdc_ctx_destroy(c); return MDC_ERR_CUDA; }
+        build_plan(c, hx.data(), hy.data());
+        if ((rc = upload_plan(c)) != MDC_OK) { mdc_ctx_destroy(c); return rc; }
+    }
+    *out = c;
+    return MDC_OK;
+}
+
+extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->owns_tables) { cudaFree(c->d_rx); cudaFree(c->d_ry); cudaFree(c->d_ginv); cudaFree(c->d_vinv); }
+    cudaFree(c->d_tiles); cudaFree(c->d_cost_prefix);
+    for (int s = 0; s < kMapSlots; ++s) free(c->maps[s]);
+    for (int s = 0; s < kHostPipeDepth; ++s) {
+        if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }
+        cudaFree(c->pipe_in[s]); cudaFree(c->pipe_out[s]);
+    }
+    cudaFree(c->scratch_a); cudaFree(c->scratch_b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int mdc_ctx_device_tables(const mdc_ctx* c, const float** rx, const float** ry, const float** ginv, const float** vinv) {
+    if (!c) return MDC_ERR_INVALID_ARG;
+    if (rx) *rx = c->d_rx;
+    if (ry) *ry = c->d_ry;
+    if (ginv) *ginv = c->d_ginv;
+    if (vinv) *vinv = c->d_vinv;
+    return MDC_OK;
+}
+
+extern "C" int mdc_ctx_level_dims(const mdc_ctx* c, int level, int* w, int* h) {
+    if (!c || level < 0 || level >= MDC_MAX_PYR_LEVELS) return MDC_ERR_INVALID_ARG;
+    if (w) *w = c->out_w >> level;
+    if (h) *h = c->out_h >> level;
+    return MDC_OK;
+}
+
+extern "C" long long mdc_ctx_launch_count(const mdc_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm) {
+    if (!c) return MDC_ERR_INVALID_ARG;
+    c->use_tma = use_tma;
+    c->ctas_per_sm = ctas_per_sm;
+    return MDC_OK;
+}
+
+// --------------------------------------------------------------- device-resident operators
+extern "C" int mdc_unmap_u8(mdc_ctx* c, const uint8_t* d_in, float* d_out, int n, int n_frames, unsigned flags, mdc_stream stream) {
+    if (!c || !d_in || !d_out || n < 0 || n_frames < 0) { mdc_set_error("mdc_unmap_u8: bad argument"); return MDC_ERR_INVALID_ARG; }
+    if (n != c->in_w * c->in_h) {   // the reference only asserts this (compiled out); refuse instead of reading the vignette out of bounds
+        mdc_set_error("unMapImage: expected %d pixels, got %d", c->in_w * c->in_h, n);
+        return MDC_ERR_INVALID_ARG;
+    }
+    CU_CHECK(cudaSetDevice(c->device));
+    const UnmapFlags u = sanitise(c, flags);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_unmap(d_in, d_out, static_cast<size_t>(n), n_frames, u.gamma ? c->d_ginv : nullptr, u.vig ? c->d_vinv : nullptr, u.kill, s));
+    c->launches++;
+    return finish(c, stream, s);
+}
+
+static int check_undistort_args(mdc_ctx* c, const void* in, const void* out, int n_pix_in, int n_pix_out, int n_frames) {
+    if (!c || !in || !out || n_frames < 0) { mdc_set_error("undistort: bad argument"); return MDC_ERR_INVALID_ARG; }
+    if (!c->have_fov) { mdc_set_error("undistort on an invalid rectifier"); return MDC_ERR_INVALID_OBJECT; }
+    if (n_pix_in != c->in_w * c->in_h) {
+        printf("ERROR: undistort called with wrong input image dismesions (expected %d pixel, got %d pixel)\n", c->in_w * c->in_h, n_pix_in);
+        mdc_set_error("undistort: expected %d input pixels, got %d", c->in_w * c->in_h, n_pix_in);
+        return MDC_ERR_INVALID_ARG;
+    }
+    if (n_pix_out != c->out_w * c->out_h) {
+        printf("ERROR: undistort called with wrong output image dismesions (expected %d pixel, got %d pixel)\n", c->out_w * c->out_h, n_pix_out);
+        mdc_set_error("undistort: expected %d output pixels, got %d", c->out_w * c->out_h, n_pix_out);
+        return MDC_ERR_INVALID_ARG;
+    }
+    return MDC_OK;
+}
+
+extern "C" int mdc_undistort_u8(mdc_ctx* c, const uint8_t* d_in, float* d_out, int n_pix_in, int n_pix_out, int n_frames, mdc_stream stream) {
+    int rc = check_undistort_args(c, d_in, d_out, n_pix_in, n_pix_out, n_frames);
+    if (rc != MDC_OK) return rc;
+    if (n_frames == 0) return MDC_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    float* lv[1] = {d_out};
+    rc = run_fused(c, d_in, n_frames, UnmapFlags{false, false, false}, lv, 1, s);
+    if (rc != MDC_OK) return rc;
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_undistort_f32(mdc_ctx* c, const float* d_in, float* d_out, int n_pix_in, int n_pix_out, int n_frames, mdc_stream stream) {
+    int rc = check_undistort_args(c, d_in, d_out, n_pix_in, n_pix_out, n_frames);
+    if (rc != MDC_OK) return rc;
+    if (n_frames == 0) return MDC_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_undistort_f32(d_in, d_out, c->in_w, n_pix_in, n_pix_out, n_frames, c->d_rx, c->d_ry, s));
+    c->launches++;
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_dst, int n_frames, mdc_stream stream) {
+    if (!c || !d_src || !d_dst || src_w < 0 || src_h < 0 || n_frames < 0) { mdc_set_error("mdc_pyr_down: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_pyr_down(d_src, src_w, src_h, d_dst, n_frames, s));
+    c->launches++;
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_frames, unsigned flags,
+                                 float* const* d_out_levels, int levels, mdc_stream stream) {
+    if (!c || !d_frames || !d_out_levels || n_frames < 0 || levels < 1 || levels > MDC_MAX_PYR_LEVELS) {
+        mdc_set_error("mdc_prepare_batch: bad argument");
+        return MDC_ERR_INVALID_ARG;
+    }
+    for (int l = 0; l < levels; ++l)
+        if (!d_out_levels[l]) { mdc_set_error("mdc_prepare_batch: output level %d is NULL", l); return MDC_ERR_INVALID_ARG; }
+    if (c->in_w < 1) { mdc_set_error("mdc_prepare_batch: context has no image geometry"); return MDC_ERR_INVALID_OBJECT; }
+    const bool rectify = (flags & MDC_RECTIFY) != 0;
+    if (rectify && !c->have_fov) { mdc_set_error("getImage(rectify) on an invalid rectifier"); return MDC_ERR_INVALID_OBJECT; }
+    if (n_frames == 0) return MDC_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    // mode switch of DatasetReader::getImage, BenchmarkDatasetReader.h:210-241
+    const bool photometric = (flags & (MDC_REMOVE_GAMMA | MDC_REMOVE_VIGNETTE | MDC_NAN_OVEREXPOSED)) != 0;
+    UnmapFlags u{false, false, false};
+    if (photometric) u = sanitise(c, flags);
+    if (rectify) {
+        int rc = run_fused(c, d_frames, n_frames, u, d_out_levels, levels, s);
+        if (rc != MDC_OK) return rc;
+    } else {
+        const size_t n = static_cast<size_t>(c->in_w) * c->in_h;
+        CU_CHECK(launch_unmap(d_frames, d_out_levels[0], n, n_frames, u.gamma ? c->d_ginv : nullptr, u.vig ? c->d_vinv : nullptr, u.kill, s));
+        c->launches++;
+        for (int l = 1; l < levels; ++l) {
+            CU_CHECK(launch_pyr_down(d_out_levels[l - 1], c->in_w >> (l - 1), c->in_h >> (l - 1), d_out_levels[l], n_frames, s));
+            c->launches++;
+        }
+    }
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, double* d_E, mdc_stream stream) {
+    if (!c || !d_data || !d_t || !d_G || !d_E || n < 0 || npix < 0) { mdc_set_error("mdc_estep: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_estep(d_data, n, npix, d_t, d_G, d_E, s));
+    c->launches++;
+    return finish(c, stream, s);
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+extern "C" int mdc_host_alloc(void** p, size_t bytes) {
+    if (!p) return MDC_ERR_INVALID_ARG;
+    CU_CHECK(cudaMallocHost(p, bytes));
+    return MDC_OK;
+}
+extern "C" void mdc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int mdc_unmap_u8_host(mdc_ctx* c, const uint8_t* in, float* out, int n, unsigned flags) {
+    if (!c || !in || !out) { mdc_set_error("mdc_unmap_u8_host: bad argument"); return MDC_ERR_INVALID_ARG; }
+    if (n != c->in_w * c->in_h) { mdc_set_error("unMapImage: expected %d pixels, got %d", c->in_w * c->in_h, n); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_bytes(&c->scratch_a, &c->scratch_a_bytes, static_cast<size_t>(n))) != MDC_OK) return rc;
+    if ((rc = ensure_bytes(&c->scratch_b, &c->scratch_b_bytes, static_cast<size_t>(n) * 4)) != MDC_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(c->scratch_a, in, static_cast<size_t>(n), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = mdc_unmap_u8(c, static_cast<const uint8_t*>(c->scratch_a), static_cast<float*>(c->scratch_b), n, 1, flags, c->stream)) != MDC_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(out, c->scratch_b, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return MDC_OK;
+}
+
+template <typename T>
+static int undistort_host(mdc_ctx* c, const T* in, float* out, int n_pix_in, int n_pix_out) {
+    int rc = check_undistort_args(c, in, out, n_pix_in, n_pix_out, 1);
+    if (rc != MDC_OK) return rc;
+    CU_CHECK(cudaSetDevice(c->device));
+    if ((rc = ensure_bytes(&c->scratch_a, &c->scratch_a_bytes, static_cast<size_t>(n_pix_in) * sizeof(T))) != MDC_OK) return rc;
+    if ((rc = ensure_bytes(&c->scratch_b, &c->scratch_b_bytes, static_cast<size_t>(n_pix_out) * 4)) != MDC_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(c->scratch_a, in, static_cast<size_t>(n_pix_in) * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    if (sizeof(T) == 1) rc = mdc_undistort_u8(c, static_cast<const uint8_t*>(c->scratch_a), static_cast<float*>(c->scratch_b), n_pix_in, n_pix_out, 1, c->stream);
+    else rc = mdc_undistort_f32(c, static_cast<const float*>(c->scratch_a), static_cast<float*>(c->scratch_b), n_pix_in, n_pix_out, 1, c->stream);
+    if (rc != MDC_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(out, c->scratch_b, static_cast<size_t>(n_pix_out) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return MDC_OK;
+}
+extern "C" int mdc_undistort_u8_host(mdc_ctx* c, const uint8_t* in, float* out, int n_pix_in, int n_pix_out) {
+    return undistort_host<uint8_t>(c, in, out, n_pix_in, n_pix_out);
+}
+extern "C" int mdc_undistort_f32_host(mdc_ctx* c, const float* in, float* out, int n_pix_in, int n_pix_out) {
+    return undistort_host<float>(c, in, out, n_pix_in, n_pix_out);
+}
+
+extern "C" int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_frames, unsigned flags,
+                                      float* const* out_levels, int levels) {
+    if (!c || !frames || !out_levels || n_frames < 0 || levels < 1 || levels > MDC_MAX_PYR_LEVELS) {
+        mdc_set_error("mdc_prepare_batch_host: bad argument");
+        return MDC_ERR_INVALID_ARG;
+    }
+    if (c->in_w < 1) { mdc_set_error("mdc_prepare_batch_host: context has no image geometry"); return MDC_ERR_INVALID_OBJECT; }
+    const bool rectify = (flags & MDC_RECTIFY) != 0;
+    if (rectify && !c->have_fov) { mdc_set_error("getImage(rectify) on an invalid rectifier"); return MDC_ERR_INVALID_OBJECT; }
+    if (n_frames == 0) return MDC_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    const size_t n_in = static_cast<size_t>(c->in_w) * c->in_h;
+    const int w0 = rectify ? c->out_w : c->in_w, h0 = rectify ? c->out_h : c->in_h;
+    size_t lvl_px[MDC_MAX_PYR_LEVELS], px_per_frame = 0;
+    for (int l = 0; l < levels; ++l) { lvl_px[l] = static_cast<size_t>(w0 >> l) * (h0 >> l); px_per_frame += lvl_px[l]; }
+    // chunking: enough frames per kernel to fill the machine, small enough to overlap copy and compute
+    const char* e = getenv("MDC_HOST_CHUNK");
+    int chunk = e ? atoi(e) : 16;
+    chunk = std::max(1, std::min(chunk, n_frames));
+    const size_t in_bytes = static_cast<size_t>(chunk) * n_in, out_bytes = static_cast<size_t>(chunk) * px_per_frame * 4;
+    if (c->pipe_in_bytes < in_bytes || c->pipe_out_bytes < out_bytes) {
+        for (int s = 0; s < kHostPipeDepth; ++s) {
+            if (c->pipe_stream[s]) cudaStreamSynchronize(c->pipe_stream[s]);
+            cudaFree(c->pipe_in[s]); cudaFree(c->pipe_out[s]);
+            c->pipe_in[s] = nullptr; c->pipe_out[s] = nullptr;
+        }
+        c->pipe_in_bytes = c->pipe_out_bytes = 0;
+        for (int s = 0; s < kHostPipeDepth; ++s) {
+            if (!c->pipe_stream[s]) CU_CHECK(cudaStreamCreateWithFlags(&c->pipe_stream[s], cudaStreamNonBlocking));
+            CU_CHECK(cudaMalloc(&c->pipe_in[s], in_bytes));
+            CU_CHECK(cudaMalloc(&c->pipe_out[s], out_bytes));
+        }
+        c->pipe_in_bytes = in_bytes; c->pipe_out_bytes = out_bytes;
+    }
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
+        const int nf = std::min(chunk, n_frames - f0);
+        const int s = k % kHostPipeDepth;
+        cudaStream_t st = c->pipe_stream[s];
+        CU_CHECK(cudaMemcpyAsync(c->pipe_in[s], frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(nf) * n_in, cudaMemcpyHostToDevice, st));
+        float* lv[MDC_MAX_PYR_LEVELS];
+        size_t off = 0;
+        for (int l = 0; l < levels; ++l) { lv[l] = c->pipe_out[s] + off; off += static_cast<size_t>(nf) * lvl_px[l]; }
+        int rc = mdc_prepare_batch(c, c->pipe_in[s], nf, flags, lv, levels, st);
+        if (rc != MDC_OK) return rc;
+        for (int l = 0; l < levels; ++l)
+            CU_CHECK(cudaMemcpyAsync(out_levels[l] + static_cast<size_t>(f0) * lvl_px[l], lv[l], static_cast<size_t>(nf) * lvl_px[l] * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kHostPipeDepth; ++s)
+        if (c->pipe_stream[s]) CU_CHECK(cudaStreamSynchronize(c->pipe_stream[s]));
+    return MDC_OK;
+}

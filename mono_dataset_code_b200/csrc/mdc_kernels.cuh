@@ -1,0 +1,67 @@
+// Device-side data structures and launch wrappers shared between mdc_kernels.cu and
+// mdc_capi.cu.  sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdc_b200.h"
+
+namespace mdc {
+
+constexpr int kTile = 32;            // output tile edge (pixels); pyramid levels 0..4 close inside a tile
+constexpr int kThreads = 256;        // 16 x 16 threads, each owning a 2x2 block of output pixels
+constexpr int kInKernelLevels = 5;   // levels 0..4 are produced by the fused kernel's epilogue
+constexpr int kMaxBoxWordsPerThread = 8;   // LDG loader: u32 words of the input box prefetched per thread
+constexpr int kMaxBoxPx = kMaxBoxWordsPerThread * 4 * kThreads;  // 8192 px: larger boxes use the direct path
+constexpr int kStages = 2;           // TMA loader: u8 box stages in flight
+constexpr int kMaxClasses = 48;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
+
+// How a tile's input pixels are fetched.
+enum TileMode : int { TILE_EMPTY = 0, TILE_STAGED = 1, TILE_DIRECT = 2 };
+
+// One output tile of the rectification plan (built once per context from the remap tables).
+struct alignas(16) TileDesc {
+    int x0, y0;        // origin of the input bounding box (x0 is a multiple of 16)
+    int bw_bh;         // box width (multiple of 16, also the smem pitch) | box height << 16
+    int mode_map;      // TileMode | (tensor-map class index << 8) | (TMA box height << 16)
+};
+
+// TMA descriptors of one launch: one 3-D u8 tensor map per box class, passed by value as a
+// __grid_constant__ kernel parameter (no device-memory copy, no lifetime to manage).
+struct TmaMaps {
+    alignas(64) CUtensorMap m[kMaxClasses];
+};
+
+struct FusedParams {
+    const uint8_t* frames;       // [n_frames][in_w*in_h]
+    int n_frames;
+    int in_w, in_h, out_w, out_h;
+    const float* remap_x;        // [out_w*out_h]
+    const float* remap_y;
+    const float* vinv;           // [in_w*in_h] or nullptr
+    const float* ginv;           // [256] or nullptr
+    const TileDesc* tiles;       // [tiles_x*tiles_y]
+    const uint32_t* tile_cost_prefix;  // [n_tiles+1] exclusive prefix sum of per-frame tile costs
+    int tiles_x, n_tiles;
+    float* out[MDC_MAX_PYR_LEVELS];
+    int lw[MDC_MAX_PYR_LEVELS], lh[MDC_MAX_PYR_LEVELS];
+    int levels;                  // 1..kInKernelLevels
+    unsigned lut_gamma, use_vig, kill;   // sanitised unMapImage flags
+    int box_px_max;              // largest staged box (pixels) -> smem carve-up
+    int vec2_ok;                 // level-0 rows can be written with 8-byte stores
+};
+
+size_t fused_smem_bytes(int box_px_max, bool tma);
+cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, cudaStream_t stream);  // maps == nullptr: LDG loader
+int fused_max_ctas_per_sm(int box_px_max, bool tma);
+
+cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, const float* ginv, const float* vinv,
+                         unsigned kill, cudaStream_t stream);
+cudaError_t launch_undistort_f32(const float* in, float* out, int in_w, int n_in, int n_out, int n_frames,
+                                 const float* remap_x, const float* remap_y, cudaStream_t stream);
+cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_frames, cudaStream_t stream);
+cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E,
+                         cudaStream_t stream);
+
+}  // namespace mdc

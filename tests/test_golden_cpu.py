@@ -1,0 +1,65 @@
+"""CPU: the C restatement (oracle/port) and the product's HOST table builders against the
+committed golden fixtures, which were produced by the reference's own code
+(tests/golden/make_golden.py).  Runs without /root/reference and without a GPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+from mono_dataset_code_b200 import api
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load_case(path, tmp_path):
+    g = np.load(path)
+    cam, pc = tmp_path / "camera.txt", tmp_path / "pcalib.txt"
+    cam.write_bytes(g["camera_txt"].tobytes())
+    pc.write_bytes(g["pcalib_txt"].tobytes())
+    return g, str(cam), str(pc)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_port_matches_golden(path, port, tmp_path):
+    g, cam, pc = load_case(path, tmp_path)
+    iw, ih, ow, oh = [int(v) for v in g["dims"]]
+    f = port.fov_from_file(cam)
+    rx, ry = f.tables()
+    assert_bits_equal(rx, g["remap_x"], "remapX")
+    assert_bits_equal(ry, g["remap_y"], "remapY")
+    assert_bits_equal(f.K()[0], g["k_rect"], "Krect")
+    assert_bits_equal(f.K()[1], g["k_org"], "Korg")
+    ginv, gf = port.photo_tables(np.loadtxt(pc, dtype=np.float32))
+    assert_bits_equal(ginv, g["ginv"], "GInv")
+    _, vinv = port.vignette_maps(g["vignette_pixels"])
+    assert_bits_equal(vinv.reshape(-1), g["vinv"], "vignetteMapInv")
+    for flags in range(16):
+        rectify, gm, v, k = flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, (flags >> 3) & 1
+        for i, fr in enumerate(g["frames"]):
+            out = port.get_image(rx, ry, iw, ih, ginv, vinv.reshape(-1), fr, rectify, gm, v, k)
+            assert_bits_equal(out, g[f"out_{flags:02d}"][i], f"getImage flags={flags} frame={i}")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_product_host_models_match_golden(path, tmp_path):
+    """Product host code (csrc/mdc_host_models.cpp, csrc/mdc_gray_image.cpp): tables bit-identical."""
+    from mono_dataset_code_b200 import synthetic as S
+    g, cam, pc = load_case(path, tmp_path)
+    iw, ih, ow, oh = [int(v) for v in g["dims"]]
+    u = api.UndistorterFOV(cam)
+    assert u.isValid() and u.getInputDims() == (iw, ih) and u.getOutputDims() == (ow, oh)
+    rx, ry = u.remap_tables()
+    assert_bits_equal(rx, g["remap_x"], "remapX")
+    assert_bits_equal(ry, g["remap_y"], "remapY")
+    assert_bits_equal(u.getK_rect(), g["k_rect"], "Krect")
+    assert_bits_equal(u.getK_org(), g["k_org"], "Korg")
+    vig = tmp_path / "vignette.png"
+    S.write_png_gray(str(vig), g["vignette_pixels"])
+    p = api.PhotometricUndistorter(pc, str(vig), iw, ih)
+    assert p.validGamma and p.validVignette
+    assert_bits_equal(p.getGInv(), g["ginv"], "GInv")
+    defined = g["g"] == g["g"]
+    assert_bits_equal(p.getG()[[0, 255]], g["g"][[0, 255]], "G ends")
+    assert_bits_equal(p.vignette_maps()[1], g["vinv"], "vignetteMapInv")
