@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the per-frame image-preparation hot path (BASELINE.json metric).
+
+Step   = one pass of the fused kernel K1 (photometric un-map + FOV rectification) over one batch
+         of BATCH synthetic 1280x1024 mono8 frames per GPU (BASELINE.json configs[1]; the batch
+         size and the 5-level pyramid of configs[2] are reported as the `c3_pyramid` extra).
+value  = whole-job frames/s with the batch already resident in HBM (CUDA events, max over ranks).
+e2e    = the same metric through the host-buffer C-ABI call (pinned host frames in, float images
+         out; H2D + kernel + D2H inside the timed region).
+roofline = algorithmic bytes of one K1 launch / its CUDA-event duration, vs MEASURED_PEAKS.json.
+cpu_baseline = the reference's own CPU code (oracle/_ref, compiled from /root/reference) — or the
+         C restatement when that is absent — timed on this box's host cores on a bounded sample.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                            (CPU reference arm)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IN_W, IN_H, OUT_W, OUT_H = 1280, 1024, 1280, 1024
+ALG_BYTES_PER_FRAME = IN_W * IN_H * 1 + OUT_W * OUT_H * 4                    # 6 553 600
+PYR_EXTRA_BYTES = sum((OUT_W >> l) * (OUT_H >> l) * 4 for l in range(1, 5))    # 1 740 800
+FLAGS_ALL = 1 | 2 | 4        # rectify + removeGamma + removeVignette (the reference viewer's full correction)
+FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def write_calibration(tmp):
+    from mono_dataset_code_b200 import synthetic as S
+    return S.write_dataset_dir(tmp, IN_W, IN_H, OUT_W, OUT_H, "crop")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_reference_setup(files):
+    """(kind, run(n_frames, threads) -> seconds, cores).  Prefers the reference's own compiled code."""
+    from oracle import loader
+    from mono_dataset_code_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    frames = S.frames(16, IN_W, IN_H)
+    if loader.ref_available():
+        R = loader.RefOracle()
+        R.register_image(files["vignette"], files["vignette_pixels"])
+        fov = R.fov(files["camera"])
+        photo = R.photo(files["pcalib"], files["vignette"], IN_W, IN_H)
+        assert fov.valid and photo.valid_vignette
+
+        def run(n_frames, threads):
+            return R.time_frames(fov, photo, frames, n_frames, threads, (1, 1, 0))
+        return "reference", run, cores
+    P = loader.PortOracle()
+    f = P.fov_from_file(files["camera"])
+    rx, ry = f.tables()
+    ginv, _ = P.photo_tables(np.loadtxt(files["pcalib"], dtype=np.float32))
+    _, vinv = P.vignette_maps(files["vignette_pixels"])
+
+    def run(n_frames, threads):
+        return P.time_frames(rx, ry, IN_W, IN_H, OUT_W, OUT_H, ginv, vinv.reshape(-1), frames, n_frames, threads, 3, 1), np.zeros(2)
+    return "port", run, cores
+
+
+def cpu_baseline(files):
+    kind, run, cores = cpu_reference_setup(files)
+    run(8, 1)                                   # warm caches / page in
+    n1 = 150
+    s1, stages = run(n1, 1)
+    nP = max(cores * 48, 256)
+    sP, _ = run(nP, cores)
+    return {"value": nP / sP, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": f"{nP} frames of 1280x1024 (16 distinct, cycled) over {cores} threads; unMapImage+undistort<float>, decode/alloc excluded",
+            "single_thread": {"value": n1 / s1, "frames": n1, "unmap_ms": 1e3 * stages[0] / n1, "undistort_ms": 1e3 * stages[1] / n1}}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tmp = tempfile.mkdtemp(prefix="mdc_bench_")
+    files = write_calibration(tmp)
+    kind, run, cores = cpu_reference_setup(files)
+    per_step = max(cores * 8, 64)
+    for _ in range(args.warmup):
+        run(max(cores, 16), cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(per_step, cores)
+    dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": "frames_per_s_1280x1024_photometric_fov_undistort", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "1280x1024 mono8 -> 1280x1024 f32, GInv LUT * vignette + FOV crop remap (BASELINE configs[1])",
+                       "frames_per_step": per_step, "threads": cores},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": f"{per_step} frames/step x {args.steps} steps over {cores} threads"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from mono_dataset_code_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- calibration: rank 0 parses/builds on the host, tables are broadcast over NCCL, every rank adopts them
+    tmp = tempfile.mkdtemp(prefix="mdc_bench_")
+    files = write_calibration(tmp) if rank == 0 else None
+    n_in, n_out = IN_W * IN_H, OUT_W * OUT_H
+    if world == 1:
+        fov = api.UndistorterFOV(files["camera"])
+        photo = api.PhotometricUndistorter(files["pcalib"], files["vignette"], IN_W, IN_H)
+        ctx = api.Context(fov, photo, local)
+    else:
+        t_rx = torch.empty(n_out, dtype=torch.float32, device=dev)
+        t_ry = torch.empty(n_out, dtype=torch.float32, device=dev)
+        t_g = torch.empty(256, dtype=torch.float32, device=dev)
+        t_v = torch.empty(n_in, dtype=torch.float32, device=dev)
+        if rank == 0:
+            fov = api.UndistorterFOV(files["camera"])
+            photo = api.PhotometricUndistorter(files["pcalib"], files["vignette"], IN_W, IN_H)
+            rx, ry = fov.remap_tables()
+            t_rx.copy_(torch.from_numpy(rx)); t_ry.copy_(torch.from_numpy(ry))
+            t_g.copy_(torch.from_numpy(photo.getGInv())); t_v.copy_(torch.from_numpy(photo.vignette_maps()[1]))
+        for t in (t_rx, t_ry, t_g, t_v):
+            dist.broadcast(t, src=0)          # one-time; no collective in steady state
+        torch.cuda.synchronize()
+        ctx = api.Context.from_device_tables(local, IN_W, IN_H, OUT_W, OUT_H, t_rx, t_ry, t_g, t_v)
+    if args.tma is not None:
+        ctx.configure(use_tma=args.tma)
+
+    B = args.batch
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    frames = torch.randint(0, 256, (B, n_in), dtype=torch.uint8, device=dev, generator=g)
+    lvl_px = [(OUT_W >> l) * (OUT_H >> l) for l in range(5)]
+    outs = [torch.empty((B, px), dtype=torch.float32, device=dev) for px in lvl_px]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(levels, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            ctx.prepare_batch(frames, FLAGS_ALL, outs[:levels])
+        barrier()
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        t_all0.record()
+        for a, b in ev:
+            a.record()
+            ctx.prepare_batch(frames, FLAGS_ALL, outs[:levels])
+            b.record()
+        t_all1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = t_all0.elapsed_time(t_all1)
+        per_launch_ms = [a.elapsed_time(b) for a, b in ev]
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, per_launch_ms, ctx.launch_count - l0, clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms, per_launch_ms, launches, clocks = timed(1, args.steps, args.warmup, sampler)
+    value = world * B * args.steps / (total_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    k1_ms = float(np.mean(per_launch_ms))
+    achieved = B * ALG_BYTES_PER_FRAME / (k1_ms * 1e-3) / 1e9
+
+    # configs[2]: + 5-level pyramid fused in the same kernel's epilogue
+    p_total_ms, p_launch_ms, _, _ = timed(5, max(2, args.steps // 2), 2)
+    p_steps = max(2, args.steps // 2)
+    pyr = {"value": world * B * p_steps / (p_total_ms * 1e-3), "unit": "frames/s", "levels": 5,
+           "achieved_gbs": B * (ALG_BYTES_PER_FRAME + PYR_EXTRA_BYTES) / (float(np.mean(p_launch_ms)) * 1e-3) / 1e9}
+
+    # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)
+    EB = args.e2e_batch
+    import ctypes as C
+    from mono_dataset_code_b200 import _lib
+    h_in, h_out = C.c_void_p(), C.c_void_p()
+    _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_in), EB * n_in), "mdc_host_alloc")
+    _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_out), EB * n_out * 4), "mdc_host_alloc")
+    np_in = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_ubyte)), (EB, n_in))
+    np_in[:] = np.random.default_rng(1000 + rank).integers(0, 256, (EB, n_in), dtype=np.uint8)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.prepare_batch_host(np_in, FLAGS_ALL, [h_out.value])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.prepare_batch_host(np_in, FLAGS_ALL, [h_out.value])      # synchronous: returns after the D2H copy
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * EB * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": EB * n_in,
+           "d2h_bytes_per_step": EB * n_out * 4, "frames_per_step": EB, "steps": e2e_steps}
+    _lib.lib.mdc_host_free(h_in); _lib.lib.mdc_host_free(h_out)
+
+    if rank == 0:
+        line = {"metric": "frames_per_s_1280x1024_photometric_fov_undistort", "value": value, "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (uniform random mono8 frames, synthetic TUM-style calibration; SURVEY.md §8d)",
+                "config": {"workload": "1280x1024 mono8 -> 1280x1024 f32: GInv[I]*vignetteInv + FOV crop remap, fused K1 (BASELINE configs[1])",
+                           "frames_per_step_per_gpu": B, "flags": "rectify|removeGamma|removeVignette", "pyramid_levels": 1,
+                           "parallelism": f"frame-sharded dp{world}, tables NCCL-broadcast at init, no steady-state collective",
+                           "l2_policy": f"inputs larger than L2 ({B * n_in >> 20} MiB in, {B * n_out * 4 >> 20} MiB out per step)",
+                           "loader": {None: "auto(tma)", 1: "tma", 0: "ldg"}[args.tma]},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "fused_prepare_kernel",
+                             "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_FRAME, "launch_ms": k1_ms},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(files)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU (device-resident)")
+    ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
+    ap.add_argument("--tma", type=int, default=None, help="force the input loader: 1 = TMA, 0 = LDG")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

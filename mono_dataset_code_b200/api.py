@@ -287,10 +287,7 @@ class Context:
         """frames / out_levels: numpy arrays or raw integer addresses of (pinned) host memory."""
         def addr(x):
             return x if isinstance(x, int) else x.ctypes.data
-        n = frames.shape[0] if hasattr(frames, "shape") else None
-        raise_if = n is None
-        if raise_if:
-            raise ValueError("frames must be an array")
+        n = frames.shape[0]
         arr = (C.c_void_p * len(out_levels))(*[addr(t) for t in out_levels])
         check(lib.mdc_prepare_batch_host(self._h, C.c_void_p(addr(frames)), n, flags, arr, len(out_levels)), "mdc_prepare_batch_host")
 

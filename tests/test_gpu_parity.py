@@ -1,0 +1,234 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the
+plain-C oracle on the same seeded inputs and against the committed golden fixtures.
+
+Bar: BIT-EXACT floats (NaN positions identical, payloads ignored) — stronger than the 1e-4
+relative tolerance BASELINE.json asks for; TOL_REL documents that contract anyway."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CALIBS, BIG_CALIBS, assert_bits_equal
+from mono_dataset_code_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+TOL_REL = 1e-4   # north_star tolerance; the assertions below are exact, so it is never exceeded
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mono_dataset_code_b200 import api as a
+    return a
+
+
+def make_models(api, files, iw, ih):
+    u = api.UndistorterFOV(files["camera"])
+    p = api.PhotometricUndistorter(files["pcalib"], files["vignette"], iw, ih)
+    assert u.isValid() and p.validGamma and p.validVignette
+    return u, p
+
+
+def oracle_tables(port, files):
+    f = port.fov_from_file(files["camera"])
+    rx, ry = f.tables()
+    ginv, _ = port.photo_tables(np.loadtxt(files["pcalib"], dtype=np.float32))
+    _, vinv = port.vignette_maps(files["vignette_pixels"])
+    return rx, ry, ginv, vinv.reshape(-1)
+
+
+def mixed_frames(n, w, h):
+    kinds = ["uniform", "speckle", "gradient", "white", "black"]
+    return np.stack([S.frame(i, w, h, kinds[i % len(kinds)]) for i in range(n)])
+
+
+@pytest.mark.parametrize("name", list(CALIBS))
+@pytest.mark.parametrize("loader", ["tma", "ldg"])
+def test_get_image_all_flag_combinations(name, loader, api, port, dataset_dir):
+    iw, ih, ow, oh, mode, calib = CALIBS[name]
+    files = dataset_dir(name, vignette_zeros=(name in ("odd_sizes", "c1_crop_640")))
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    if loader == "tma" and iw % 16 != 0:
+        pytest.skip("TMA needs a 16-byte row pitch; the LDG loader covers this width")
+    prep.ctx.configure(use_tma=1 if loader == "tma" else 0)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(7, iw, ih)
+    d_frames = torch.from_numpy(frames).cuda()
+    for flags in range(16):
+        rectify, g, v, k = flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, (flags >> 3) & 1
+        out = prep.prepare_device(d_frames, rectify, g, v, k)[0].cpu().numpy()
+        for i in range(frames.shape[0]):
+            exp = port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], rectify, g, v, k)
+            assert_bits_equal(out[i], exp, f"{name}/{loader} flags={flags} frame={i}")
+
+
+@pytest.mark.parametrize("name", ["c1_crop_640", "odd_sizes", "upscale", "full_blackpx"])
+@pytest.mark.parametrize("loader", ["tma", "ldg"])
+def test_pyramid_levels(name, loader, api, port, dataset_dir):
+    iw, ih, ow, oh, mode, calib = CALIBS[name]
+    if loader == "tma" and iw % 16 != 0:
+        pytest.skip("LDG loader covers this width")
+    files = dataset_dir(name)
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    prep.ctx.configure(use_tma=1 if loader == "tma" else 0)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(5, iw, ih)
+    d_frames = torch.from_numpy(frames).cuda()
+    for levels, flags in [(5, (1, 1, 1, 1)), (3, (1, 1, 1, 0)), (7, (1, 0, 0, 0)), (4, (0, 1, 1, 0))]:
+        outs = [o.cpu().numpy() for o in prep.prepare_device(d_frames, *flags, levels=levels)]
+        w0, h0 = (ow, oh) if flags[0] else (iw, ih)
+        for i in range(frames.shape[0]):
+            lvl0 = port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], *flags)
+            exp = port.pyramid(lvl0, w0, h0, levels)
+            for l in range(levels):
+                assert outs[l].shape[1] == (w0 >> l) * (h0 >> l)
+                assert_bits_equal(outs[l][i], exp[l], f"{name}/{loader} levels={levels} flags={flags} frame={i} level={l}")
+
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_against_reference_golden_vectors(path, api, tmp_path):
+    """Outputs of the reference's own compiled code (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    iw, ih, ow, oh = [int(v) for v in g["dims"]]
+    cam, pc, vig = tmp_path / "camera.txt", tmp_path / "pcalib.txt", tmp_path / "vignette.png"
+    cam.write_bytes(g["camera_txt"].tobytes())
+    pc.write_bytes(g["pcalib_txt"].tobytes())
+    S.write_png_gray(str(vig), g["vignette_pixels"])
+    u = api.UndistorterFOV(str(cam))
+    p = api.PhotometricUndistorter(str(pc), str(vig), iw, ih)
+    prep = api.FramePreparer(u, p)
+    d_frames = torch.from_numpy(g["frames"]).cuda()
+    for use_tma in (0, -1):
+        prep.ctx.configure(use_tma=use_tma)
+        for flags in range(16):
+            rectify, gm, v, k = flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, (flags >> 3) & 1
+            out = prep.prepare_device(d_frames, rectify, gm, v, k)[0].cpu().numpy()
+            assert_bits_equal(out, g[f"out_{flags:02d}"], f"golden flags={flags} tma={use_tma}")
+    # host-buffer entry point (what the C++ compat classes call): one frame at a time
+    for flags in (0, 1, 7, 15):
+        img = prep.getImage(g["frames"][1].reshape(ih, iw), 1, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, (flags >> 3) & 1)
+        assert_bits_equal(img.image, g[f"out_{flags:02d}"][1], f"golden host getImage flags={flags}")
+
+
+def test_standalone_operators_and_error_behaviour(api, port, dataset_dir, capfd):
+    iw, ih, ow, oh, mode, calib = CALIBS["c1_crop_640"]
+    files = dataset_dir("c1_crop_640")
+    u, p = make_models(api, files, iw, ih)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    img = S.frame(4, iw, ih, "speckle")
+    # unMapImage on host buffers, all 8 flag combinations
+    for g in (0, 1):
+        for v in (0, 1):
+            for k in (0, 1):
+                out = np.zeros(iw * ih, np.float32)
+                p.unMapImage(img, out, iw * ih, g, v, k)
+                assert_bits_equal(out, port.unmap(ginv, vinv, img, g, v, k), f"unMapImage {g}{v}{k}")
+    # undistort<uchar> and undistort<float> on host buffers
+    out = np.zeros(ow * oh, np.float32)
+    u.undistort(img, out, iw * ih, ow * oh)
+    assert_bits_equal(out, port.undistort(rx, ry, iw, img), "undistort<uchar>")
+    fl = port.unmap(ginv, vinv, img, 1, 1, 1)
+    u.undistort(fl, out, iw * ih, ow * oh)
+    assert_bits_equal(out, port.undistort(rx, ry, iw, fl), "undistort<float>")
+    # device tensors
+    d_img = torch.from_numpy(fl).cuda()
+    d_out = torch.zeros(ow * oh, dtype=torch.float32, device="cuda")
+    u.undistort(d_img, d_out)
+    assert_bits_equal(d_out.cpu().numpy(), port.undistort(rx, ry, iw, fl), "undistort<float> device")
+    # wrong pixel counts: message + output untouched (FOVUndistorter.cpp:327-338)
+    out[:] = 7.0
+    u.undistort(img, out, iw * ih - 1, ow * oh)
+    u.undistort(img, out, iw * ih, ow * oh + 3)
+    assert (out == 7.0).all()
+    assert "wrong input image dismesions" in capfd.readouterr().out
+    # photometric object with invalid vignette: undoVignette silently drops to gamma only
+    p2 = api.PhotometricUndistorter(files["pcalib"], "/nonexistent.png", iw, ih)
+    out2 = np.zeros(iw * ih, np.float32)
+    p2.unMapImage(img, out2, iw * ih, True, True, False)
+    assert_bits_equal(out2, port.unmap(ginv, None, img, 1, 1, 0), "gamma-only fallback")
+    # getImage refuses wrong-size / wrong-type frames like the reference (returns 0)
+    prep = api.FramePreparer(u, p)
+    assert prep.getImage(np.zeros((ih, iw + 1), np.uint8), 0, True, True, True, False) is None
+    assert prep.getImage(np.zeros((ih, iw), np.uint16), 0, True, True, True, False) is None
+
+
+def test_stand_alone_pyr_down_matches_fused_epilogue(api, port, dataset_dir):
+    iw, ih, ow, oh, mode, calib = CALIBS["odd_sizes"]
+    files = dataset_dir("odd_sizes")
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    d_frames = torch.from_numpy(mixed_frames(3, iw, ih)).cuda()
+    outs = prep.prepare_device(d_frames, 1, 1, 1, 0, levels=5)
+    for l in range(1, 5):
+        dst = torch.empty_like(outs[l])
+        prep.ctx.pyr_down(outs[l - 1], ow >> (l - 1), oh >> (l - 1), dst, n_frames=3)
+        assert_bits_equal(dst.cpu().numpy(), outs[l].cpu().numpy(), f"K2 vs fused level {l}")
+
+
+@pytest.mark.parametrize("name", list(BIG_CALIBS))
+def test_full_size_configs(name, api, port, dataset_dir):
+    """BASELINE.json configs[1]/[3] geometry: a handful of frames against the oracle, then the
+    size-independent properties on a larger batch (batch position independence; pyramid closure)."""
+    iw, ih, ow, oh, mode, calib = BIG_CALIBS[name]
+    files = dataset_dir(name)
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(4, iw, ih)
+    n_big = 64
+    big = torch.from_numpy(np.concatenate([frames] * (n_big // 4))).cuda()
+    for use_tma in (-1, 0):
+        prep.ctx.configure(use_tma=use_tma)
+        outs = prep.prepare_device(big, 1, 1, 1, 1, levels=5)
+        lv = [o.cpu().numpy() for o in outs]
+        for i in range(4):
+            exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 1), ow, oh, 5)
+            for l in range(5):
+                assert_bits_equal(lv[l][i], exp[l], f"{name} tma={use_tma} frame={i} level={l}")
+        # every replica of a frame in the batch gives the same bits, wherever the schedule put it
+        for l in range(5):
+            a = lv[l].reshape(n_big // 4, 4, -1)
+            assert np.array_equal(a.view(np.uint32), np.broadcast_to(a[:1], a.shape).view(np.uint32)), f"batch position dependence, level {l}"
+
+
+def test_estep_bit_exact(api, port):
+    rng = np.random.default_rng(11)
+    for n, npix in [(37, 4096), (20, 1001), (64, 12 * 1024)]:
+        data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+        data[:, 5] = 255                       # never-valid pixel -> 0/0 = NaN survives the clamp
+        data[:, 7] = 0
+        t = rng.uniform(0.05, 20.0, n).astype(np.float32).astype(np.float64)   # exposures come through a float (main_responseCalib.cpp:209)
+        G = np.sort(rng.uniform(-5, 300, 256))
+        G[3] = -2.0
+        exp = port.estep(data, t, G)
+        ctx = api.Context(None, None, 0)
+        E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+        ctx.estep(torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda(), E)
+        assert_bits_equal(E.cpu().numpy(), exp, f"E-step n={n} npix={npix}")
+        assert np.isnan(exp[5])
+
+
+def test_multi_gpu_style_adopted_tables(api, port, dataset_dir):
+    """Context built from device tables (the path ranks > 0 take after the NCCL broadcast)."""
+    iw, ih, ow, oh, mode, calib = CALIBS["c1_crop_640"]
+    files = dataset_dir("c1_crop_640")
+    u, p = make_models(api, files, iw, ih)
+    rx, ry = u.remap_tables()
+    t = [torch.from_numpy(a).cuda() for a in (rx, ry, p.getGInv(), p.vignette_maps()[1])]
+    ctx = api.Context.from_device_tables(0, iw, ih, ow, oh, *t)
+    frames = mixed_frames(3, iw, ih)
+    d = torch.from_numpy(frames).cuda()
+    out = torch.empty((3, ow * oh), dtype=torch.float32, device="cuda")
+    ctx.prepare_batch(d, 1 | 2 | 4, [out])
+    prx, pry, ginv, vinv = oracle_tables(port, files)
+    for i in range(3):
+        assert_bits_equal(out[i].cpu().numpy(), port.get_image(prx, pry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 0), f"adopted ctx frame {i}")
