@@ -184,25 +184,17 @@ def run_gpu_arm(args):
     tmp = tempfile.mkdtemp(prefix="mdc_bench_")
     files = write_calibration(tmp) if rank == 0 else None
     n_in, n_out = IN_W * IN_H, OUT_W * OUT_H
-    if world == 1:
+    fov = photo = None
+    if rank == 0:
         fov = api.UndistorterFOV(files["camera"])
         photo = api.PhotometricUndistorter(files["pcalib"], files["vignette"], IN_W, IN_H)
+    if world == 1:
         ctx = api.Context(fov, photo, local)
     else:
-        t_rx = torch.empty(n_out, dtype=torch.float32, device=dev)
-        t_ry = torch.empty(n_out, dtype=torch.float32, device=dev)
-        t_g = torch.empty(256, dtype=torch.float32, device=dev)
-        t_v = torch.empty(n_in, dtype=torch.float32, device=dev)
-        if rank == 0:
-            fov = api.UndistorterFOV(files["camera"])
-            photo = api.PhotometricUndistorter(files["pcalib"], files["vignette"], IN_W, IN_H)
-            rx, ry = fov.remap_tables()
-            t_rx.copy_(torch.from_numpy(rx)); t_ry.copy_(torch.from_numpy(ry))
-            t_g.copy_(torch.from_numpy(photo.getGInv())); t_v.copy_(torch.from_numpy(photo.vignette_maps()[1]))
-        for t in (t_rx, t_ry, t_g, t_v):
-            dist.broadcast(t, src=0)          # one-time; no collective in steady state
+        from mono_dataset_code_b200 import sharding
+        dims, tabs = sharding.broadcast_calibration(fov, photo, dev)     # one-time NCCL broadcast; no collective in steady state
         torch.cuda.synchronize()
-        ctx = api.Context.from_device_tables(local, IN_W, IN_H, OUT_W, OUT_H, t_rx, t_ry, t_g, t_v)
+        ctx = api.Context.from_device_tables(local, *dims, *tabs)
     if args.tma is not None:
         ctx.configure(use_tma=args.tma)
 
