@@ -384,7 +384,11 @@ size_t fused_smem_bytes(int box_px_max, bool tma) {
 int fused_max_ctas_per_sm(int box_px_max, bool tma) {
     int n = 0;
     const int smem = static_cast<int>(fused_smem_bytes(box_px_max, tma));
-    cudaError_t e = tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_prepare_kernel<true>, kThreads, smem)
+    // the opt-in limit must be raised before the occupancy query, or it reports 0 for > 48 KB
+    cudaError_t e = tma ? cudaFuncSetAttribute(fused_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : cudaFuncSetAttribute(fused_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return 0;
+    e = tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_prepare_kernel<true>, kThreads, smem)
                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_prepare_kernel<false>, kThreads, smem);
     return e == cudaSuccess ? n : 0;
 }
