@@ -55,45 +55,53 @@ def write_calibration(tmp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons polled through NVML (nvidia_ml_py) every few ms DURING the timed region;
+    falls back to one nvidia-smi query if NVML is unavailable."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.samples, self.reason_bits, self._stop, self.t, self.h = gpu_index, [], 0, False, None, None
+        self.max_mhz = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.h is None:
+            return
+        self._stop = False
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
-            c = [x.strip() for x in r.split(",")]
-            if len(c) < 9:
-                continue
+        if self.h is None:
             try:
-                sm.append(float(c[1])); smax.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=20).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["nvml unavailable: single nvidia-smi sample after the run"], "samples": 1}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"], "samples": 0}
+        self._stop = True
+        self.t.join()
+        reasons = [n for n, b in {**self.BAD, **self.NOTE}.items() if self.reason_bits & b]
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------ CPU arms
@@ -243,6 +251,12 @@ def run_gpu_arm(args):
     k1_ms = float(np.mean(per_launch_ms))
     achieved = B * ALG_BYTES_PER_FRAME / (k1_ms * 1e-3) / 1e9
 
+    if args.only_kernel:
+        if rank == 0:
+            print(json.dumps({"value": value, "achieved_gbs": achieved, "frac": achieved / peak, "launch_ms": k1_ms, "clocks": clocks,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("MDC_")}, "tma": args.tma}), flush=True)
+        return
+
     # configs[2]: + 5-level pyramid fused in the same kernel's epilogue
     p_total_ms, p_launch_ms, _, _ = timed(5, max(2, args.steps // 2), 2)
     p_steps = max(2, args.steps // 2)
@@ -306,6 +320,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
     ap.add_argument("--tma", type=int, default=None, help="force the input loader: 1 = TMA, 0 = LDG")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only-kernel", action="store_true", help="tuning sweeps: device-resident K1 timing only (no pyramid / e2e / cpu legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

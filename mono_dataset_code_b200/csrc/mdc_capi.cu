@@ -72,7 +72,7 @@ struct mdc_ctx {
     int map_key_frames[kMapSlots] = {};
     int map_next = 0;
     // knobs
-    int use_tma = -1, ctas_per_sm = 0;
+    int use_tma = -1, ctas_per_sm = 0, chunk_frames = 0;
     // streams + host pipeline scratch
     cudaStream_t stream = nullptr;
     cudaStream_t pipe_stream[kHostPipeDepth] = {nullptr, nullptr, nullptr};
@@ -107,9 +107,9 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     const bool tma_geom_ok = (W % 16 == 0) && (static_cast<long long>(W) * H % 16 == 0);
     // relative per-frame cost of a tile (pixel-equivalents), used to balance the static schedule
     const char* e;
-    const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 1;       // per staged input pixel (LUT pass)
-    const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 4;     // per output pixel (gather + blend + store)
-    const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 12;
+    const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 0;       // per 4 staged input bytes (free with TMA)
+    const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 8;     // per output pixel (taps + LUT + blend + store)
+    const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 16;
     // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
     for (int gran = 8; gran <= 256; gran *= 2) {
     c->classes.clear();
@@ -118,10 +118,11 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     for (int t = 0; t < n_tiles; ++t) {
         const int tx0 = (t % c->tiles_x) * kTile, ty0 = (t / c->tiles_x) * kTile;
         int xlo = 1 << 30, xhi = -1, ylo = 1 << 30, yhi = -1;
+        bool black = false;
         for (int y = ty0; y < std::min(ty0 + kTile, OH); ++y)
             for (int x = tx0; x < std::min(tx0 + kTile, OW); ++x) {
                 const float sx = rx[static_cast<size_t>(y) * OW + x], sy = ry[static_cast<size_t>(y) * OW + x];
-                if (sx < 0) continue;
+                if (sx < 0) { black = true; continue; }
                 const int xi = static_cast<int>(sx), yi = static_cast<int>(sy);
                 xlo = std::min(xlo, xi); xhi = std::max(xhi, xi + 1);
                 ylo = std::min(ylo, yi); yhi = std::max(yhi, yi + 1);
@@ -132,7 +133,7 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
             // defensive: a table that violates the reference's in-bounds guarantee would read outside the frame
             xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
             xhi = std::min(xhi, W - 1); yhi = std::min(yhi, H - 1);
-            const int x0 = xlo & ~15;
+            const int x0 = xlo & ~3;
             const int bw = ((xhi - x0 + 1) + 15) & ~15;
             const int bh = yhi - ylo + 1, bh8 = (bh + gran - 1) / gran * gran;
             int lg = 2;
@@ -154,12 +155,13 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
                 }
                 td.mode_map = TILE_STAGED | (cls << 8) | (bh8 << 16);
                 c->box_px_max = std::max(c->box_px_max, bw * bh8);
-                cost = static_cast<uint32_t>(cost_in * bw * bh + cost_out * kTile * kTile);
+                cost = static_cast<uint32_t>(cost_in * (bw * bh / 4) + cost_out * kTile * kTile);
             } else {
                 td.mode_map = TILE_DIRECT;
                 cost = static_cast<uint32_t>(cost_direct * kTile * kTile);
             }
         }
+        if (black) td.mode_map |= TILE_HAS_BLACK;
         c->tiles[t] = td;
         c->cost_prefix[t + 1] = c->cost_prefix[t] + std::max<uint32_t>(cost, 1u);
     }
@@ -188,6 +190,8 @@ int ctx_common_init(mdc_ctx* c, int device) {
     if (e) c->use_tma = atoi(e);
     e = getenv("MDC_CTAS_PER_SM");
     if (e) c->ctas_per_sm = atoi(e);
+    e = getenv("MDC_CHUNK_FRAMES");
+    if (e) c->chunk_frames = atoi(e);
     return MDC_OK;
 }
 
@@ -257,7 +261,7 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     for (int l = in_kernel; l < MDC_MAX_PYR_LEVELS; ++l) { p.lw[l] = p.lh[l] = 0; }
     p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
     p.box_px_max = c->box_px_max;
-    p.vec2_ok = (c->out_w % 2 == 0) && (reinterpret_cast<uintptr_t>(d_out_levels[0]) % 8 == 0);
+    p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 16;
     bool tma = c->plan_tma_ok && c->use_tma != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
     if (c->use_tma == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
     const TmaMaps* maps = nullptr;
@@ -265,7 +269,7 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
         int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
         if (rc != MDC_OK) return rc;
     }
-    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma);
+    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma, u.vig, in_kernel > 1);
     if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
     if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
     long long units = static_cast<long long>(p.n_tiles) * n_frames;

@@ -24,17 +24,44 @@
 namespace mdc {
 
 // =====================================================================================
-// small PTX helpers: mbarrier + TMA (cp.async.bulk.tensor)
+// small PTX helpers: shared-memory access by 32-bit address, mbarrier, TMA, streaming stores
 // =====================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// volatile: the staged bytes change every frame (TMA / other warps write them), so these loads must
+// neither be hoisted out of the frame loop nor merged across iterations.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ uint32_t lds_u8_1(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// evict-first store: the rectified images are written once and never re-read by this kernel; keep L2
+// for the input frames of the current chunk and for the calibration tables.
+__device__ __forceinline__ void stg_cs(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -43,45 +70,60 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
 // 3-D tiled TMA load: box (bw, bh, 1) of the u8 frame stack at (x, y, frame) -> shared memory.
-__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int frame) {
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int frame) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(frame), "r"(smem_u32(bar))
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(frame), "r"(bar)
         : "memory");
 }
+// Blackwell packed FP32: one FMUL2 issues two IEEE round-to-nearest multiplies (same results as two
+// FMULs).  Only the multiplies are packed: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// under --fmad=false, which would break bit-exactness, so the adds stay scalar __fadd_rn.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 // =====================================================================================
 // K1: fused photometric un-map + FOV rectification (+ pyramid epilogue)
 // =====================================================================================
 //
-// Work decomposition.  The output image is cut into 32x32 tiles; a tile's bilinear taps fall into
-// a compact bounding box of the input image (host-precomputed, TileDesc).  The unit of work is
-// (tile, frame).  Units are ordered tile-major and split into gridDim.x contiguous, cost-balanced
-// ranges, one per persistent CTA, so a CTA works through a few tiles and, for each, loops over a
-// long run of frames.  Everything that depends only on the calibration — the remap entry of each of
-// the thread's 4 pixels (turned into 4 bilinear weights and a box-local offset) and the 4 vignette
-// reciprocals under the taps — is loaded ONCE per tile into registers and reused for every frame,
+// Work decomposition.  The output image is cut into 32x32 tiles; a tile's bilinear taps fall into a
+// compact bounding box of the input image (host-precomputed, TileDesc).  The unit of work is
+// (tile, frame).  Frames are grouped into chunks of `chunk_frames`; units are ordered
+// chunk-major, then tile-major, then by frame, and this order is cut into gridDim.x contiguous,
+// cost-balanced ranges, one per persistent CTA.  So a CTA works through a few tiles per chunk and, for
+// each, loops over a run of consecutive frames — while, chip-wide, all CTAs are inside the same
+// chunk at the same time, which keeps that chunk's input frames (and the 15.7 MB of tables) resident
+// in the 126 MB L2 although neighbouring tiles re-read overlapping parts of them.
+//
+// Everything that depends only on the calibration — the remap entry of each of the thread's 4 pixels
+// (turned into 4 bilinear weights and a box-local byte offset) and the 4 vignette reciprocals under
+// the taps — is loaded ONCE per (tile, chunk) into registers and reused for every frame of the run,
 // which removes the 15.7 MB/frame of table traffic a naive fused kernel would add to the
 // 6.5 MB/frame of unavoidable image traffic (SURVEY.md §7 "hard parts").
 //
-// Per frame: the u8 input box is brought on chip (TMA tensor load into a 2-stage mbarrier ring, or
-// register-prefetched LDG for image widths TMA cannot describe), pushed once through the
-// response LUT (lane-replicated in shared memory, so the 256-entry gather is bank-conflict free)
-// into a float tile, and then each thread gathers 4 taps per pixel from that tile, applies the
-// vignette reciprocals and the bilinear blend in the reference's exact operation order, and
-// writes its 2x2 block.  The 2x2 ownership makes pyramid level 1 thread-local, level 2 a 4-lane
-// shuffle, and levels 3-4 a 64-float shared-memory hand-off to warp 0.
+// Per frame the u8 input box is staged in shared memory:
+//   * TMA loader: a dedicated producer warp issues one 3-D cp.async.bulk.tensor per (tile, frame)
+//     into a 3-stage ring; full/empty mbarriers connect it to the 8 consumer warps, so in steady state
+//     there is no CTA-wide barrier at all and the producer runs ahead across tile boundaries;
+//   * LDG loader (image widths TMA cannot describe): every consumer prefetches its share of the next
+//     frame's box into registers during the gather and stores it to the other stage afterwards.
+// A consumer warp owns 4 output rows of the tile; lane = x.  For each of its 4 pixels a thread reads
+// the 4 tap bytes (LDS.U8; 32 lanes along one output row touch ~24 different words, so the access is
+// nearly conflict-free), pushes them through the response LUT — lane-replicated in shared memory,
+// `lut[v*32+lane]`, so the data-dependent lookup is bank-conflict-free —, multiplies by the cached
+// vignette reciprocals and blends with the cached weights in the reference's exact operation order.
+// `killOverexposed` is folded into the LUT (lut[255]=NaN) and the no-gamma modes use an identity LUT,
+// so one kernel covers all flag combinations as well as undistort<unsigned char>.
 
-struct TileRegs {
-    float w[4][4];    // per pixel: w0 (x,y) w1 (x+1,y) w2 (x,y+1) w3 (x+1,y+1)
-    float vi[4][4];   // vignette reciprocals under the same taps
-    int off[4];       // box-local (staged) or image-global (direct) offset of tap 0; <0 = black pixel
-};
+struct WorkPos { int chunk, tile, frame; };
 
 __device__ __forceinline__ float lut_value(const FusedParams& p, int v) {
     float r = p.lut_gamma ? __ldg(p.ginv + v) : static_cast<float>(v);
@@ -89,112 +131,169 @@ __device__ __forceinline__ float lut_value(const FusedParams& p, int v) {
     return r;
 }
 
-// locate the (tile, frame) at work position `pos` (in cost units) of the tile-major unit order
-__device__ void locate_unit(const FusedParams& p, unsigned long long pos, int& tile, int& frame) {
-    const unsigned long long nf = static_cast<unsigned long long>(p.n_frames);
-    const unsigned long long total = static_cast<unsigned long long>(p.tile_cost_prefix[p.n_tiles]) * nf;
-    if (pos >= total) { tile = p.n_tiles; frame = 0; return; }
-    int lo = 0, hi = p.n_tiles;  // invariant: prefix[lo]*nf <= pos < prefix[hi]*nf
+// (chunk, tile, frame-in-chunk) at work position `pos` (cost units) of the chunk/tile-major unit order
+__device__ WorkPos locate_unit(const FusedParams& p, unsigned long long pos) {
+    const unsigned long long ct = p.tile_cost_prefix[p.n_tiles];
+    const unsigned long long total = ct * static_cast<unsigned long long>(p.n_frames);
+    const int n_chunks = (p.n_frames + p.chunk_frames - 1) / p.chunk_frames;
+    WorkPos w;
+    if (pos >= total) { w.chunk = n_chunks; w.tile = 0; w.frame = 0; return w; }
+    const unsigned long long per_chunk = ct * static_cast<unsigned long long>(p.chunk_frames);
+    w.chunk = static_cast<int>(pos / per_chunk);
+    const unsigned long long rem = pos - per_chunk * w.chunk;
+    const unsigned long long fk = static_cast<unsigned long long>(min(p.chunk_frames, p.n_frames - w.chunk * p.chunk_frames));
+    int lo = 0, hi = p.n_tiles;  // invariant: prefix[lo]*fk <= rem < prefix[hi]*fk
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (static_cast<unsigned long long>(p.tile_cost_prefix[mid]) * nf <= pos) lo = mid; else hi = mid;
+        if (static_cast<unsigned long long>(p.tile_cost_prefix[mid]) * fk <= rem) lo = mid; else hi = mid;
     }
-    const unsigned long long base = static_cast<unsigned long long>(p.tile_cost_prefix[lo]) * nf;
     const unsigned long long wt = p.tile_cost_prefix[lo + 1] - p.tile_cost_prefix[lo];
-    tile = lo;
-    frame = static_cast<int>((pos - base) / wt);
+    w.tile = lo;
+    w.frame = static_cast<int>((rem - static_cast<unsigned long long>(p.tile_cost_prefix[lo]) * fk) / wt);
+    return w;
 }
 
-template <bool kTma>
-__global__ void __launch_bounds__(kThreads, 2) fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TmaMaps maps) {
+// Iterates the segments (tile, global frame range) of the CTA's work range in order.  Kept to three
+// registers of state (the end position is re-read from shared memory once per segment) because it is
+// live across the register-critical frame loop.
+struct SegmentIter {
+    int k, t, fb;   // current chunk, next tile, first frame (in chunk) of the next segment
+    __device__ __forceinline__ void init(const int* sched) { k = sched[0]; t = sched[1]; fb = sched[2]; }
+    // next non-empty segment; false when the range is exhausted
+    __device__ __forceinline__ bool next(const FusedParams& p, const int* sched, int& tile, int& f0, int& f1) {
+        const int e_chunk = sched[3], e_tile = sched[4], e_frame = sched[5];
+        const int n_chunks = (p.n_frames + p.chunk_frames - 1) / p.chunk_frames;
+        for (;;) {
+            if (k >= n_chunks || k > e_chunk) return false;
+            const int t_last = (k == e_chunk) ? e_tile : p.n_tiles - 1;
+            if (t > t_last || t >= p.n_tiles) { ++k; t = 0; fb = 0; continue; }
+            const int base = k * p.chunk_frames, fk = min(p.chunk_frames, p.n_frames - base);
+            const int fe = (k == e_chunk && t == e_tile) ? e_frame : fk;
+            const int first = fb;
+            tile = t; f0 = base + first; f1 = base + fe;
+            ++t; fb = 0;
+            if (first < fe) return true;
+        }
+    }
+};
+
+template <bool kTma, bool kVig, bool kPyr>
+__global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, 3)
+fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TmaMaps maps) {
+    constexpr int kNs = kTma ? kTmaStages : kLdgStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // ---- shared-memory carve-up (see fused_smem_bytes)
     float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
-    float* ftile = lut + 256 * 32;                                      // [box_px_max] LUT-mapped input box
-    float* s_l2 = ftile + p.box_px_max;                                 // [64] pyramid level-2 hand-off
-    int* s_sched = reinterpret_cast<int*>(s_l2 + 64);                   // [4] tile_b, frame_b, tile_e, frame_e
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sched + 4);         // [kStages] mbarriers (TMA only)
+    float* s_l2 = lut + 256 * 32;                                       // [2][64] pyramid level-2 hand-off (double-buffered)
+    int* s_sched = reinterpret_cast<int*>(s_l2 + 128);                  // [8] begin / end work positions
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sched + 8);         // [2*kMaxStages] full[], empty[]
     const uint32_t stage_bytes = (static_cast<uint32_t>(p.box_px_max) + 127u) & ~127u;
-    uint8_t* u8stage = smem_raw + ((256u * 32u * 4u + static_cast<uint32_t>(p.box_px_max) * 4u + 64u * 4u + 16u + 8u * kStages + 127u) & ~127u);
+    const uint32_t stage0 = smem_u32(smem_raw) + kSmemHeaderBytes;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8u * kMaxStages;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx = tid & 15, by = tid >> 4;   // position of this thread's 2x2 block inside the tile
 
     // ---- one-time per CTA: LUT, barriers, work range
-    for (int i = tid; i < 256 * 32; i += kThreads) lut[i] = lut_value(p, i >> 5);
+    for (int i = tid; i < 256 * 32; i += blockDim.x) lut[i] = lut_value(p, i >> 5);
     if (tid == 0) {
-        const unsigned long long nf = static_cast<unsigned long long>(p.n_frames);
-        const unsigned long long total = static_cast<unsigned long long>(p.tile_cost_prefix[p.n_tiles]) * nf;
-        int t, f;
-        locate_unit(p, total * blockIdx.x / gridDim.x, t, f);
-        s_sched[0] = t; s_sched[1] = f;
-        locate_unit(p, total * (blockIdx.x + 1ull) / gridDim.x, t, f);
-        s_sched[2] = t; s_sched[3] = f;
+        const unsigned long long total = static_cast<unsigned long long>(p.tile_cost_prefix[p.n_tiles]) * static_cast<unsigned long long>(p.n_frames);
+        const WorkPos b = locate_unit(p, total * blockIdx.x / gridDim.x);
+        const WorkPos e = locate_unit(p, total * (blockIdx.x + 1ull) / gridDim.x);
+        s_sched[0] = b.chunk; s_sched[1] = b.tile; s_sched[2] = b.frame;
+        s_sched[3] = e.chunk; s_sched[4] = e.tile; s_sched[5] = e.frame;
         if (kTma) {
-            for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
+            for (int s = 0; s < kNs; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, kConsumers / 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
     __syncthreads();
-    const int tile_b = s_sched[0], frame_b = s_sched[1], tile_e = s_sched[2], frame_e = s_sched[3];
+    SegmentIter seg;
+    seg.init(s_sched);
+    int tile, f_begin, f_end;
+
+    // ================================================================ producer warp (TMA loader only)
+    if (kTma && warp == kConsumers / 32) {
+        if (lane == 0) {
+            uint32_t st = 0, round = 0;   // ring position of the next staged frame to issue
+            while (seg.next(p, s_sched, tile, f_begin, f_end)) {
+                const TileDesc td = p.tiles[tile];
+                if ((td.mode_map & 0x0f) != TILE_STAGED) continue;
+                const CUtensorMap* tmap = &maps.m[(td.mode_map >> 8) & 0xff];
+                const uint32_t bytes = static_cast<uint32_t>(td.bw_bh & 0xffff) * static_cast<uint32_t>(td.mode_map >> 16);
+                for (int f = f_begin; f < f_end; ++f) {
+                    if (round > 0) mbar_wait(bar_empty + 8u * st, (round - 1u) & 1u);   // consumers released this slot
+                    mbar_expect_tx(bar_full + 8u * st, bytes);
+                    tma_load_box(stage0 + st * stage_bytes, tmap, bar_full + 8u * st, td.x0, td.y0, f);
+                    if (++st == static_cast<uint32_t>(kNs)) { st = 0; ++round; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================================================ consumer warps
     const size_t n_in = static_cast<size_t>(p.in_w) * p.in_h;
-    const size_t n_out0 = static_cast<size_t>(p.lw[0]) * p.lh[0];
-    uint32_t it = 0;  // frames consumed so far by this CTA (TMA stage/parity bookkeeping)
+    const uint32_t lut_lane = smem_u32(lut) + 4u * lane;
+    uint32_t st = 0, phase = 0;   // ring position / parity of the next staged frame to consume
+    uint32_t st_addr = stage0;    // = stage0 + st * stage_bytes
+    uint32_t pyr_it = 0;   // frames processed so far (parity selects the level-2 hand-off buffer)
 
-    for (int tile = tile_b; tile <= tile_e && tile < p.n_tiles; ++tile) {
-        const int f_begin = (tile == tile_b) ? frame_b : 0;
-        const int f_end = (tile == tile_e) ? frame_e : p.n_frames;
-        if (f_begin >= f_end) continue;
-
-        // ------------------------------------------------------------ per-tile prologue
+    while (seg.next(p, s_sched, tile, f_begin, f_end)) {
+        // ------------------------------------------------------------ per-(tile, run) prologue
         const TileDesc td = p.tiles[tile];
-        const int mode = td.mode_map & 0xff;
+        const int mode = td.mode_map & 0x0f;
+        const bool staged = mode == TILE_STAGED;
         const int bw = td.bw_bh & 0xffff, bh = td.bw_bh >> 16;
         const int tx0 = (tile % p.tiles_x) * kTile, ty0 = (tile / p.tiles_x) * kTile;
-        TileRegs r;
+        const int ox = tx0 + lane, oy0 = ty0 + 4 * warp;
+        const int pitch = staged ? bw : p.in_w;       // distance between the two tap rows
+
+        float w[4][4], vi[4][4];
+        uint32_t off[4];
+        unsigned valid = 0;
+        const bool has_black = (td.mode_map & TILE_HAS_BLACK) != 0;   // some in-image pixel of the tile has no source
+        const bool full_tile = tx0 + kTile <= p.out_w && ty0 + kTile <= p.out_h;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int ox = tx0 + 2 * bx + (q & 1), oy = ty0 + 2 * by + (q >> 1);
+            const int oy = oy0 + q;
             float sx = -1.0f, sy = -1.0f;
             if (ox < p.out_w && oy < p.out_h) {
                 const size_t o = static_cast<size_t>(oy) * p.out_w + ox;
                 sx = __ldg(p.remap_x + o);
                 sy = __ldg(p.remap_y + o);
             }
-            r.off[q] = -1;
+            off[q] = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { r.w[q][k] = 0.0f; r.vi[q][k] = 1.0f; }
+            for (int k = 0; k < 4; ++k) { w[q][k] = 0.0f; vi[q][k] = 1.0f; }
             if (!(sx < 0)) {  // the reference tests only remapX (FOVUndistorter.cpp:347)
+                valid |= 1u << q;
                 const int xi = static_cast<int>(sx), yi = static_cast<int>(sy);   // truncation, :352-353
                 const float fx = __fsub_rn(sx, static_cast<float>(xi));
                 const float fy = __fsub_rn(sy, static_cast<float>(yi));
                 const float fxy = __fmul_rn(fx, fy);
-                r.w[q][3] = fxy;
-                r.w[q][2] = __fsub_rn(fy, fxy);
-                r.w[q][1] = __fsub_rn(fx, fxy);
-                r.w[q][0] = __fadd_rn(__fsub_rn(__fsub_rn(1.0f, fx), fy), fxy);
+                w[q][3] = fxy;
+                w[q][2] = __fsub_rn(fy, fxy);
+                w[q][1] = __fsub_rn(fx, fxy);
+                w[q][0] = __fadd_rn(__fsub_rn(__fsub_rn(1.0f, fx), fy), fxy);
                 const int g = yi * p.in_w + xi;
-                r.off[q] = (mode == TILE_STAGED) ? (yi - td.y0) * bw + (xi - td.x0) : g;
-                if (p.use_vig) {
-                    r.vi[q][0] = __ldg(p.vinv + g);
-                    r.vi[q][1] = __ldg(p.vinv + g + 1);
-                    r.vi[q][2] = __ldg(p.vinv + g + p.in_w);
-                    r.vi[q][3] = __ldg(p.vinv + g + p.in_w + 1);
+                off[q] = static_cast<uint32_t>(staged ? (yi - td.y0) * bw + (xi - td.x0) : g);
+                if (kVig) {
+                    vi[q][0] = __ldg(p.vinv + g);
+                    vi[q][1] = __ldg(p.vinv + g + 1);
+                    vi[q][2] = __ldg(p.vinv + g + p.in_w);
+                    vi[q][3] = __ldg(p.vinv + g + p.in_w + 1);
                 }
             }
         }
 
-        // loader geometry for the staged modes
-        const int n_words = (bw * bh) >> 2;                 // u32 words in the box
-        // LDG loader: threads tiled (rows x words-per-row) with a power-of-two row length
-        int lg = 2;                                          // log2 of padded words per row (>= 4 words)
+        // LDG loader geometry: threads tiled (rows x words-per-row) with a power-of-two row length
+        int lg = 2;
         while ((4 << lg) < bw) ++lg;
-        const int ld_col = tid & ((1 << lg) - 1), ld_row = tid >> lg, ld_rstep = kThreads >> lg;
-        const int ld_pass = (mode == TILE_STAGED && !kTma) ? (bh + ld_rstep - 1) / ld_rstep : 0;
+        const int ld_col = tid & ((1 << lg) - 1), ld_row = tid >> lg, ld_rstep = kConsumers >> lg;
+        const int ld_pass = (staged && !kTma) ? (bh + ld_rstep - 1) / ld_rstep : 0;
         const bool ld_col_ok = (ld_col * 4) < bw;
         const bool ld_fast = ((p.in_w & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0);
         uint32_t pre[kMaxBoxWordsPerThread];
-
         auto ldg_box = [&](int frame) {   // issue the global loads of `frame`'s box into registers
             const uint8_t* src = p.frames + static_cast<size_t>(frame) * n_in;
 #pragma unroll
@@ -216,197 +315,189 @@ __global__ void __launch_bounds__(kThreads, 2) fused_prepare_kernel(const __grid
                 pre[k] = v;
             }
         };
-        auto lut4 = [&](uint32_t v) {
-            float4 f;
-            f.x = lut[((v & 0xffu) << 5) + lane];
-            f.y = lut[(((v >> 8) & 0xffu) << 5) + lane];
-            f.z = lut[(((v >> 16) & 0xffu) << 5) + lane];
-            f.w = lut[((v >> 24) << 5) + lane];
-            return f;
-        };
-
-        const CUtensorMap* tmap = &maps.m[kTma ? ((td.mode_map >> 8) & 0xff) : 0];
-        const uint32_t tma_bytes = static_cast<uint32_t>(bw) * static_cast<uint32_t>(td.mode_map >> 16);
-        if (mode == TILE_STAGED) {
-            if (kTma) {
-                if (tid == 0) {
+        auto sts_box = [&](uint32_t stage) {
 #pragma unroll
-                    for (int s = 0; s < kStages; ++s)
-                        if (f_begin + s < f_end) {
-                            const uint32_t st = (it + s) % kStages;
-                            mbar_expect_tx(&s_bar[st], tma_bytes);
-                            tma_load_box(u8stage + st * stage_bytes, tmap, &s_bar[st], td.x0, td.y0, f_begin + s);
-                        }
-                }
-            } else {
-                ldg_box(f_begin);
+            for (int k = 0; k < kMaxBoxWordsPerThread; ++k) {
+                const int row = ld_row + k * ld_rstep;
+                if (k < ld_pass && ld_col_ok && row < bh) sts_u32(stage + static_cast<uint32_t>(row * bw + ld_col * 4), pre[k]);
             }
+        };
+        if (!kTma && staged) {   // first frame of the run: load + publish before anybody gathers
+            ldg_box(f_begin);        // (the barrier closing the previous run's last frame already freed both stages)
+            sts_box(st_addr);
+            consumer_barrier();
         }
+        // packed (pixel q, pixel q+1) weights / vignette reciprocals for FMUL2
+        uint64_t w2[2][4], vi2[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w2[h][k] = pack2(w[2 * h][k], w[2 * h + 1][k]);
+                vi2[h][k] = pack2(vi[2 * h][k], vi[2 * h + 1][k]);
+            }
+
+        float* o0 = p.out[0] + static_cast<size_t>(f_begin) * p.lw[0] * p.lh[0] + static_cast<size_t>(oy0) * p.out_w + ox;
+        const size_t o0_step = static_cast<size_t>(p.lw[0]) * p.lh[0];
+        const bool x_ok = ox < p.out_w;
 
         // ------------------------------------------------------------ frame loop
         for (int f = f_begin; f < f_end; ++f) {
-            const uint8_t* frame = p.frames + static_cast<size_t>(f) * n_in;
-            if (mode == TILE_STAGED) {
-                // bring the box through the response LUT into the float tile
-                if (kTma) {
-                    const uint32_t st = it % kStages;
-                    mbar_wait(&s_bar[st], (it / kStages) & 1u);
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(u8stage + st * stage_bytes);
-                    float4* dst = reinterpret_cast<float4*>(ftile);
-                    for (int g = tid; g < n_words; g += kThreads) dst[g] = lut4(src[g]);
-                } else {
+            uint32_t b[4][4];
+            if (staged) {
+                if (kTma) mbar_wait(bar_full + 8u * st, phase);
+                else if (f + 1 < f_end) ldg_box(f + 1);          // in flight during the gather below
+                const uint32_t base = st_addr;
 #pragma unroll
-                    for (int k = 0; k < kMaxBoxWordsPerThread; ++k) {
-                        const int row = ld_row + k * ld_rstep;
-                        if (k < ld_pass && ld_col_ok && row < bh)
-                            *reinterpret_cast<float4*>(ftile + row * bw + ld_col * 4) = lut4(pre[k]);
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t a0 = base + off[q], a1 = a0 + static_cast<uint32_t>(pitch);
+                    b[q][0] = lds_u8(a0); b[q][1] = lds_u8_1(a0);
+                    b[q][2] = lds_u8(a1); b[q][3] = lds_u8_1(a1);
+                }
+            } else {
+                const uint8_t* frame = p.frames + static_cast<size_t>(f) * n_in;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint8_t* s = frame + off[q];
+                    b[q][0] = __ldg(s); b[q][1] = __ldg(s + 1);
+                    b[q][2] = __ldg(s + pitch); b[q][3] = __ldg(s + pitch + 1);
                 }
             }
-            __syncthreads();   // (A) float tile complete; u8 stage / prefetch registers free
-            if (mode == TILE_STAGED) {
-                if (kTma) {
-                    if (tid == 0 && f + kStages < f_end) {
-                        const uint32_t st = it % kStages;
-                        mbar_expect_tx(&s_bar[st], tma_bytes);
-                        tma_load_box(u8stage + st * stage_bytes, tmap, &s_bar[st], td.x0, td.y0, f + kStages);
-                    }
-                } else if (f + 1 < f_end) {
-                    ldg_box(f + 1);   // in flight during the gather below
+            float g[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[q][k] = lds_f32(lut_lane + (b[q][k] << 7));
+            if (staged) {
+                if (kTma) {          // all tap bytes of this warp are in registers: hand the stage back to the producer
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8u * st);
                 }
+                st_addr += stage_bytes;
+                if (++st == static_cast<uint32_t>(kNs)) { st = 0; st_addr = stage0; phase ^= 1u; }
             }
 
-            // ---- gather + blend (reference order: FOVUndistorter.cpp:362-365)
+            // ---- unMapImage multiply + bilinear blend, reference order (PhotometricUndistorter.cpp:205, FOVUndistorter.cpp:362-365)
             float px[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float v = 0.0f;
-                if (r.off[q] >= 0) {
-                    float g0, g1, g2, g3;
-                    if (mode == TILE_STAGED) {
-                        const float* s = ftile + r.off[q];
-                        g0 = s[0]; g1 = s[1]; g2 = s[bw]; g3 = s[bw + 1];
-                    } else {
-                        const uint8_t* s = frame + r.off[q];
-                        g0 = lut[(static_cast<int>(__ldg(s)) << 5) + lane];
-                        g1 = lut[(static_cast<int>(__ldg(s + 1)) << 5) + lane];
-                        g2 = lut[(static_cast<int>(__ldg(s + p.in_w)) << 5) + lane];
-                        g3 = lut[(static_cast<int>(__ldg(s + p.in_w + 1)) << 5) + lane];
-                    }
-                    if (p.use_vig) {   // unMapImage: GInv[I] * vignetteMapInv (PhotometricUndistorter.cpp:205)
-                        g0 = __fmul_rn(g0, r.vi[q][0]); g1 = __fmul_rn(g1, r.vi[q][1]);
-                        g2 = __fmul_rn(g2, r.vi[q][2]); g3 = __fmul_rn(g3, r.vi[q][3]);
-                    }
-                    v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.w[q][3], g3), __fmul_rn(r.w[q][2], g2)),
-                                            __fmul_rn(r.w[q][1], g1)),
-                                  __fmul_rn(r.w[q][0], g0));
+            for (int h = 0; h < 2; ++h) {      // pixels 2h and 2h+1 ride in the two halves of packed registers
+                float t_lo[4], t_hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t v = pack2(g[2 * h][k], g[2 * h + 1][k]);
+                    if (kVig) v = mul2(v, vi2[h][k]);
+                    v = mul2(w2[h][k], v);
+                    unpack2(v, t_lo[k], t_hi[k]);
                 }
-                px[q] = v;
+                px[2 * h] = __fadd_rn(__fadd_rn(__fadd_rn(t_lo[3], t_lo[2]), t_lo[1]), t_lo[0]);
+                px[2 * h + 1] = __fadd_rn(__fadd_rn(__fadd_rn(t_hi[3], t_hi[2]), t_hi[1]), t_hi[0]);
+            }
+            if (has_black) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) px[q] = ((valid >> q) & 1u) ? px[q] : 0.0f;
             }
 
-            // ---- level 0 store (2x2 block)
-            {
-                const int ox = tx0 + 2 * bx, oy = ty0 + 2 * by;
-                float* o = p.out[0] + static_cast<size_t>(f) * n_out0 + static_cast<size_t>(oy) * p.out_w + ox;
-                if (p.vec2_ok && ox + 1 < p.out_w) {
-                    if (oy < p.out_h) *reinterpret_cast<float2*>(o) = make_float2(px[0], px[1]);
-                    if (oy + 1 < p.out_h) *reinterpret_cast<float2*>(o + p.out_w) = make_float2(px[2], px[3]);
-                } else {
-                    if (oy < p.out_h) {
-                        if (ox < p.out_w) o[0] = px[0];
-                        if (ox + 1 < p.out_w) o[1] = px[1];
-                    }
-                    if (oy + 1 < p.out_h) {
-                        if (ox < p.out_w) o[p.out_w] = px[2];
-                        if (ox + 1 < p.out_w) o[p.out_w + 1] = px[3];
-                    }
-                }
+            // ---- level 0: one full 128-byte row segment per warp store
+            if (full_tile) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stg_cs(o0 + static_cast<size_t>(q) * p.out_w, px[q]);
+            } else if (x_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (oy0 + q < p.out_h) stg_cs(o0 + static_cast<size_t>(q) * p.out_w, px[q]);
             }
+            o0 += o0_step;
 
             // ---- pyramid epilogue: dst = 0.25f*(((a+b)+c)+d), a=(2x,2y) b=(2x+1,2y) c=(2x,2y+1) d=(2x+1,2y+1)
-            if (p.levels > 1) {
-                const float l1 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(px[0], px[1]), px[2]), px[3]));
-                {
-                    const int X = (tx0 >> 1) + bx, Y = (ty0 >> 1) + by;
-                    if (X < p.lw[1] && Y < p.lh[1])
-                        p.out[1][static_cast<size_t>(f) * p.lw[1] * p.lh[1] + static_cast<size_t>(Y) * p.lw[1] + X] = l1;
+            if (kPyr) {
+                float l1[2];
+#pragma unroll
+                for (int rp = 0; rp < 2; ++rp) {
+                    const float a = px[2 * rp], c = px[2 * rp + 1];
+                    const float bb = __shfl_xor_sync(0xffffffffu, a, 1), d = __shfl_xor_sync(0xffffffffu, c, 1);
+                    l1[rp] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(a, bb), c), d));   // meaningful on even lanes
+                    const int X = (tx0 >> 1) + (lane >> 1), Y = (ty0 >> 1) + 2 * warp + rp;
+                    if ((lane & 1) == 0 && X < p.lw[1] && Y < p.lh[1])
+                        stg_cs(p.out[1] + static_cast<size_t>(f) * p.lw[1] * p.lh[1] + static_cast<size_t>(Y) * p.lw[1] + X, l1[rp]);
                 }
                 if (p.levels > 2) {
-                    // a 2x2 group of level-1 pixels lives in lanes (l, l+1, l+16, l+17) of one warp
-                    const float b = __shfl_down_sync(0xffffffffu, l1, 1);
-                    const float c = __shfl_down_sync(0xffffffffu, l1, 16);
-                    const float d = __shfl_down_sync(0xffffffffu, l1, 17);
-                    const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1, b), c), d));
-                    if (lane < 16 && (lane & 1) == 0) {
-                        const int X = (tx0 >> 2) + (bx >> 1), Y = (ty0 >> 2) + warp;
+                    const float bb = __shfl_down_sync(0xffffffffu, l1[0], 2), d = __shfl_down_sync(0xffffffffu, l1[1], 2);
+                    const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1[0], bb), l1[1]), d));   // lanes = 0 mod 4
+                    if ((lane & 3) == 0) {
+                        const int X = (tx0 >> 2) + (lane >> 2), Y = (ty0 >> 2) + warp;
                         if (X < p.lw[2] && Y < p.lh[2])
-                            p.out[2][static_cast<size_t>(f) * p.lw[2] * p.lh[2] + static_cast<size_t>(Y) * p.lw[2] + X] = l2;
-                        s_l2[warp * 8 + (bx >> 1)] = l2;
+                            stg_cs(p.out[2] + static_cast<size_t>(f) * p.lw[2] * p.lh[2] + static_cast<size_t>(Y) * p.lw[2] + X, l2);
+                        s_l2[(pyr_it & 1) * 64 + warp * 8 + (lane >> 2)] = l2;
                     }
                 }
             }
-            __syncthreads();   // (B) float tile free for the next frame; level-2 hand-off visible
-            if (kTma && mode == TILE_STAGED) ++it;   // one mbarrier phase consumed
-            if (p.levels > 3 && warp == 0) {
+            if (!kTma && staged) {
+                if (f + 1 < f_end) sts_box(st_addr);   // st_addr already points at the next frame's stage
+                consumer_barrier();     // next stage published; everybody done reading the current one; level-2 hand-off visible
+            } else if (kPyr && p.levels > 3) {
+                consumer_barrier();     // level-2 hand-off visible to warp 0
+            }
+            if (kPyr && p.levels > 3 && warp == 0) {
                 float l3 = 0.0f;
                 if (lane < 16) {
                     const int X = lane & 3, Y = lane >> 2;
-                    const float* s = s_l2 + (2 * Y) * 8 + 2 * X;
+                    const float* s = s_l2 + (pyr_it & 1) * 64 + (2 * Y) * 8 + 2 * X;
                     l3 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), s[8]), s[9]));
                     const int GX = (tx0 >> 3) + X, GY = (ty0 >> 3) + Y;
                     if (GX < p.lw[3] && GY < p.lh[3])
-                        p.out[3][static_cast<size_t>(f) * p.lw[3] * p.lh[3] + static_cast<size_t>(GY) * p.lw[3] + GX] = l3;
+                        stg_cs(p.out[3] + static_cast<size_t>(f) * p.lw[3] * p.lh[3] + static_cast<size_t>(GY) * p.lw[3] + GX, l3);
                 }
                 if (p.levels > 4) {
-                    const float b = __shfl_down_sync(0xffffffffu, l3, 1);
+                    const float bb = __shfl_down_sync(0xffffffffu, l3, 1);
                     const float c = __shfl_down_sync(0xffffffffu, l3, 4);
                     const float d = __shfl_down_sync(0xffffffffu, l3, 5);
-                    const float l4 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l3, b), c), d));
+                    const float l4 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l3, bb), c), d));
                     if (lane < 16 && (lane & 1) == 0 && (lane & 4) == 0) {
                         const int GX = (tx0 >> 4) + ((lane & 3) >> 1), GY = (ty0 >> 4) + (lane >> 3);
                         if (GX < p.lw[4] && GY < p.lh[4])
-                            p.out[4][static_cast<size_t>(f) * p.lw[4] * p.lh[4] + static_cast<size_t>(GY) * p.lw[4] + GX] = l4;
+                            stg_cs(p.out[4] + static_cast<size_t>(f) * p.lw[4] * p.lh[4] + static_cast<size_t>(GY) * p.lw[4] + GX, l4);
                     }
                 }
             }
+            ++pyr_it;
         }
     }
 }
 
-// smem layout (bytes): lut 32768 | ftile 4*box | s_l2 256 | sched 16 | bars 8*kStages | pad to 128 | stages
+// smem layout (bytes): lut 32768 | s_l2 512 | sched 32 | barriers 8*2*kMaxStages | pad -> kSmemHeaderBytes | stages
 size_t fused_smem_bytes(int box_px_max, bool tma) {
-    size_t b = 256u * 32u * 4u + static_cast<size_t>(box_px_max) * 4u + 64u * 4u + 16u + 8u * kStages;
-    b = (b + 127u) & ~static_cast<size_t>(127u);
-    if (tma) b += static_cast<size_t>(kStages) * ((static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u));
-    return b;
+    const size_t stage = (static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u);
+    return kSmemHeaderBytes + static_cast<size_t>(tma ? kTmaStages : kLdgStages) * stage;
 }
 
-int fused_max_ctas_per_sm(int box_px_max, bool tma) {
+typedef void (*FusedKernelFn)(const FusedParams, const TmaMaps);
+static FusedKernelFn fused_variant(bool tma, bool vig, bool pyr) {
+    if (tma) {
+        if (vig) return pyr ? fused_prepare_kernel<true, true, true> : fused_prepare_kernel<true, true, false>;
+        return pyr ? fused_prepare_kernel<true, false, true> : fused_prepare_kernel<true, false, false>;
+    }
+    if (vig) return pyr ? fused_prepare_kernel<false, true, true> : fused_prepare_kernel<false, true, false>;
+    return pyr ? fused_prepare_kernel<false, false, true> : fused_prepare_kernel<false, false, false>;
+}
+
+int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr) {
     int n = 0;
     const int smem = static_cast<int>(fused_smem_bytes(box_px_max, tma));
+    FusedKernelFn fn = fused_variant(tma, vig, pyr);
     // the opt-in limit must be raised before the occupancy query, or it reports 0 for > 48 KB
-    cudaError_t e = tma ? cudaFuncSetAttribute(fused_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                        : cudaFuncSetAttribute(fused_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return 0;
-    e = tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_prepare_kernel<true>, kThreads, smem)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_prepare_kernel<false>, kThreads, smem);
-    return e == cudaSuccess ? n : 0;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tma ? kConsumers + 32 : kConsumers, smem) != cudaSuccess) return 0;
+    return n;
 }
 
 cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, cudaStream_t stream) {
     const bool tma = maps != nullptr;
     const size_t smem = fused_smem_bytes(p.box_px_max, tma);
-    cudaError_t e;
-    if (tma) {
-        e = cudaFuncSetAttribute(fused_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        fused_prepare_kernel<true><<<grid, kThreads, smem, stream>>>(p, *maps);
-    } else {
-        static const TmaMaps none = {};
-        e = cudaFuncSetAttribute(fused_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        fused_prepare_kernel<false><<<grid, kThreads, smem, stream>>>(p, none);
-    }
+    FusedKernelFn fn = fused_variant(tma, p.use_vig != 0, p.levels > 1);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    static const TmaMaps none = {};
+    fn<<<grid, tma ? kConsumers + 32 : kConsumers, smem, stream>>>(p, tma ? *maps : none);
     return cudaGetLastError();
 }
 

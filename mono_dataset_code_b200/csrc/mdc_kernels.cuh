@@ -10,21 +10,25 @@
 namespace mdc {
 
 constexpr int kTile = 32;            // output tile edge (pixels); pyramid levels 0..4 close inside a tile
-constexpr int kThreads = 256;        // 16 x 16 threads, each owning a 2x2 block of output pixels
+constexpr int kConsumers = 256;      // 8 consumer warps; warp w owns tile rows 4w..4w+3, lane = x
+constexpr int kThreads = kConsumers;
 constexpr int kInKernelLevels = 5;   // levels 0..4 are produced by the fused kernel's epilogue
 constexpr int kMaxBoxWordsPerThread = 8;   // LDG loader: u32 words of the input box prefetched per thread
 constexpr int kMaxBoxPx = kMaxBoxWordsPerThread * 4 * kThreads;  // 8192 px: larger boxes use the direct path
-constexpr int kStages = 2;           // TMA loader: u8 box stages in flight
+constexpr int kTmaStages = 3;         // TMA loader: u8 box stages in the full/empty mbarrier ring
+constexpr int kLdgStages = 2;         // LDG loader: double buffer
+constexpr int kMaxStages = 4;
+constexpr int kSmemHeaderBytes = 33536;   // lut 32768 + s_l2 512 + sched 32 + barriers 64, rounded up to 128
 constexpr int kMaxClasses = 48;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
 
 // How a tile's input pixels are fetched.
-enum TileMode : int { TILE_EMPTY = 0, TILE_STAGED = 1, TILE_DIRECT = 2 };
+enum TileMode : int { TILE_EMPTY = 0, TILE_STAGED = 1, TILE_DIRECT = 2, TILE_HAS_BLACK = 0x10 /* flag */ };
 
 // One output tile of the rectification plan (built once per context from the remap tables).
 struct alignas(16) TileDesc {
-    int x0, y0;        // origin of the input bounding box (x0 is a multiple of 16)
+    int x0, y0;        // origin of the input bounding box (x0 is a multiple of 4)
     int bw_bh;         // box width (multiple of 16, also the smem pitch) | box height << 16
-    int mode_map;      // TileMode | (tensor-map class index << 8) | (TMA box height << 16)
+    int mode_map;      // TileMode (low nibble) | TILE_HAS_BLACK | (tensor-map class index << 8) | (TMA box height << 16)
 };
 
 // TMA descriptors of one launch: one 3-D u8 tensor map per box class, passed by value as a
@@ -49,12 +53,12 @@ struct FusedParams {
     int levels;                  // 1..kInKernelLevels
     unsigned lut_gamma, use_vig, kill;   // sanitised unMapImage flags
     int box_px_max;              // largest staged box (pixels) -> smem carve-up
-    int vec2_ok;                 // level-0 rows can be written with 8-byte stores
+    int chunk_frames;            // frames per schedule chunk (L2 residency of the inputs)
 };
 
 size_t fused_smem_bytes(int box_px_max, bool tma);
 cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, cudaStream_t stream);  // maps == nullptr: LDG loader
-int fused_max_ctas_per_sm(int box_px_max, bool tma);
+int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr);
 
 cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, const float* ginv, const float* vinv,
                          unsigned kill, cudaStream_t stream);
