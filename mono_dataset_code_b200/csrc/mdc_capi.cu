@@ -133,7 +133,7 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
             // defensive: a table that violates the reference's in-bounds guarantee would read outside the frame
             xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
             xhi = std::min(xhi, W - 1); yhi = std::min(yhi, H - 1);
-            const int x0 = xlo & ~3;
+            const int x0 = tma_geom_ok ? (xlo & ~15) : (xlo & ~3);   // TMA faults on box origins that are not 16-byte aligned
             const int bw = ((xhi - x0 + 1) + 15) & ~15;
             const int bh = yhi - ylo + 1, bh8 = (bh + gran - 1) / gran * gran;
             int lg = 2;
