@@ -269,12 +269,13 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
         int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
         if (rc != MDC_OK) return rc;
     }
-    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma, u.vig, in_kernel > 1);
+    const int min_ctas = (c->ctas_per_sm > 0 && c->ctas_per_sm <= 2) ? 2 : 3;   // which register budget the kernel was compiled for
+    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma, u.vig, in_kernel > 1, min_ctas);
     if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
     if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
     long long units = static_cast<long long>(p.n_tiles) * n_frames;
     int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(units, 1)));
-    CU_CHECK(launch_fused(p, maps, grid, stream));
+    CU_CHECK(launch_fused(p, maps, grid, min_ctas, stream));
     c->launches++;
     // levels beyond the fused epilogue: stand-alone K2 chain
     for (int l = in_kernel; l < levels; ++l) {

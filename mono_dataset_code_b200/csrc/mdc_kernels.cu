@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "mdc_kernels.cuh"
 
 namespace mdc {
@@ -73,6 +75,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+// Producer-side wait: the producer is always up to kTmaStages frames ahead, so it polls politely
+// (a spinning lane would steal issue slots from the consumer warps of its scheduler).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(2000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(100);
+    }
 }
 // 3-D tiled TMA load: box (bw, bh, 1) of the u8 frame stack at (x, y, frame) -> shared memory.
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int frame) {
@@ -177,8 +197,8 @@ struct SegmentIter {
     }
 };
 
-template <bool kTma, bool kVig, bool kPyr>
-__global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, 3)
+template <bool kTma, bool kVig, bool kPyr, int kMinCtas>
+__global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, kMinCtas)
 fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TmaMaps maps) {
     constexpr int kNs = kTma ? kTmaStages : kLdgStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -221,7 +241,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                 const CUtensorMap* tmap = &maps.m[(td.mode_map >> 8) & 0xff];
                 const uint32_t bytes = static_cast<uint32_t>(td.bw_bh & 0xffff) * static_cast<uint32_t>(td.mode_map >> 16);
                 for (int f = f_begin; f < f_end; ++f) {
-                    if (round > 0) mbar_wait(bar_empty + 8u * st, (round - 1u) & 1u);   // consumers released this slot
+                    if (round > 0) mbar_wait_backoff(bar_empty + 8u * st, (round - 1u) & 1u);   // consumers released this slot
                     mbar_expect_tx(bar_full + 8u * st, bytes);
                     tma_load_box(stage0 + st * stage_bytes, tmap, bar_full + 8u * st, td.x0, td.y0, f);
                     if (++st == static_cast<uint32_t>(kNs)) { st = 0; ++round; }
@@ -341,10 +361,12 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         const size_t o0_step = static_cast<size_t>(p.lw[0]) * p.lh[0];
         const bool x_ok = ox < p.out_w;
 
-        // ------------------------------------------------------------ frame loop
+        // ------------------------------------------------------------ frame loop, specialised on how the taps are fetched
+        auto run_frames = [&](auto staged_c) {
+        constexpr bool kStaged = decltype(staged_c)::value;
         for (int f = f_begin; f < f_end; ++f) {
             uint32_t b[4][4];
-            if (staged) {
+            if (kStaged) {
                 if (kTma) mbar_wait(bar_full + 8u * st, phase);
                 else if (f + 1 < f_end) ldg_box(f + 1);          // in flight during the gather below
                 const uint32_t base = st_addr;
@@ -368,7 +390,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) g[q][k] = lds_f32(lut_lane + (b[q][k] << 7));
-            if (staged) {
+            if (kStaged) {
                 if (kTma) {          // all tap bytes of this warp are in registers: hand the stage back to the producer
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_empty + 8u * st);
@@ -431,7 +453,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                     }
                 }
             }
-            if (!kTma && staged) {
+            if (!kTma && kStaged) {
                 if (f + 1 < f_end) sts_box(st_addr);   // st_addr already points at the next frame's stage
                 consumer_barrier();     // next stage published; everybody done reading the current one; level-2 hand-off visible
             } else if (kPyr && p.levels > 3) {
@@ -461,6 +483,8 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             }
             ++pyr_it;
         }
+        };
+        if (staged) run_frames(std::true_type{}); else run_frames(std::false_type{});
     }
 }
 
@@ -471,29 +495,33 @@ size_t fused_smem_bytes(int box_px_max, bool tma) {
 }
 
 typedef void (*FusedKernelFn)(const FusedParams, const TmaMaps);
-static FusedKernelFn fused_variant(bool tma, bool vig, bool pyr) {
+template <int kMinCtas>
+static FusedKernelFn fused_variant_t(bool tma, bool vig, bool pyr) {
     if (tma) {
-        if (vig) return pyr ? fused_prepare_kernel<true, true, true> : fused_prepare_kernel<true, true, false>;
-        return pyr ? fused_prepare_kernel<true, false, true> : fused_prepare_kernel<true, false, false>;
+        if (vig) return pyr ? fused_prepare_kernel<true, true, true, kMinCtas> : fused_prepare_kernel<true, true, false, kMinCtas>;
+        return pyr ? fused_prepare_kernel<true, false, true, kMinCtas> : fused_prepare_kernel<true, false, false, kMinCtas>;
     }
-    if (vig) return pyr ? fused_prepare_kernel<false, true, true> : fused_prepare_kernel<false, true, false>;
-    return pyr ? fused_prepare_kernel<false, false, true> : fused_prepare_kernel<false, false, false>;
+    if (vig) return pyr ? fused_prepare_kernel<false, true, true, kMinCtas> : fused_prepare_kernel<false, true, false, kMinCtas>;
+    return pyr ? fused_prepare_kernel<false, false, true, kMinCtas> : fused_prepare_kernel<false, false, false, kMinCtas>;
+}
+static FusedKernelFn fused_variant(bool tma, bool vig, bool pyr, int min_ctas) {
+    return min_ctas <= 2 ? fused_variant_t<2>(tma, vig, pyr) : fused_variant_t<3>(tma, vig, pyr);
 }
 
-int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr) {
+int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr, int min_ctas) {
     int n = 0;
     const int smem = static_cast<int>(fused_smem_bytes(box_px_max, tma));
-    FusedKernelFn fn = fused_variant(tma, vig, pyr);
+    FusedKernelFn fn = fused_variant(tma, vig, pyr, min_ctas);
     // the opt-in limit must be raised before the occupancy query, or it reports 0 for > 48 KB
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, tma ? kConsumers + 32 : kConsumers, smem) != cudaSuccess) return 0;
     return n;
 }
 
-cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, cudaStream_t stream) {
+cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, int min_ctas, cudaStream_t stream) {
     const bool tma = maps != nullptr;
     const size_t smem = fused_smem_bytes(p.box_px_max, tma);
-    FusedKernelFn fn = fused_variant(tma, p.use_vig != 0, p.levels > 1);
+    FusedKernelFn fn = fused_variant(tma, p.use_vig != 0, p.levels > 1, min_ctas);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     static const TmaMaps none = {};

@@ -57,8 +57,8 @@ struct FusedParams {
 };
 
 size_t fused_smem_bytes(int box_px_max, bool tma);
-cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, cudaStream_t stream);  // maps == nullptr: LDG loader
-int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr);
+cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, int min_ctas, cudaStream_t stream);  // maps == nullptr: LDG loader
+int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr, int min_ctas);
 
 cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, const float* ginv, const float* vinv,
                          unsigned kill, cudaStream_t stream);
