@@ -47,6 +47,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 constexpr int kMapSlots = 8;        // host-side cache of encoded descriptor sets, keyed by (frames ptr, n_frames)
 constexpr int kHostPipeDepth = 3;   // host-buffer pipeline: chunks in flight
+constexpr int kCounterRing = 64;
 constexpr int kMaxStagedPx = 8192;  // largest staged box (pixels, height rounded to 8): 32 KB float tile
 
 }  // namespace
@@ -66,6 +67,8 @@ struct mdc_ctx {
     bool plan_tma_ok = false;
     TileDesc* d_tiles = nullptr;
     uint32_t* d_cost_prefix = nullptr;
+    int* d_counters = nullptr;   // ring of work counters (one per launch in flight)
+    unsigned counter_next = 0;
     // TMA descriptor cache (host memory; descriptors are passed to the kernel by value)
     TmaMaps* maps[kMapSlots] = {};
     const void* map_key_ptr[kMapSlots] = {};
@@ -110,6 +113,8 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 0;       // per 4 staged input bytes (free with TMA)
     const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 8;     // per output pixel (taps + LUT + blend + store)
     const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 16;
+    int pitch_align = (e = getenv("MDC_BOX_PITCH")) ? atoi(e) : 16;   // 128 was measured slower: the wider TMA boxes cost more shared-memory write bandwidth than the conflicts they remove
+    if (pitch_align != 16 && pitch_align != 32 && pitch_align != 64 && pitch_align != 128) pitch_align = 16;
     // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
     for (int gran = 8; gran <= 256; gran *= 2) {
     c->classes.clear();
@@ -134,7 +139,10 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
             xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
             xhi = std::min(xhi, W - 1); yhi = std::min(yhi, H - 1);
             const int x0 = tma_geom_ok ? (xlo & ~15) : (xlo & ~3);   // TMA faults on box origins that are not 16-byte aligned
-            const int bw = ((xhi - x0 + 1) + 15) & ~15;
+            // Box width = shared-memory pitch.  With a pitch of 128 bytes (32 banks x 4) the bank of a tap depends on x
+            // only, so the 32 lanes of a warp — one output row, < 128 input bytes wide — never conflict however the
+            // row curves through input rows.  MDC_BOX_PITCH=16 restores the tight (conflict-prone) packing.
+            const int bw = ((xhi - x0 + 1) + pitch_align - 1) / pitch_align * pitch_align;
             const int bh = yhi - ylo + 1, bh8 = (bh + gran - 1) / gran * gran;
             int lg = 2;
             while ((4 << lg) < bw) ++lg;
@@ -186,6 +194,7 @@ int ctx_common_init(mdc_ctx* c, int device) {
     CU_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
     c->sm_count = v;
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_CHECK(cudaMalloc(&c->d_counters, kCounterRing * sizeof(int)));
     const char* e = getenv("MDC_USE_TMA");
     if (e) c->use_tma = atoi(e);
     e = getenv("MDC_CTAS_PER_SM");
@@ -253,7 +262,9 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     p.frames = d_frames; p.n_frames = n_frames;
     p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h;
     p.remap_x = c->d_rx; p.remap_y = c->d_ry; p.vinv = c->d_vinv; p.ginv = c->d_ginv;
-    p.tiles = c->d_tiles; p.tile_cost_prefix = c->d_cost_prefix;
+    p.tiles = c->d_tiles;
+    p.work_counter = c->d_counters + (c->counter_next++ % kCounterRing);
+    CU_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
     p.tiles_x = c->tiles_x; p.n_tiles = static_cast<int>(c->tiles.size());
     const int in_kernel = std::min(levels, kInKernelLevels);
     p.levels = in_kernel;
@@ -273,8 +284,8 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma, u.vig, in_kernel > 1, min_ctas);
     if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
     if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
-    long long units = static_cast<long long>(p.n_tiles) * n_frames;
-    int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(units, 1)));
+    const long long items = static_cast<long long>(p.n_tiles) * ((n_frames + p.chunk_frames - 1) / p.chunk_frames);
+    int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(items, 1)));
     CU_CHECK(launch_fused(p, maps, grid, min_ctas, stream));
     c->launches++;
     // levels beyond the fused epilogue: stand-alone K2 chain
@@ -375,7 +386,7 @@ extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->owns_tables) { cudaFree(c->d_rx); cudaFree(c->d_ry); cudaFree(c->d_ginv); cudaFree(c->d_vinv); }
-    cudaFree(c->d_tiles); cudaFree(c->d_cost_prefix);
+    cudaFree(c->d_tiles); cudaFree(c->d_cost_prefix); cudaFree(c->d_counters);
     for (int s = 0; s < kMapSlots; ++s) free(c->maps[s]);
     for (int s = 0; s < kHostPipeDepth; ++s) {
         if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }

@@ -116,12 +116,12 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 //
 // Work decomposition.  The output image is cut into 32x32 tiles; a tile's bilinear taps fall into a
 // compact bounding box of the input image (host-precomputed, TileDesc).  The unit of work is
-// (tile, frame).  Frames are grouped into chunks of `chunk_frames`; units are ordered
-// chunk-major, then tile-major, then by frame, and this order is cut into gridDim.x contiguous,
-// cost-balanced ranges, one per persistent CTA.  So a CTA works through a few tiles per chunk and, for
-// each, loops over a run of consecutive frames — while, chip-wide, all CTAs are inside the same
-// chunk at the same time, which keeps that chunk's input frames (and the 15.7 MB of tables) resident
-// in the 126 MB L2 although neighbouring tiles re-read overlapping parts of them.
+// (tile, frame).  Frames are grouped into chunks of `chunk_frames`; a work ITEM is (chunk, tile) — one
+// tile over the consecutive frames of one chunk — and items are numbered chunk-major, tile-minor.
+// Persistent CTAs pull items from a global atomic counter (first item = blockIdx.x), so the load
+// balances itself whatever the per-tile cost, and, chip-wide, all CTAs are inside the same chunk at
+// the same time, which keeps that chunk's input frames (and the 15.7 MB of tables) resident in the
+// 126 MB L2 although neighbouring tiles re-read overlapping parts of them.
 //
 // Everything that depends only on the calibration — the remap entry of each of the thread's 4 pixels
 // (turned into 4 bilinear weights and a box-local byte offset) and the 4 vignette reciprocals under
@@ -143,59 +143,11 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 // `killOverexposed` is folded into the LUT (lut[255]=NaN) and the no-gamma modes use an identity LUT,
 // so one kernel covers all flag combinations as well as undistort<unsigned char>.
 
-struct WorkPos { int chunk, tile, frame; };
-
 __device__ __forceinline__ float lut_value(const FusedParams& p, int v) {
     float r = p.lut_gamma ? __ldg(p.ginv + v) : static_cast<float>(v);
     if (p.kill && v == 255) r = __int_as_float(0x7fc00000);  // NAN
     return r;
 }
-
-// (chunk, tile, frame-in-chunk) at work position `pos` (cost units) of the chunk/tile-major unit order
-__device__ WorkPos locate_unit(const FusedParams& p, unsigned long long pos) {
-    const unsigned long long ct = p.tile_cost_prefix[p.n_tiles];
-    const unsigned long long total = ct * static_cast<unsigned long long>(p.n_frames);
-    const int n_chunks = (p.n_frames + p.chunk_frames - 1) / p.chunk_frames;
-    WorkPos w;
-    if (pos >= total) { w.chunk = n_chunks; w.tile = 0; w.frame = 0; return w; }
-    const unsigned long long per_chunk = ct * static_cast<unsigned long long>(p.chunk_frames);
-    w.chunk = static_cast<int>(pos / per_chunk);
-    const unsigned long long rem = pos - per_chunk * w.chunk;
-    const unsigned long long fk = static_cast<unsigned long long>(min(p.chunk_frames, p.n_frames - w.chunk * p.chunk_frames));
-    int lo = 0, hi = p.n_tiles;  // invariant: prefix[lo]*fk <= rem < prefix[hi]*fk
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (static_cast<unsigned long long>(p.tile_cost_prefix[mid]) * fk <= rem) lo = mid; else hi = mid;
-    }
-    const unsigned long long wt = p.tile_cost_prefix[lo + 1] - p.tile_cost_prefix[lo];
-    w.tile = lo;
-    w.frame = static_cast<int>((rem - static_cast<unsigned long long>(p.tile_cost_prefix[lo]) * fk) / wt);
-    return w;
-}
-
-// Iterates the segments (tile, global frame range) of the CTA's work range in order.  Kept to three
-// registers of state (the end position is re-read from shared memory once per segment) because it is
-// live across the register-critical frame loop.
-struct SegmentIter {
-    int k, t, fb;   // current chunk, next tile, first frame (in chunk) of the next segment
-    __device__ __forceinline__ void init(const int* sched) { k = sched[0]; t = sched[1]; fb = sched[2]; }
-    // next non-empty segment; false when the range is exhausted
-    __device__ __forceinline__ bool next(const FusedParams& p, const int* sched, int& tile, int& f0, int& f1) {
-        const int e_chunk = sched[3], e_tile = sched[4], e_frame = sched[5];
-        const int n_chunks = (p.n_frames + p.chunk_frames - 1) / p.chunk_frames;
-        for (;;) {
-            if (k >= n_chunks || k > e_chunk) return false;
-            const int t_last = (k == e_chunk) ? e_tile : p.n_tiles - 1;
-            if (t > t_last || t >= p.n_tiles) { ++k; t = 0; fb = 0; continue; }
-            const int base = k * p.chunk_frames, fk = min(p.chunk_frames, p.n_frames - base);
-            const int fe = (k == e_chunk && t == e_tile) ? e_frame : fk;
-            const int first = fb;
-            tile = t; f0 = base + first; f1 = base + fe;
-            ++t; fb = 0;
-            if (first < fe) return true;
-        }
-    }
-};
 
 template <bool kTma, bool kVig, bool kPyr, int kMinCtas>
 __global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, kMinCtas)
@@ -205,47 +157,53 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     // ---- shared-memory carve-up (see fused_smem_bytes)
     float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
     float* s_l2 = lut + 256 * 32;                                       // [2][64] pyramid level-2 hand-off (double-buffered)
-    int* s_sched = reinterpret_cast<int*>(s_l2 + 128);                  // [8] begin / end work positions
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sched + 8);         // [2*kMaxStages] full[], empty[]
+    volatile int* s_item = reinterpret_cast<volatile int*>(s_l2 + 128); // [kItemSlots] work items handed from the producer to the consumers
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_l2 + 128 + 8);      // full[kMaxStages] empty[kMaxStages] item_full[kItemSlots] item_empty[kItemSlots]
     const uint32_t stage_bytes = (static_cast<uint32_t>(p.box_px_max) + 127u) & ~127u;
     const uint32_t stage0 = smem_u32(smem_raw) + kSmemHeaderBytes;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8u * kMaxStages;
+    const uint32_t bar_item_full = bar_empty + 8u * kMaxStages, bar_item_empty = bar_item_full + 8u * kItemSlots;
+    const int n_items = ((p.n_frames + p.chunk_frames - 1) / p.chunk_frames) * p.n_tiles;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- one-time per CTA: LUT, barriers, work range
     for (int i = tid; i < 256 * 32; i += blockDim.x) lut[i] = lut_value(p, i >> 5);
-    if (tid == 0) {
-        const unsigned long long total = static_cast<unsigned long long>(p.tile_cost_prefix[p.n_tiles]) * static_cast<unsigned long long>(p.n_frames);
-        const WorkPos b = locate_unit(p, total * blockIdx.x / gridDim.x);
-        const WorkPos e = locate_unit(p, total * (blockIdx.x + 1ull) / gridDim.x);
-        s_sched[0] = b.chunk; s_sched[1] = b.tile; s_sched[2] = b.frame;
-        s_sched[3] = e.chunk; s_sched[4] = e.tile; s_sched[5] = e.frame;
-        if (kTma) {
-            for (int s = 0; s < kNs; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, kConsumers / 32); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    if (tid == 0 && kTma) {
+        for (int i = 0; i < kNs; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, kConsumers / 32); }
+        for (int i = 0; i < kItemSlots; ++i) { mbar_init(bar_item_full + 8u * i, 1); mbar_init(bar_item_empty + 8u * i, kConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    SegmentIter seg;
-    seg.init(s_sched);
     int tile, f_begin, f_end;
 
     // ================================================================ producer warp (TMA loader only)
     if (kTma && warp == kConsumers / 32) {
         if (lane == 0) {
-            uint32_t st = 0, round = 0;   // ring position of the next staged frame to issue
-            while (seg.next(p, s_sched, tile, f_begin, f_end)) {
+            uint32_t st = 0, round = 0;        // stage ring position of the next frame to issue
+            uint32_t islot = 0, iround = 0;    // item ring position
+            int item = blockIdx.x;
+            for (;;) {
+                if (iround > 0) mbar_wait_backoff(bar_item_empty + 8u * islot, (iround - 1u) & 1u);
+                s_item[islot] = item;
+                mbar_arrive(bar_item_full + 8u * islot);      // release: the item id is visible to whoever sees this phase complete
+                if (++islot == static_cast<uint32_t>(kItemSlots)) { islot = 0; ++iround; }
+                if (item >= n_items) break;
+                tile = item % p.n_tiles;
+                f_begin = (item / p.n_tiles) * p.chunk_frames;
+                f_end = min(f_begin + p.chunk_frames, p.n_frames);
                 const TileDesc td = p.tiles[tile];
-                if ((td.mode_map & 0x0f) != TILE_STAGED) continue;
-                const CUtensorMap* tmap = &maps.m[(td.mode_map >> 8) & 0xff];
-                const uint32_t bytes = static_cast<uint32_t>(td.bw_bh & 0xffff) * static_cast<uint32_t>(td.mode_map >> 16);
-                for (int f = f_begin; f < f_end; ++f) {
-                    if (round > 0) mbar_wait_backoff(bar_empty + 8u * st, (round - 1u) & 1u);   // consumers released this slot
-                    mbar_expect_tx(bar_full + 8u * st, bytes);
-                    tma_load_box(stage0 + st * stage_bytes, tmap, bar_full + 8u * st, td.x0, td.y0, f);
-                    if (++st == static_cast<uint32_t>(kNs)) { st = 0; ++round; }
+                if ((td.mode_map & 0x0f) == TILE_STAGED) {
+                    const CUtensorMap* tmap = &maps.m[(td.mode_map >> 8) & 0xff];
+                    const uint32_t bytes = static_cast<uint32_t>(td.bw_bh & 0xffff) * static_cast<uint32_t>(td.mode_map >> 16);
+                    for (int f = f_begin; f < f_end; ++f) {
+                        if (round > 0) mbar_wait_backoff(bar_empty + 8u * st, (round - 1u) & 1u);   // consumers released this slot
+                        mbar_expect_tx(bar_full + 8u * st, bytes);
+                        tma_load_box(stage0 + st * stage_bytes, tmap, bar_full + 8u * st, td.x0, td.y0, f);
+                        if (++st == static_cast<uint32_t>(kNs)) { st = 0; ++round; }
+                    }
                 }
+                item = static_cast<int>(gridDim.x) + atomicAdd(p.work_counter, 1);
             }
         }
         return;
@@ -257,8 +215,21 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     uint32_t st = 0, phase = 0;   // ring position / parity of the next staged frame to consume
     uint32_t st_addr = stage0;    // = stage0 + st * stage_bytes
     uint32_t pyr_it = 0;   // frames processed so far (parity selects the level-2 hand-off buffer)
+    uint32_t islot = 0, iphase = 0;
+    int item = blockIdx.x;
 
-    while (seg.next(p, s_sched, tile, f_begin, f_end)) {
+    for (;;) {
+        if (kTma) {          // next item from the producer warp
+            mbar_wait(bar_item_full + 8u * islot, iphase);
+            item = s_item[islot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_item_empty + 8u * islot);
+            if (++islot == static_cast<uint32_t>(kItemSlots)) { islot = 0; iphase ^= 1u; }
+        }
+        if (item >= n_items) break;
+        tile = item % p.n_tiles;
+        f_begin = (item / p.n_tiles) * p.chunk_frames;
+        f_end = min(f_begin + p.chunk_frames, p.n_frames);
         // ------------------------------------------------------------ per-(tile, run) prologue
         const TileDesc td = p.tiles[tile];
         const int mode = td.mode_map & 0x0f;
@@ -485,10 +456,16 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         }
         };
         if (staged) run_frames(std::true_type{}); else run_frames(std::false_type{});
+        if (!kTma) {         // LDG loader: thread 0 pulls the next item for the whole CTA
+            consumer_barrier();
+            if (tid == 0) s_item[0] = static_cast<int>(gridDim.x) + atomicAdd(p.work_counter, 1);
+            consumer_barrier();
+            item = s_item[0];
+        }
     }
 }
 
-// smem layout (bytes): lut 32768 | s_l2 512 | sched 32 | barriers 8*2*kMaxStages | pad -> kSmemHeaderBytes | stages
+// smem layout (bytes): lut 32768 | s_l2 512 | items 32 | barriers 8*(2*kMaxStages+2*kItemSlots) | pad -> kSmemHeaderBytes | stages
 size_t fused_smem_bytes(int box_px_max, bool tma) {
     const size_t stage = (static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u);
     return kSmemHeaderBytes + static_cast<size_t>(tma ? kTmaStages : kLdgStages) * stage;

@@ -18,6 +18,7 @@ constexpr int kMaxBoxPx = kMaxBoxWordsPerThread * 4 * kThreads;  // 8192 px: lar
 constexpr int kTmaStages = 3;         // TMA loader: u8 box stages in the full/empty mbarrier ring
 constexpr int kLdgStages = 2;         // LDG loader: double buffer
 constexpr int kMaxStages = 4;
+constexpr int kItemSlots = 4;          // work items in flight between the producer warp and the consumers
 constexpr int kSmemHeaderBytes = 33536;   // lut 32768 + s_l2 512 + sched 32 + barriers 64, rounded up to 128
 constexpr int kMaxClasses = 48;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
 
@@ -46,7 +47,7 @@ struct FusedParams {
     const float* vinv;           // [in_w*in_h] or nullptr
     const float* ginv;           // [256] or nullptr
     const TileDesc* tiles;       // [tiles_x*tiles_y]
-    const uint32_t* tile_cost_prefix;  // [n_tiles+1] exclusive prefix sum of per-frame tile costs
+    int* work_counter;           // zeroed before the launch; item = gridDim.x + atomicAdd(work_counter, 1)
     int tiles_x, n_tiles;
     float* out[MDC_MAX_PYR_LEVELS];
     int lw[MDC_MAX_PYR_LEVELS], lh[MDC_MAX_PYR_LEVELS];
