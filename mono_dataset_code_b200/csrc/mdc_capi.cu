@@ -113,8 +113,7 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 0;       // per 4 staged input bytes (free with TMA)
     const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 8;     // per output pixel (taps + LUT + blend + store)
     const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 16;
-    int pitch_align = (e = getenv("MDC_BOX_PITCH")) ? atoi(e) : 16;   // 128 was measured slower: the wider TMA boxes cost more shared-memory write bandwidth than the conflicts they remove
-    if (pitch_align != 16 && pitch_align != 32 && pitch_align != 64 && pitch_align != 128) pitch_align = 16;
+    const bool pitch_search = (e = getenv("MDC_PITCH_SEARCH")) ? atoi(e) != 0 : true;
     // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
     for (int gran = 8; gran <= 256; gran *= 2) {
     c->classes.clear();
@@ -139,11 +138,43 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
             xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
             xhi = std::min(xhi, W - 1); yhi = std::min(yhi, H - 1);
             const int x0 = tma_geom_ok ? (xlo & ~15) : (xlo & ~3);   // TMA faults on box origins that are not 16-byte aligned
-            // Box width = shared-memory pitch.  With a pitch of 128 bytes (32 banks x 4) the bank of a tap depends on x
-            // only, so the 32 lanes of a warp — one output row, < 128 input bytes wide — never conflict however the
-            // row curves through input rows.  MDC_BOX_PITCH=16 restores the tight (conflict-prone) packing.
-            const int bw = ((xhi - x0 + 1) + pitch_align - 1) / pitch_align * pitch_align;
             const int bh = yhi - ylo + 1, bh8 = (bh + gran - 1) / gran * gran;
+            // Box width = shared-memory pitch of the staged box.  The tap loads of a warp (32 lanes = one output
+            // row, 4 byte taps each) are a fixed, calibration-dependent access pattern, so their bank conflicts
+            // can be SIMULATED here, per tile and per candidate pitch, and traded against the extra bytes TMA has to
+            // write for a wider box.  Picks the pitch with the fewest shared-memory wavefronts per frame.
+            const int bw_min = ((xhi - x0 + 1) + 15) & ~15;
+            int bw = bw_min;
+            if (pitch_search) {
+                long best_cost = -1;
+                for (int pitch = bw_min; pitch <= std::min(bw_min + 112, 256); pitch += 16) {
+                    if (pitch * bh8 > kMaxStagedPx) break;
+                    long wavefronts = 0;
+                    for (int y = ty0; y < std::min(ty0 + kTile, OH); ++y) {
+                        int offs[kTile];
+                        int nl = 0;
+                        for (int x = tx0; x < std::min(tx0 + kTile, OW); ++x) {
+                            const float sx = rx[static_cast<size_t>(y) * OW + x], sy = ry[static_cast<size_t>(y) * OW + x];
+                            offs[nl++] = (sx < 0) ? 0 : (static_cast<int>(sy) - ylo) * pitch + (static_cast<int>(sx) - x0);
+                        }
+                        const int delta[4] = {0, 1, pitch, pitch + 1};
+                        for (int d = 0; d < 4; ++d) {
+                            int words[32][4], cnt[32];
+                            for (int b = 0; b < 32; ++b) cnt[b] = 0;
+                            int worst = 1;
+                            for (int l = 0; l < nl; ++l) {
+                                const int w = (offs[l] + delta[d]) >> 2, b = w & 31;
+                                bool seen = false;
+                                for (int i = 0; i < cnt[b] && i < 4; ++i) seen |= (words[b][i] == w);
+                                if (!seen) { if (cnt[b] < 4) words[b][cnt[b]] = w; ++cnt[b]; worst = std::max(worst, cnt[b]); }
+                            }
+                            wavefronts += worst;
+                        }
+                    }
+                    const long cost = wavefronts + pitch * bh8 / 128;   // + wavefronts TMA spends writing the box
+                    if (best_cost < 0 || cost < best_cost) { best_cost = cost; bw = pitch; }
+                }
+            }
             int lg = 2;
             while ((4 << lg) < bw) ++lg;
             const int rstep = std::max(1, kThreads >> lg);
@@ -172,6 +203,12 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
         if (black) td.mode_map |= TILE_HAS_BLACK;
         c->tiles[t] = td;
         c->cost_prefix[t + 1] = c->cost_prefix[t] + std::max<uint32_t>(cost, 1u);
+    }
+    if (getenv("MDC_VERBOSE")) {
+        long staged_bytes = 0; int n_staged = 0;
+        for (const TileDesc& t : c->tiles) if ((t.mode_map & 0x0f) == TILE_STAGED) { staged_bytes += (t.bw_bh & 0xffff) * (t.mode_map >> 16); ++n_staged; }
+        fprintf(stderr, "[mdc] plan: %d tiles (%d staged), %zu TMA box classes at row granularity %d, largest box %d B, mean box %ld B\n",
+                n_tiles, n_staged, c->classes.size(), gran, c->box_px_max, n_staged ? staged_bytes / n_staged : 0);
     }
     if (static_cast<int>(c->classes.size()) <= kMaxClasses) break;
     }

@@ -7,6 +7,6 @@ while IFS= read -r line; do
   [ -z "$line" ] && continue
   envs="${line%%--*}"; args=""; case "$line" in *--*) args="${line#*--}";; esac
   echo "## $line" >> gpurun_out/sweep.jsonl
-  env $envs timeout 300 python bench.py --steps 20 --warmup 3 --only-kernel $args 2>/dev/null | tail -1 | cut -c1-160 >> gpurun_out/sweep.jsonl
+  env $envs timeout 300 python bench.py --steps 20 --warmup 3 --only-kernel $args 2> gpurun_out/sweep.err | tail -1 | cut -c1-160 >> gpurun_out/sweep.jsonl; grep "\[mdc\]" gpurun_out/sweep.err | tail -3 >> gpurun_out/sweep.jsonl
 done < "${SWEEP_FILE:-scripts/sweep.txt}"
 cat gpurun_out/sweep.jsonl
