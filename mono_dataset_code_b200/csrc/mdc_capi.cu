@@ -149,6 +149,12 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
                 long best_cost = -1;
                 for (int pitch = bw_min; pitch <= std::min(bw_min + 112, 256); pitch += 16) {
                     if (pitch * bh8 > kMaxStagedPx) break;
+                    {   // must stay loadable by the LDG loader as well (rows x words-per-row thread tiling)
+                        int lgp = 2;
+                        while ((4 << lgp) < pitch) ++lgp;
+                        const int rs = std::max(1, kThreads >> lgp);
+                        if ((bh + rs - 1) / rs > kMaxBoxWordsPerThread) break;
+                    }
                     long wavefronts = 0;
                     for (int y = ty0; y < std::min(ty0 + kTile, OH); ++y) {
                         int offs[kTile];
@@ -309,7 +315,7 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     for (int l = in_kernel; l < MDC_MAX_PYR_LEVELS; ++l) { p.lw[l] = p.lh[l] = 0; }
     p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
     p.box_px_max = c->box_px_max;
-    p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 16;
+    p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 32;
     bool tma = c->plan_tma_ok && c->use_tma != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
     if (c->use_tma == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
     const TmaMaps* maps = nullptr;
