@@ -156,7 +156,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // ---- shared-memory carve-up (see fused_smem_bytes)
     float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
-    float* s_l2 = lut + 256 * 32;                                       // [2][64] pyramid level-2 hand-off (double-buffered)
+    float* s_l2 = lut + 256 * 32;                                       // [128] spare
     volatile int* s_item = reinterpret_cast<volatile int*>(s_l2 + 128); // [kItemSlots] work items handed from the producer to the consumers
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_l2 + 128 + 8);      // full[kMaxStages] empty[kMaxStages] item_full[kItemSlots] item_empty[kItemSlots]
     const uint32_t stage_bytes = (static_cast<uint32_t>(p.box_px_max) + 127u) & ~127u;
@@ -214,7 +214,6 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     const uint32_t lut_lane = smem_u32(lut) + 4u * lane;
     uint32_t st = 0, phase = 0;   // ring position / parity of the next staged frame to consume
     uint32_t st_addr = stage0;    // = stage0 + st * stage_bytes
-    uint32_t pyr_it = 0;   // frames processed so far (parity selects the level-2 hand-off buffer)
     uint32_t islot = 0, iphase = 0;
     int item = blockIdx.x;
 
@@ -420,39 +419,13 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                         const int X = (tx0 >> 2) + (lane >> 2), Y = (ty0 >> 2) + warp;
                         if (X < p.lw[2] && Y < p.lh[2])
                             stg_cs(p.out[2] + static_cast<size_t>(f) * p.lw[2] * p.lh[2] + static_cast<size_t>(Y) * p.lw[2] + X, l2);
-                        s_l2[(pyr_it & 1) * 64 + warp * 8 + (lane >> 2)] = l2;
                     }
                 }
             }
             if (!kTma && kStaged) {
                 if (f + 1 < f_end) sts_box(st_addr);   // st_addr already points at the next frame's stage
-                consumer_barrier();     // next stage published; everybody done reading the current one; level-2 hand-off visible
-            } else if (kPyr && p.levels > 3) {
-                consumer_barrier();     // level-2 hand-off visible to warp 0
+                consumer_barrier();     // next stage published; everybody done reading the current one
             }
-            if (kPyr && p.levels > 3 && warp == 0) {
-                float l3 = 0.0f;
-                if (lane < 16) {
-                    const int X = lane & 3, Y = lane >> 2;
-                    const float* s = s_l2 + (pyr_it & 1) * 64 + (2 * Y) * 8 + 2 * X;
-                    l3 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), s[8]), s[9]));
-                    const int GX = (tx0 >> 3) + X, GY = (ty0 >> 3) + Y;
-                    if (GX < p.lw[3] && GY < p.lh[3])
-                        stg_cs(p.out[3] + static_cast<size_t>(f) * p.lw[3] * p.lh[3] + static_cast<size_t>(GY) * p.lw[3] + GX, l3);
-                }
-                if (p.levels > 4) {
-                    const float bb = __shfl_down_sync(0xffffffffu, l3, 1);
-                    const float c = __shfl_down_sync(0xffffffffu, l3, 4);
-                    const float d = __shfl_down_sync(0xffffffffu, l3, 5);
-                    const float l4 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l3, bb), c), d));
-                    if (lane < 16 && (lane & 1) == 0 && (lane & 4) == 0) {
-                        const int GX = (tx0 >> 4) + ((lane & 3) >> 1), GY = (ty0 >> 4) + (lane >> 3);
-                        if (GX < p.lw[4] && GY < p.lh[4])
-                            stg_cs(p.out[4] + static_cast<size_t>(f) * p.lw[4] * p.lh[4] + static_cast<size_t>(GY) * p.lw[4] + GX, l4);
-                    }
-                }
-            }
-            ++pyr_it;
         }
         };
         if (staged) run_frames(std::true_type{}); else run_frames(std::false_type{});

@@ -12,7 +12,7 @@ namespace mdc {
 constexpr int kTile = 32;            // output tile edge (pixels); pyramid levels 0..4 close inside a tile
 constexpr int kConsumers = 256;      // 8 consumer warps; warp w owns tile rows 4w..4w+3, lane = x
 constexpr int kThreads = kConsumers;
-constexpr int kInKernelLevels = 5;   // levels 0..4 are produced by the fused kernel's epilogue
+constexpr int kInKernelLevels = 3;   // levels 0..2 come out of the fused kernel's (warp-local) epilogue; deeper levels use K2
 constexpr int kMaxBoxWordsPerThread = 8;   // LDG loader: u32 words of the input box prefetched per thread
 constexpr int kMaxBoxPx = kMaxBoxWordsPerThread * 4 * kThreads;  // 8192 px: larger boxes use the direct path
 constexpr int kTmaStages = 3;         // TMA loader: u8 box stages in the full/empty mbarrier ring
@@ -51,7 +51,7 @@ struct FusedParams {
     int tiles_x, n_tiles;
     float* out[MDC_MAX_PYR_LEVELS];
     int lw[MDC_MAX_PYR_LEVELS], lh[MDC_MAX_PYR_LEVELS];
-    int levels;                  // 1..kInKernelLevels
+    int levels;                  // 1..kInKernelLevels (levels written by K1 itself)
     unsigned lut_gamma, use_vig, kill;   // sanitised unMapImage flags
     int box_px_max;              // largest staged box (pixels) -> smem carve-up
     int chunk_frames;            // frames per schedule chunk (L2 residency of the inputs)
