@@ -91,7 +91,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity), "r"(2000u)
             : "memory");
         if (done) break;
-        __nanosleep(100);
+        __nanosleep(400);
     }
 }
 // 3-D tiled TMA load: box (bw, bh, 1) of the u8 frame stack at (x, y, frame) -> shared memory.
@@ -332,51 +332,56 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         const bool x_ok = ox < p.out_w;
 
         // ------------------------------------------------------------ frame loop, specialised on how the taps are fetched
-        auto run_frames = [&](auto staged_c) {
+        auto run_frames = [&](auto staged_c, auto black_c) {
         constexpr bool kStaged = decltype(staged_c)::value;
+        constexpr bool kBlack = decltype(black_c)::value;
         for (int f = f_begin; f < f_end; ++f) {
-            uint32_t b[4][4];
+            float px[4];
+            uint32_t base = 0;
+            const uint8_t* frame = nullptr;
             if (kStaged) {
                 if (kTma) mbar_wait(bar_full + 8u * st, phase);
                 else if (f + 1 < f_end) ldg_box(f + 1);          // in flight during the gather below
-                const uint32_t base = st_addr;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t a0 = base + off[q], a1 = a0 + static_cast<uint32_t>(pitch);
-                    b[q][0] = lds_u8(a0); b[q][1] = lds_u8_1(a0);
-                    b[q][2] = lds_u8(a1); b[q][3] = lds_u8_1(a1);
-                }
+                base = st_addr;
             } else {
-                const uint8_t* frame = p.frames + static_cast<size_t>(f) * n_in;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint8_t* s = frame + off[q];
-                    b[q][0] = __ldg(s); b[q][1] = __ldg(s + 1);
-                    b[q][2] = __ldg(s + pitch); b[q][3] = __ldg(s + pitch + 1);
-                }
+                frame = p.frames + static_cast<size_t>(f) * n_in;
             }
-            float g[4][4];
+            // two halves of two pixels each: keeps the live temporaries (tap bytes, LUT values) at 8 registers
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int h = 0; h < 2; ++h) {
+                uint32_t b[2][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) g[q][k] = lds_f32(lut_lane + (b[q][k] << 7));
-            if (kStaged) {
-                if (kTma) {          // all tap bytes of this warp are in registers: hand the stage back to the producer
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_empty + 8u * st);
+                for (int j = 0; j < 2; ++j) {
+                    const int q = 2 * h + j;
+                    if (kStaged) {
+                        const uint32_t a0 = base + off[q], a1 = a0 + static_cast<uint32_t>(pitch);
+                        b[j][0] = lds_u8(a0); b[j][1] = lds_u8_1(a0);
+                        b[j][2] = lds_u8(a1); b[j][3] = lds_u8_1(a1);
+                    } else {
+                        const uint8_t* s = frame + off[q];
+                        b[j][0] = __ldg(s); b[j][1] = __ldg(s + 1);
+                        b[j][2] = __ldg(s + pitch); b[j][3] = __ldg(s + pitch + 1);
+                    }
                 }
-                st_addr += stage_bytes;
-                if (++st == static_cast<uint32_t>(kNs)) { st = 0; st_addr = stage0; phase ^= 1u; }
-            }
-
-            // ---- unMapImage multiply + bilinear blend, reference order (PhotometricUndistorter.cpp:205, FOVUndistorter.cpp:362-365)
-            float px[4];
+                float g[2][4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {      // pixels 2h and 2h+1 ride in the two halves of packed registers
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) g[j][k] = lds_f32(lut_lane + (b[j][k] << 7));
+                if (kStaged && h == 1) {
+                    if (kTma) {          // all tap bytes of this warp are in registers: hand the stage back to the producer
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + 8u * st);
+                    }
+                    st_addr += stage_bytes;
+                    if (++st == static_cast<uint32_t>(kNs)) { st = 0; st_addr = stage0; phase ^= 1u; }
+                }
+                // unMapImage multiply + bilinear blend, reference order (PhotometricUndistorter.cpp:205, FOVUndistorter.cpp:362-365);
+                // pixels 2h and 2h+1 ride in the two halves of packed registers
                 float t_lo[4], t_hi[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    uint64_t v = pack2(g[2 * h][k], g[2 * h + 1][k]);
+                    uint64_t v = pack2(g[0][k], g[1][k]);
                     if (kVig) v = mul2(v, vi2[h][k]);
                     v = mul2(w2[h][k], v);
                     unpack2(v, t_lo[k], t_hi[k]);
@@ -384,7 +389,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                 px[2 * h] = __fadd_rn(__fadd_rn(__fadd_rn(t_lo[3], t_lo[2]), t_lo[1]), t_lo[0]);
                 px[2 * h + 1] = __fadd_rn(__fadd_rn(__fadd_rn(t_hi[3], t_hi[2]), t_hi[1]), t_hi[0]);
             }
-            if (has_black) {
+            if (kBlack) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) px[q] = ((valid >> q) & 1u) ? px[q] : 0.0f;
             }
@@ -428,7 +433,8 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             }
         }
         };
-        if (staged) run_frames(std::true_type{}); else run_frames(std::false_type{});
+        if (staged) { if (has_black) run_frames(std::true_type{}, std::true_type{}); else run_frames(std::true_type{}, std::false_type{}); }
+        else run_frames(std::false_type{}, std::true_type{});
         if (!kTma) {         // LDG loader: thread 0 pulls the next item for the whole CTA
             consumer_barrier();
             if (tid == 0) s_item[0] = static_cast<int>(gridDim.x) + atomicAdd(p.work_counter, 1);
