@@ -49,6 +49,15 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_per_frame():
+    """dram__bytes_read+write of K1 per frame from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def write_calibration(tmp):
     from mono_dataset_code_b200 import synthetic as S
     return S.write_dataset_dir(tmp, IN_W, IN_H, OUT_W, OUT_H, "crop")
@@ -244,6 +253,7 @@ def run_gpu_arm(args):
             total_ms = float(t.item())
         return total_ms, per_launch_ms, ctx.launch_count - l0, clocks
 
+    TRAFFIC = ncu_traffic_per_frame()
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, per_launch_ms, launches, clocks = timed(1, args.steps, args.warmup, sampler)
     value = world * B * args.steps / (total_ms * 1e-3)
@@ -262,6 +272,27 @@ def run_gpu_arm(args):
     p_steps = max(2, args.steps // 2)
     pyr = {"value": world * B * p_steps / (p_total_ms * 1e-3), "unit": "frames/s", "levels": 5,
            "achieved_gbs": B * (ALG_BYTES_PER_FRAME + PYR_EXTRA_BYTES) / (float(np.mean(p_launch_ms)) * 1e-3) / 1e9}
+
+    # ---- BASELINE configs[4]: responseCalib E-step, 1000 exposures x 1 MP, fp64, bit-exact kernel K3 (1 GPU only)
+    estep = None
+    if world == 1 and not args.no_estep:
+        n_img, npix = 1000, 1000 * 1000
+        data = torch.randint(0, 256, (n_img, npix), dtype=torch.uint8, device=dev, generator=g)
+        t_exp = torch.linspace(0.05, 20.0, n_img, dtype=torch.float64, device=dev)
+        G_tab = torch.linspace(0.0, 255.0, 256, dtype=torch.float64, device=dev)
+        E_out = torch.empty(npix, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            ctx.estep(data, t_exp, G_tab, E_out)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in evs:
+            a.record(); ctx.estep(data, t_exp, G_tab, E_out); b.record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        alg = n_img * npix + 8 * npix
+        estep = {"ms_per_pass": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "workload": "n=1000 x 1 MP u8 -> f64 E[1 MP]"}
+        del data, E_out
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)
     EB = args.e2e_batch
@@ -300,9 +331,11 @@ def run_gpu_arm(args):
                            "l2_policy": f"inputs larger than L2 ({B * n_in >> 20} MiB in, {B * n_out * 4 >> 20} MiB out per step)",
                            "loader": {None: "auto(tma)", 1: "tma", 0: "ldg"}[args.tma]},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "fused_prepare_kernel",
+                             "traffic": (TRAFFIC["dram_bytes_per_frame"] * B / 1e9 if TRAFFIC else None),
+                             "traffic_note": (TRAFFIC["note"] if TRAFFIC else "no ncu capture committed"),
+                             "peak_source": peak_src, "kernel": "fused_prepare_kernel",
                              "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_FRAME, "launch_ms": k1_ms},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c5_estep": estep}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(files)
         print(json.dumps(line), flush=True)
@@ -320,6 +353,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
     ap.add_argument("--tma", type=int, default=None, help="force the input loader: 1 = TMA, 0 = LDG")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-estep", action="store_true", help="skip the configs[4] E-step leg")
     ap.add_argument("--only-kernel", action="store_true", help="tuning sweeps: device-resident K1 timing only (no pyramid / e2e / cpu legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -61,12 +61,10 @@ struct mdc_ctx {
     float *d_rx = nullptr, *d_ry = nullptr, *d_ginv = nullptr, *d_vinv = nullptr;
     // tile plan
     std::vector<TileDesc> tiles;
-    std::vector<uint32_t> cost_prefix;
     std::vector<std::pair<int, int>> classes;   // (bw, bh rounded to 8) of every TMA box class
     int tiles_x = 0, tiles_y = 0, box_px_max = 128;
     bool plan_tma_ok = false;
     TileDesc* d_tiles = nullptr;
-    uint32_t* d_cost_prefix = nullptr;
     int* d_counters = nullptr;   // ring of work counters (one per launch in flight)
     unsigned counter_next = 0;
     // TMA descriptor cache (host memory; descriptors are passed to the kernel by value)
@@ -106,13 +104,8 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     c->tiles_y = (OH + kTile - 1) / kTile;
     const int n_tiles = c->tiles_x * c->tiles_y;
     c->tiles.assign(n_tiles, TileDesc{0, 0, 0, TILE_EMPTY});
-    c->cost_prefix.assign(n_tiles + 1, 0);
     const bool tma_geom_ok = (W % 16 == 0) && (static_cast<long long>(W) * H % 16 == 0);
-    // relative per-frame cost of a tile (pixel-equivalents), used to balance the static schedule
     const char* e;
-    const int cost_in = (e = getenv("MDC_COST_IN")) ? atoi(e) : 0;       // per 4 staged input bytes (free with TMA)
-    const int cost_out = (e = getenv("MDC_COST_OUT")) ? atoi(e) : 8;     // per output pixel (taps + LUT + blend + store)
-    const int cost_direct = (e = getenv("MDC_COST_DIRECT")) ? atoi(e) : 16;
     const bool pitch_search = (e = getenv("MDC_PITCH_SEARCH")) ? atoi(e) != 0 : true;
     // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
     for (int gran = 8; gran <= 256; gran *= 2) {
@@ -132,7 +125,6 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
                 ylo = std::min(ylo, yi); yhi = std::max(yhi, yi + 1);
             }
         TileDesc td{0, 0, 0, TILE_EMPTY};
-        uint32_t cost = kTile * kTile;   // an empty tile still writes zeros
         if (xhi >= 0) {
             // defensive: a table that violates the reference's in-bounds guarantee would read outside the frame
             xlo = std::max(xlo, 0); ylo = std::max(ylo, 0);
@@ -200,15 +192,12 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
                 }
                 td.mode_map = TILE_STAGED | (cls << 8) | (bh8 << 16);
                 c->box_px_max = std::max(c->box_px_max, bw * bh8);
-                cost = static_cast<uint32_t>(cost_in * (bw * bh / 4) + cost_out * kTile * kTile);
             } else {
                 td.mode_map = TILE_DIRECT;
-                cost = static_cast<uint32_t>(cost_direct * kTile * kTile);
             }
         }
         if (black) td.mode_map |= TILE_HAS_BLACK;
         c->tiles[t] = td;
-        c->cost_prefix[t + 1] = c->cost_prefix[t] + std::max<uint32_t>(cost, 1u);
     }
     if (getenv("MDC_VERBOSE")) {
         long staged_bytes = 0; int n_staged = 0;
@@ -224,9 +213,7 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
 int upload_plan(mdc_ctx* c) {
     const size_t n = c->tiles.size();
     CU_CHECK(cudaMalloc(&c->d_tiles, std::max<size_t>(n, 1) * sizeof(TileDesc)));
-    CU_CHECK(cudaMalloc(&c->d_cost_prefix, (n + 1) * sizeof(uint32_t)));
     CU_CHECK(cudaMemcpy(c->d_tiles, c->tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice));
-    CU_CHECK(cudaMemcpy(c->d_cost_prefix, c->cost_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return MDC_OK;
 }
 
@@ -315,7 +302,7 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     for (int l = in_kernel; l < MDC_MAX_PYR_LEVELS; ++l) { p.lw[l] = p.lh[l] = 0; }
     p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
     p.box_px_max = c->box_px_max;
-    p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 32;
+    p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 48;
     bool tma = c->plan_tma_ok && c->use_tma != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
     if (c->use_tma == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
     const TmaMaps* maps = nullptr;
@@ -429,7 +416,7 @@ extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->owns_tables) { cudaFree(c->d_rx); cudaFree(c->d_ry); cudaFree(c->d_ginv); cudaFree(c->d_vinv); }
-    cudaFree(c->d_tiles); cudaFree(c->d_cost_prefix); cudaFree(c->d_counters);
+    cudaFree(c->d_tiles); cudaFree(c->d_counters);
     for (int s = 0; s < kMapSlots; ++s) free(c->maps[s]);
     for (int s = 0; s < kHostPipeDepth; ++s) {
         if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }

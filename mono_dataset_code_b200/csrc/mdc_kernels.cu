@@ -606,34 +606,38 @@ template <int kPix>
 __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
                                                     const double* __restrict__ t, const double* __restrict__ G,
                                                     double* __restrict__ E) {
-    __shared__ double sG[256];
-    sG[threadIdx.x] = G[threadIdx.x];
+    // G[256] replicated 16x (slot = lane & 15): a 64-bit shared load is served per half-warp, so with one slot
+    // per lane of the half-warp the data-dependent lookup is bank-conflict-free.
+    __shared__ double sG[256 * 16];
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = G[i >> 4];
     __syncthreads();
+    const double* gl = sG + (threadIdx.x & 15);
     const size_t k0 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kPix;
     if (k0 >= npix) return;
     double esum[kPix], enumr[kPix];
 #pragma unroll
     for (int j = 0; j < kPix; ++j) { esum[j] = 0.0; enumr[j] = 0.0; }
-#pragma unroll 4
+    const uint8_t* col = data + k0;
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
         const double ti = __ldg(t + i);
         const double tt = __dmul_rn(ti, ti);
         uint32_t v;
-        if (kPix == 4) v = __ldg(reinterpret_cast<const uint32_t*>(data + static_cast<size_t>(i) * npix + k0));
-        else v = __ldg(data + static_cast<size_t>(i) * npix + k0);
+        if (kPix == 4) v = __ldg(reinterpret_cast<const uint32_t*>(col + static_cast<size_t>(i) * npix));
+        else v = __ldg(col + static_cast<size_t>(i) * npix);
 #pragma unroll
         for (int j = 0; j < kPix; ++j) {
             const unsigned b = (v >> (8 * j)) & 0xffu;
-            if (b != 255u) {
+            if (b != 255u) {          // saturated samples are skipped (main_responseCalib.cpp:329)
                 enumr[j] = __dadd_rn(enumr[j], tt);
-                esum[j] = __dadd_rn(esum[j], __dmul_rn(sG[b], ti));
+                esum[j] = __dadd_rn(esum[j], __dmul_rn(gl[b << 4], ti));
             }
         }
     }
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
         double e = __ddiv_rn(esum[j], enumr[j]);
-        if (e < 0) e = 0;
+        if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
         E[k0 + j] = e;
     }
 }
