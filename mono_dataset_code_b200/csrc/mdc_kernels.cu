@@ -619,8 +619,8 @@ __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ 
     for (int j = 0; j < kPix; ++j) { esum[j] = 0.0; enumr[j] = 0.0; }
     const uint8_t* col = data + k0;
     // Saturated samples (b == 255) are skipped in the reference (main_responseCalib.cpp:329).  Here both sums are
-    // computed unconditionally and the old value is kept by a select: branch-free (no divergence on the rare 255s,
-    // loads of the unrolled iterations can be hoisted), and still bit-exact because a select changes no arithmetic.
+    // looked up / multiplied unconditionally and only the two adds are predicated: branch-free (no divergence on
+    // the rare 255s, loads of the unrolled iterations can be hoisted) and still bit-exact.
 #pragma unroll 8
     for (int i = 0; i < n; ++i) {
         const double ti = __ldg(t + i);
@@ -631,11 +631,11 @@ __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < kPix; ++j) {
             const unsigned b = (v >> (8 * j)) & 0xffu;
-            const double en = __dadd_rn(enumr[j], tt);
-            const double es = __dadd_rn(esum[j], __dmul_rn(gl[b << 4], ti));
-            const bool keep = b != 255u;
-            enumr[j] = keep ? en : enumr[j];
-            esum[j] = keep ? es : esum[j];
+            const double prod = __dmul_rn(gl[b << 4], ti);   // lookup + product unconditionally, so that only
+            if (b != 255u) {                                  // the two adds are predicated (no branch)
+                enumr[j] = __dadd_rn(enumr[j], tt);
+                esum[j] = __dadd_rn(esum[j], prod);
+            }
         }
     }
 #pragma unroll

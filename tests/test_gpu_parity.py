@@ -232,3 +232,43 @@ def test_multi_gpu_style_adopted_tables(api, port, dataset_dir):
     prx, pry, ginv, vinv = oracle_tables(port, files)
     for i in range(3):
         assert_bits_equal(out[i].cpu().numpy(), port.get_image(prx, pry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 0), f"adopted ctx frame {i}")
+
+
+def test_host_pipeline_with_pyramid_and_many_chunks(api, port, dataset_dir):
+    """mdc_prepare_batch_host: 3-deep chunked H2D/kernel/D2H pipeline, frame count not a multiple of the chunk,
+    pyramid levels beyond the in-kernel ones (K2 chain), pageable host memory."""
+    iw, ih, ow, oh, mode, calib = CALIBS["tum_explicit"]
+    files = dataset_dir("tum_explicit")
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    n = 37
+    frames = mixed_frames(n, iw, ih)
+    levels = 6
+    outs = [np.full((n, (ow >> l) * (oh >> l)), -1.0, np.float32) for l in range(levels)]
+    prep.ctx.prepare_batch_host(frames, 1 | 2 | 4 | 8, outs)
+    for i in (0, 1, 15, 16, 17, 35, 36):
+        exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 1), ow, oh, levels)
+        for l in range(levels):
+            assert_bits_equal(outs[l][i], exp[l], f"host pipeline frame={i} level={l}")
+
+
+def test_many_frames_cross_chunk_boundaries(api, port, dataset_dir):
+    """More frames than one schedule chunk (48) on a small geometry: every frame must come out right whatever
+    item/CTA processed it."""
+    iw, ih, ow, oh, mode, calib = CALIBS["omega0"]
+    files = dataset_dir("omega0")
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    n = 131
+    frames = mixed_frames(n, iw, ih)
+    d = torch.from_numpy(frames).cuda()
+    for use_tma in (-1, 0):
+        prep.ctx.configure(use_tma=use_tma)
+        out = prep.prepare_device(d, 1, 1, 1, 0, levels=3)
+        lv = [o.cpu().numpy() for o in out]
+        for i in range(n):
+            exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 0), ow, oh, 3)
+            for l in range(3):
+                assert_bits_equal(lv[l][i], exp[l], f"tma={use_tma} frame={i} level={l}")
