@@ -156,9 +156,8 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // ---- shared-memory carve-up (see fused_smem_bytes)
     float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
-    float* s_l2 = lut + 256 * 32;                                       // [128] spare
-    volatile int* s_item = reinterpret_cast<volatile int*>(s_l2 + 128); // [kItemSlots] work items handed from the producer to the consumers
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_l2 + 128 + 8);      // full[kMaxStages] empty[kMaxStages] item_full[kItemSlots] item_empty[kItemSlots]
+    volatile int* s_item = reinterpret_cast<volatile int*>(lut + 256 * 32);   // [kItemSlots] work items handed from the producer to the consumers
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(lut + 256 * 32 + 8);        // full[kMaxStages] empty[kMaxStages] item_full[kItemSlots] item_empty[kItemSlots]
     const uint32_t stage_bytes = (static_cast<uint32_t>(p.box_px_max) + 127u) & ~127u;
     const uint32_t stage0 = smem_u32(smem_raw) + kSmemHeaderBytes;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 8u * kMaxStages;
@@ -444,7 +443,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     }
 }
 
-// smem layout (bytes): lut 32768 | s_l2 512 | items 32 | barriers 8*(2*kMaxStages+2*kItemSlots) | pad -> kSmemHeaderBytes | stages
+// smem layout (bytes): lut 32768 | items 32 | barriers 8*(2*kMaxStages+2*kItemSlots) | pad -> kSmemHeaderBytes | stages
 size_t fused_smem_bytes(int box_px_max, bool tma) {
     const size_t stage = (static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u);
     return kSmemHeaderBytes + static_cast<size_t>(tma ? kTmaStages : kLdgStages) * stage;

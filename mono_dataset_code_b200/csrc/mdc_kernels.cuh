@@ -14,12 +14,11 @@ constexpr int kConsumers = 256;      // 8 consumer warps; warp w owns tile rows 
 constexpr int kThreads = kConsumers;
 constexpr int kInKernelLevels = 3;   // levels 0..2 come out of the fused kernel's (warp-local) epilogue; deeper levels use K2
 constexpr int kMaxBoxWordsPerThread = 8;   // LDG loader: u32 words of the input box prefetched per thread
-constexpr int kMaxBoxPx = kMaxBoxWordsPerThread * 4 * kThreads;  // 8192 px: larger boxes use the direct path
 constexpr int kTmaStages = 3;         // TMA loader: u8 box stages in the full/empty mbarrier ring
 constexpr int kLdgStages = 2;         // LDG loader: double buffer
 constexpr int kMaxStages = 4;
 constexpr int kItemSlots = 4;          // work items in flight between the producer warp and the consumers
-constexpr int kSmemHeaderBytes = 33536;   // lut 32768 + s_l2 512 + sched 32 + barriers 64, rounded up to 128
+constexpr int kSmemHeaderBytes = 33024;   // lut 32768 + item ring 32 + 16 mbarriers 128, rounded up to 128
 constexpr int kMaxClasses = 48;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
 
 // How a tile's input pixels are fetched.
