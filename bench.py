@@ -255,7 +255,7 @@ def run_gpu_arm(args):
 
     TRAFFIC = ncu_traffic_per_frame()
     sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, per_launch_ms, launches, clocks = timed(1, args.steps, args.warmup, sampler)
+    total_ms, per_launch_ms, launches, clocks = timed(args.levels if args.only_kernel else 1, args.steps, args.warmup, sampler)
     value = world * B * args.steps / (total_ms * 1e-3)
     peak, peak_src = measured_peak()
     k1_ms = float(np.mean(per_launch_ms))
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
     ap.add_argument("--tma", type=int, default=None, help="force the input loader: 1 = TMA, 0 = LDG")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--levels", type=int, default=1, help="pyramid levels for --only-kernel sweeps")
     ap.add_argument("--no-estep", action="store_true", help="skip the configs[4] E-step leg")
     ap.add_argument("--only-kernel", action="store_true", help="tuning sweeps: device-resident K1 timing only (no pyramid / e2e / cpu legs)")
     args = ap.parse_args()

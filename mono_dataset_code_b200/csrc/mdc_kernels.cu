@@ -329,6 +329,24 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         float* o0 = p.out[0] + static_cast<size_t>(f_begin) * p.lw[0] * p.lh[0] + static_cast<size_t>(oy0) * p.out_w + ox;
         const size_t o0_step = static_cast<size_t>(p.lw[0]) * p.lh[0];
         const bool x_ok = ox < p.out_w;
+        // pyramid levels 1-2: per-item output pointers and store predicates (advanced by one image per frame)
+        float *o1 = nullptr, *o2 = nullptr;
+        uint32_t o1_step = 0, o2_step = 0;   // elements per image of level 1 / 2 (< 2^31)
+        bool st1a = false, st1b = false, st2 = false;
+        if (kPyr) {
+            const int X1 = (tx0 >> 1) + (lane >> 1), Y1 = (ty0 >> 1) + 2 * warp;
+            const bool own1 = (lane & 1) == 0 && X1 < p.lw[1];
+            st1a = own1 && Y1 < p.lh[1];
+            st1b = own1 && Y1 + 1 < p.lh[1];
+            o1_step = static_cast<uint32_t>(p.lw[1]) * static_cast<uint32_t>(p.lh[1]);
+            o1 = p.out[1] + static_cast<size_t>(f_begin) * o1_step + static_cast<size_t>(Y1) * p.lw[1] + X1;
+            if (p.levels > 2) {
+                const int X2 = (tx0 >> 2) + (lane >> 2), Y2 = (ty0 >> 2) + warp;
+                st2 = (lane & 3) == 0 && X2 < p.lw[2] && Y2 < p.lh[2];
+                o2_step = static_cast<uint32_t>(p.lw[2]) * static_cast<uint32_t>(p.lh[2]);
+                o2 = p.out[2] + static_cast<size_t>(f_begin) * o2_step + static_cast<size_t>(Y2) * p.lw[2] + X2;
+            }
+        }
 
         // ------------------------------------------------------------ frame loop, specialised on how the taps are fetched
         auto run_frames = [&](auto staged_c, auto black_c) {
@@ -412,18 +430,15 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                     const float a = px[2 * rp], c = px[2 * rp + 1];
                     const float bb = __shfl_xor_sync(0xffffffffu, a, 1), d = __shfl_xor_sync(0xffffffffu, c, 1);
                     l1[rp] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(a, bb), c), d));   // meaningful on even lanes
-                    const int X = (tx0 >> 1) + (lane >> 1), Y = (ty0 >> 1) + 2 * warp + rp;
-                    if ((lane & 1) == 0 && X < p.lw[1] && Y < p.lh[1])
-                        stg_cs(p.out[1] + static_cast<size_t>(f) * p.lw[1] * p.lh[1] + static_cast<size_t>(Y) * p.lw[1] + X, l1[rp]);
                 }
+                if (st1a) stg_cs(o1, l1[0]);
+                if (st1b) stg_cs(o1 + p.lw[1], l1[1]);
+                o1 += o1_step;
                 if (p.levels > 2) {
                     const float bb = __shfl_down_sync(0xffffffffu, l1[0], 2), d = __shfl_down_sync(0xffffffffu, l1[1], 2);
                     const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1[0], bb), l1[1]), d));   // lanes = 0 mod 4
-                    if ((lane & 3) == 0) {
-                        const int X = (tx0 >> 2) + (lane >> 2), Y = (ty0 >> 2) + warp;
-                        if (X < p.lw[2] && Y < p.lh[2])
-                            stg_cs(p.out[2] + static_cast<size_t>(f) * p.lw[2] * p.lh[2] + static_cast<size_t>(Y) * p.lw[2] + X, l2);
-                    }
+                    if (st2) stg_cs(o2, l2);
+                    o2 += o2_step;
                 }
             }
             if (!kTma && kStaged) {
