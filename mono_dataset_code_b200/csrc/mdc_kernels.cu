@@ -623,7 +623,14 @@ __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ 
     // G[256] replicated 16x (slot = lane & 15): a 64-bit shared load is served per half-warp, so with one slot
     // per lane of the half-warp the data-dependent lookup is bank-conflict-free.
     __shared__ double sG[256 * 16];
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = G[i >> 4];
+    // Saturated samples (b == 255) are skipped in the reference (main_responseCalib.cpp:329).  Fast path: give
+    // them exact-zero contributions instead — table entry 255 := +0.0 (so G[255]*t = +-0) and t*t := +0.0 — because
+    // adding a signed zero never changes these sums: they start at +0.0 and RN addition can only produce -0.0 from
+    // two -0.0 operands.  That needs every t[i] finite (0*inf = NaN); otherwise the select path below is used.
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) bad |= !isfinite(t[i]);
+    const bool exact_zero_ok = __syncthreads_or(bad) == 0;
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = (exact_zero_ok && (i >> 4) == 255) ? 0.0 : G[i >> 4];
     __syncthreads();
     const double* gl = sG + (threadIdx.x & 15);
     const size_t k0 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kPix;
@@ -632,23 +639,36 @@ __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ 
 #pragma unroll
     for (int j = 0; j < kPix; ++j) { esum[j] = 0.0; enumr[j] = 0.0; }
     const uint8_t* col = data + k0;
-    // Saturated samples (b == 255) are skipped in the reference (main_responseCalib.cpp:329).  Here both sums are
-    // looked up / multiplied unconditionally and only the two adds are predicated: branch-free (no divergence on
-    // the rare 255s, loads of the unrolled iterations can be hoisted) and still bit-exact.
+    if (exact_zero_ok) {
 #pragma unroll 8
-    for (int i = 0; i < n; ++i) {
-        const double ti = __ldg(t + i);
-        const double tt = __dmul_rn(ti, ti);
-        uint32_t v;
-        if (kPix == 4) v = __ldg(reinterpret_cast<const uint32_t*>(col + static_cast<size_t>(i) * npix));
-        else v = __ldg(col + static_cast<size_t>(i) * npix);
+        for (int i = 0; i < n; ++i) {
+            const double ti = __ldg(t + i);
+            const double tt = __dmul_rn(ti, ti);
+            uint32_t v;
+            if (kPix == 4) v = __ldg(reinterpret_cast<const uint32_t*>(col + static_cast<size_t>(i) * npix));
+            else v = __ldg(col + static_cast<size_t>(i) * npix);
 #pragma unroll
-        for (int j = 0; j < kPix; ++j) {
-            const unsigned b = (v >> (8 * j)) & 0xffu;
-            const double prod = __dmul_rn(gl[b << 4], ti);   // lookup + product unconditionally, so that only
-            if (b != 255u) {                                  // the two adds are predicated (no branch)
-                enumr[j] = __dadd_rn(enumr[j], tt);
-                esum[j] = __dadd_rn(esum[j], prod);
+            for (int j = 0; j < kPix; ++j) {
+                const unsigned b = (v >> (8 * j)) & 0xffu;
+                enumr[j] = __dadd_rn(enumr[j], b != 255u ? tt : 0.0);
+                esum[j] = __dadd_rn(esum[j], __dmul_rn(gl[b << 4], ti));
+            }
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const double ti = __ldg(t + i);
+            const double tt = __dmul_rn(ti, ti);
+            uint32_t v;
+            if (kPix == 4) v = __ldg(reinterpret_cast<const uint32_t*>(col + static_cast<size_t>(i) * npix));
+            else v = __ldg(col + static_cast<size_t>(i) * npix);
+#pragma unroll
+            for (int j = 0; j < kPix; ++j) {
+                const unsigned b = (v >> (8 * j)) & 0xffu;
+                const double prod = __dmul_rn(gl[b << 4], ti);
+                if (b != 255u) {
+                    enumr[j] = __dadd_rn(enumr[j], tt);
+                    esum[j] = __dadd_rn(esum[j], prod);
+                }
             }
         }
     }

@@ -272,3 +272,19 @@ def test_many_frames_cross_chunk_boundaries(api, port, dataset_dir):
             exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 0), ow, oh, 3)
             for l in range(3):
                 assert_bits_equal(lv[l][i], exp[l], f"tma={use_tma} frame={i} level={l}")
+
+
+def test_estep_non_finite_exposure_takes_the_select_path(api, port):
+    """t[i] = inf would turn the fast path's exact-zero trick (0*inf) into NaN; the kernel must detect it and
+    reproduce the reference's skip semantics instead."""
+    rng = np.random.default_rng(12)
+    n, npix = 9, 2048
+    data = rng.integers(250, 256, (n, npix), dtype=np.uint8)       # many saturated samples
+    t = rng.uniform(0.5, 2.0, n)
+    t[4] = np.inf
+    G = np.linspace(0.0, 255.0, 256)
+    exp = port.estep(data, t, G)
+    ctx = api.Context(None, None, 0)
+    E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+    ctx.estep(torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda(), E)
+    assert_bits_equal(E.cpu().numpy(), exp, "E-step with t=inf")
