@@ -33,6 +33,14 @@ sys.path.insert(0, ROOT)
 IN_W, IN_H, OUT_W, OUT_H = 1280, 1024, 1280, 1024
 ALG_BYTES_PER_FRAME = IN_W * IN_H * 1 + OUT_W * OUT_H * 4                    # 6 553 600
 PYR_EXTRA_BYTES = sum((OUT_W >> l) * (OUT_H >> l) * 4 for l in range(1, 5))    # 1 740 800
+
+
+def set_geometry(w, h):
+    """--geom WxH (tuning / other BASELINE configs, e.g. 1920x1080 = configs[3]); the default is configs[1]."""
+    global IN_W, IN_H, OUT_W, OUT_H, ALG_BYTES_PER_FRAME, PYR_EXTRA_BYTES
+    IN_W, IN_H, OUT_W, OUT_H = w, h, w, h
+    ALG_BYTES_PER_FRAME = w * h + w * h * 4
+    PYR_EXTRA_BYTES = sum((w >> l) * (h >> l) * 4 for l in range(1, 5))
 FLAGS_ALL = 1 | 2 | 4        # rectify + removeGamma + removeVignette (the reference viewer's full correction)
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -356,7 +364,10 @@ def main():
     ap.add_argument("--levels", type=int, default=1, help="pyramid levels for --only-kernel sweeps")
     ap.add_argument("--no-estep", action="store_true", help="skip the configs[4] E-step leg")
     ap.add_argument("--only-kernel", action="store_true", help="tuning sweeps: device-resident K1 timing only (no pyramid / e2e / cpu legs)")
+    ap.add_argument("--geom", default=None, help="WxH for --only-kernel sweeps (default 1280x1024)")
     args = ap.parse_args()
+    if args.geom:
+        set_geometry(*[int(v) for v in args.geom.lower().split("x")])
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
