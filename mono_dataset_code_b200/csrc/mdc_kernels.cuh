@@ -19,7 +19,7 @@ constexpr int kLdgStages = 2;         // LDG loader: double buffer
 constexpr int kMaxStages = 4;
 constexpr int kItemSlots = 4;          // work items in flight between the producer warp and the consumers
 constexpr int kSmemHeaderBytes = 33024;   // lut 32768 + item ring 32 + 16 mbarriers 128, rounded up to 128
-constexpr int kMaxClasses = 48;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
+constexpr int kMaxClasses = 64;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
 
 // How a tile's input pixels are fetched.
 enum TileMode : int { TILE_EMPTY = 0, TILE_STAGED = 1, TILE_DIRECT = 2, TILE_HAS_BLACK = 0x10 /* flag */ };
