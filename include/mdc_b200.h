@@ -161,6 +161,22 @@ int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_
  * Bit-exact with the reference's loop (sequential fp64 accumulation per pixel, no FMA). */
 int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, double* d_E, mdc_stream stream);
 
+/* responseCalib building blocks around the E-step (all DEVICE pointers, data = [n][npix] u8
+ * image-major, t = [n] f64 exposure times, G = [256] f64, E = [npix] f64):
+ *   mdc_rc_leak_padding  3x3 dilation of saturated interior pixels, `iterations` rounds, in place   main_responseCalib.cpp:212-236  bit-exact
+ *   mdc_rc_einit         E = per-pixel mean over the n images                                          :249-259                       bit-exact
+ *   mdc_rc_gstep         G[b] = sum(E[k]*t[i]) / count over samples with value b != 255, gaps extrapolated  :286-304   rounding-level (sum order)
+ *   mdc_rc_rescale       factor = 255/G[255]; E *= factor; G *= factor; *factor_host = factor           :350-355                       bit-exact
+ *   mdc_rc_rmse          out_host = {1e5*sqrt(mean((G[b]-t*E)^2 * 1e-10)), count}                       :50-69                         rounding-level
+ *   mdc_response_calib   the optimisation loop of main(): E := mean, then nits x {G-step, E-step, rescale}, rmse after
+ *                        each half-step; log_host (may be NULL) receives nits x 4 doubles {rmse_G, rmse_E, rmse_rescaled, count}. */
+int mdc_rc_leak_padding(mdc_ctx* c, uint8_t* d_data, int n, int w, int h, int iterations, mdc_stream stream);
+int mdc_rc_einit(mdc_ctx* c, const uint8_t* d_data, int n, int npix, double* d_E, mdc_stream stream);
+int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, mdc_stream stream);
+int mdc_rc_rescale(mdc_ctx* c, int npix, double* d_E, double* d_G, double* factor_host);
+int mdc_rc_rmse(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E, double out_host[2]);
+int mdc_response_calib(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, int nits, double* d_E, double* d_G, double* log_host);
+
 /* -------------------------------------------------------------------------------------
  * Host-buffer entry points (what the compat classes call): H2D copy, kernels, D2H copy.
  * Host pointers may be pageable; pinned memory (mdc_host_alloc) makes the copies async.

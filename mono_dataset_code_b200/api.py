@@ -272,6 +272,42 @@ class Context:
         check(lib.mdc_estep(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
                             C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), self._stream(data)), "mdc_estep")
 
+    # ---- responseCalib building blocks (CUDA tensors; main_responseCalib.cpp)
+    def rc_leak_padding(self, data, w, h, iterations):
+        check(lib.mdc_rc_leak_padding(self._h, C.c_void_p(data.data_ptr()), data.shape[0], w, h, iterations, self._stream(data)), "mdc_rc_leak_padding")
+
+    def rc_einit(self, data, E):
+        check(lib.mdc_rc_einit(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(E.data_ptr()), self._stream(data)), "mdc_rc_einit")
+
+    def rc_gstep(self, data, t, E, G):
+        check(lib.mdc_rc_gstep(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                               C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), self._stream(data)), "mdc_rc_gstep")
+
+    def rc_rescale(self, E, G) -> float:
+        import torch
+        torch.cuda.current_stream(E.device).synchronize()
+        f = C.c_double()
+        check(lib.mdc_rc_rescale(self._h, E.shape[0], C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), C.byref(f)), "mdc_rc_rescale")
+        return f.value
+
+    def rc_rmse(self, data, t, G, E):
+        import torch
+        torch.cuda.current_stream(data.device).synchronize()
+        out = (C.c_double * 2)()
+        check(lib.mdc_rc_rmse(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                              C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), out), "mdc_rc_rmse")
+        return out[0], out[1]
+
+    def response_calib(self, data, t, nits, E, G):
+        """The optimisation loop of responseCalib's main(); returns the per-iteration log [nits, 4]."""
+        import torch
+        torch.cuda.current_stream(data.device).synchronize()
+        log = np.zeros((max(nits, 1), 4), np.float64)
+        check(lib.mdc_response_calib(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()), nits,
+                                     C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), log.ctypes.data_as(C.POINTER(C.c_double))),
+              "mdc_response_calib")
+        return log[:nits]
+
     # ---- host-buffer operators (numpy)
     def unmap_host(self, image_in: np.ndarray, image_out: np.ndarray, n, flags):
         assert image_in.dtype == np.uint8 and image_out.dtype == np.float32

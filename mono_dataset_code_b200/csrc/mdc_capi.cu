@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,6 +84,7 @@ struct mdc_ctx {
     // scratch for the single-op host entry points
     void* scratch_a = nullptr; size_t scratch_a_bytes = 0;
     void* scratch_b = nullptr; size_t scratch_b_bytes = 0;
+    double* d_rc = nullptr;      // responseCalib scratch: gsum[256] gnum[256] factor[1] acc[2]
     long long launches = 0;
 };
 
@@ -225,6 +227,7 @@ int ctx_common_init(mdc_ctx* c, int device) {
     c->sm_count = v;
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&c->d_counters, kCounterRing * sizeof(int)));
+    CU_CHECK(cudaMalloc(&c->d_rc, (256 + 256 + 1 + 2) * sizeof(double)));
     const char* e = getenv("MDC_USE_TMA");
     if (e) c->use_tma = atoi(e);
     e = getenv("MDC_CTAS_PER_SM");
@@ -416,7 +419,7 @@ extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->owns_tables) { cudaFree(c->d_rx); cudaFree(c->d_ry); cudaFree(c->d_ginv); cudaFree(c->d_vinv); }
-    cudaFree(c->d_tiles); cudaFree(c->d_counters);
+    cudaFree(c->d_tiles); cudaFree(c->d_counters); cudaFree(c->d_rc);
     for (int s = 0; s < kMapSlots; ++s) free(c->maps[s]);
     for (int s = 0; s < kHostPipeDepth; ++s) {
         if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }
@@ -555,6 +558,91 @@ extern "C" int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, con
     CU_CHECK(launch_estep(d_data, n, npix, d_t, d_G, d_E, s));
     c->launches++;
     return finish(c, stream, s);
+}
+
+// ------------------------------------------------------------------ responseCalib building blocks
+extern "C" int mdc_rc_leak_padding(mdc_ctx* c, uint8_t* d_data, int n, int w, int h, int iterations, mdc_stream stream) {
+    if (!c || !d_data || n < 0 || w < 1 || h < 1 || iterations < 0) { mdc_set_error("mdc_rc_leak_padding: bad argument"); return MDC_ERR_INVALID_ARG; }
+    if (n == 0 || iterations == 0) return MDC_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    const size_t bytes = static_cast<size_t>(n) * w * h;
+    int rc = ensure_bytes(&c->scratch_a, &c->scratch_a_bytes, bytes);
+    if (rc != MDC_OK) return rc;
+    uint8_t* tmp = static_cast<uint8_t*>(c->scratch_a);
+    for (int it = 0; it < iterations; ++it) {      // ping-pong; an odd count ends in tmp and is copied back
+        const uint8_t* src = (it & 1) ? tmp : d_data;
+        uint8_t* dst = (it & 1) ? d_data : tmp;
+        CU_CHECK(launch_rc_leak_padding(src, dst, n, w, h, s));
+        c->launches++;
+    }
+    if (iterations & 1) CU_CHECK(cudaMemcpyAsync(d_data, tmp, bytes, cudaMemcpyDeviceToDevice, s));
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_rc_einit(mdc_ctx* c, const uint8_t* d_data, int n, int npix, double* d_E, mdc_stream stream) {
+    if (!c || !d_data || !d_E || n < 0 || npix < 0) { mdc_set_error("mdc_rc_einit: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if (npix > 0) { CU_CHECK(launch_rc_einit(d_data, n, npix, d_E, s)); c->launches++; }
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, mdc_stream stream) {
+    if (!c || !d_data || !d_t || !d_E || !d_G || n < 0 || npix < 0) { mdc_set_error("mdc_rc_gstep: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_rc_gstep(d_data, n, npix, d_t, d_E, c->d_rc, reinterpret_cast<unsigned long long*>(c->d_rc + 256), d_G, s));
+    c->launches += 2;
+    return finish(c, stream, s);
+}
+
+extern "C" int mdc_rc_rescale(mdc_ctx* c, int npix, double* d_E, double* d_G, double* factor_host) {
+    if (!c || !d_E || !d_G || npix < 0) { mdc_set_error("mdc_rc_rescale: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(launch_rc_rescale(npix, d_E, d_G, c->d_rc + 512, c->stream));
+    c->launches += 3;
+    if (factor_host) CU_CHECK(cudaMemcpyAsync(factor_host, c->d_rc + 512, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    return MDC_OK;
+}
+
+extern "C" int mdc_rc_rmse(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E, double out_host[2]) {
+    if (!c || !d_data || !d_t || !d_G || !d_E || !out_host || n < 0 || npix < 0) { mdc_set_error("mdc_rc_rmse: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(launch_rc_rmse(d_data, n, npix, d_t, d_G, d_E, c->d_rc + 513, c->stream));
+    c->launches++;
+    double acc[2];
+    CU_CHECK(cudaMemcpyAsync(acc, c->d_rc + 513, sizeof acc, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    out_host[0] = 1e5 * sqrt(acc[0] / acc[1]);
+    out_host[1] = acc[1];
+    return MDC_OK;
+}
+
+extern "C" int mdc_response_calib(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, int nits, double* d_E, double* d_G, double* log_host) {
+    if (!c || !d_data || !d_t || !d_E || !d_G || n < 1 || npix < 1 || nits < 0) { mdc_set_error("mdc_response_calib: bad argument"); return MDC_ERR_INVALID_ARG; }
+    int rc = mdc_rc_einit(c, d_data, n, npix, d_E, c->stream);          // starting irradiance = mean of all images
+    if (rc != MDC_OK) return rc;
+    CU_CHECK(cudaMemsetAsync(d_G, 0, 256 * sizeof(double), c->stream));
+    for (int it = 0; it < nits; ++it) {
+        double r[2], row[4] = {0, 0, 0, 0};
+        if ((rc = mdc_rc_gstep(c, d_data, n, npix, d_t, d_E, d_G, c->stream)) != MDC_OK) return rc;
+        if ((rc = mdc_rc_rmse(c, d_data, n, npix, d_t, d_G, d_E, r)) != MDC_OK) return rc;
+        row[0] = r[0];
+        printf("optG RMSE = %f! \t", r[0]);
+        if ((rc = mdc_estep(c, d_data, n, npix, d_t, d_G, d_E, c->stream)) != MDC_OK) return rc;
+        if ((rc = mdc_rc_rmse(c, d_data, n, npix, d_t, d_G, d_E, r)) != MDC_OK) return rc;
+        row[1] = r[0];
+        printf("OptE RMSE = %f!  \t", r[0]);
+        double factor = 0;
+        if ((rc = mdc_rc_rescale(c, npix, d_E, d_G, &factor)) != MDC_OK) return rc;
+        if ((rc = mdc_rc_rmse(c, d_data, n, npix, d_t, d_G, d_E, r)) != MDC_OK) return rc;
+        row[2] = r[0]; row[3] = r[1];
+        printf("resc RMSE = %f!  \trescale with %f!\n", r[0], factor);
+        if (log_host) memcpy(log_host + 4 * it, row, sizeof row);
+    }
+    return MDC_OK;
 }
 
 // ------------------------------------------------------------------ host-buffer entry points

@@ -692,4 +692,145 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
     return cudaGetLastError();
 }
 
+// =====================================================================================
+// responseCalib building blocks around the E-step: saturation leak padding, initial irradiance,
+// G-step, rescale, rmse.  Integer / per-element work is bit-exact; the two global reductions (G-step bins, rmse)
+// are order-dependent in the reference (one long sequential fp64 / long-double sum), so they match to rounding only.
+// =====================================================================================
+
+// 3x3 dilation of the value 255 around INTERIOR saturated pixels, main_responseCalib.cpp:212-236 (one iteration).
+__global__ void __launch_bounds__(256) rc_leak_padding_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int w, int h) {
+    const size_t per = static_cast<size_t>(w) * h, total = per * n;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t f = i / per, r = i - f * per;
+        const int y = static_cast<int>(r / w), x = static_cast<int>(r - static_cast<size_t>(y) * w);
+        const uint8_t* img = in + f * per;
+        uint8_t v = img[r];
+        if (v != 255) {
+            // a neighbour c spreads onto (x,y) only if c itself lies in the interior [1,w-2] x [1,h-2]
+            for (int dy = -1; dy <= 1 && v != 255; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int cx = x + dx, cy = y + dy;
+                    if (cx >= 1 && cx <= w - 2 && cy >= 1 && cy <= h - 2 && img[static_cast<size_t>(cy) * w + cx] == 255) { v = 255; break; }
+                }
+        }
+        out[i] = v;
+    }
+}
+
+// E[k] = (sum_i data[i][k]) / n, main_responseCalib.cpp:249-259 (integer-valued sums: exact in any order).
+__global__ void __launch_bounds__(256) rc_einit_kernel(const uint8_t* __restrict__ data, int n, size_t npix, double* __restrict__ E) {
+    const size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= npix) return;
+    double s = 0.0, c = 0.0;
+    for (int i = 0; i < n; ++i) { s = __dadd_rn(s, static_cast<double>(data[static_cast<size_t>(i) * npix + k])); c = __dadd_rn(c, 1.0); }
+    E[k] = __ddiv_rn(s, c);
+}
+
+// G-step accumulation, main_responseCalib.cpp:290-299: GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.
+// Per-CTA shared-memory histograms (fp64 atomics), flushed with one global atomic per bin per CTA.
+__global__ void __launch_bounds__(256) rc_gstep_accum_kernel(const uint8_t* __restrict__ data, int n, size_t npix, const double* __restrict__ t,
+                                                             const double* __restrict__ E, double* __restrict__ gsum, unsigned long long* __restrict__ gnum) {
+    __shared__ double s_sum[256];
+    __shared__ unsigned long long s_num[256];
+    s_sum[threadIdx.x] = 0.0; s_num[threadIdx.x] = 0ull;
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npix; k += stride) {
+        const double e = E[k];
+        for (int i = 0; i < n; ++i) {
+            const unsigned b = data[static_cast<size_t>(i) * npix + k];
+            if (b == 255u) continue;
+            atomicAdd(&s_sum[b], __dmul_rn(e, __ldg(t + i)));
+            atomicAdd(&s_num[b], 1ull);
+        }
+    }
+    __syncthreads();
+    atomicAdd(&gsum[threadIdx.x], s_sum[threadIdx.x]);
+    atomicAdd(&gnum[threadIdx.x], s_num[threadIdx.x]);
+}
+
+// G[i] = GSum[i]/GNum[i]; non-finite entries (empty bins) with i > 1 are extrapolated linearly, :300-304.  One thread: sequential.
+__global__ void rc_gstep_finish_kernel(const double* __restrict__ gsum, const unsigned long long* __restrict__ gnum, double* __restrict__ G) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < 256; ++i) {
+        double g = __ddiv_rn(gsum[i], static_cast<double>(gnum[i]));
+        if (!isfinite(g) && i > 1) g = __dadd_rn(G[i - 1], __dsub_rn(G[i - 1], G[i - 2]));
+        G[i] = g;
+    }
+}
+
+// Rescale so that G[255] = 255, :350-355.  `factor` is 255.0 / G[255] evaluated BEFORE G is touched.
+__global__ void rc_factor_kernel(const double* __restrict__ G, double* __restrict__ factor) { if (threadIdx.x == 0 && blockIdx.x == 0) *factor = __ddiv_rn(255.0, G[255]); }
+__global__ void __launch_bounds__(256) rc_scale_kernel(double* __restrict__ v, size_t n, const double* __restrict__ factor) {
+    const double f = *factor;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = __dmul_rn(v[i], f);
+}
+
+// rmse(), :50-69: e = sum (G[b] - t*E)^2 * 1e-10 over finite residuals of unsaturated samples, num = their count.
+__global__ void __launch_bounds__(256) rc_rmse_kernel(const uint8_t* __restrict__ data, int n, size_t npix, const double* __restrict__ t,
+                                                      const double* __restrict__ G, const double* __restrict__ E, double* __restrict__ acc /*[2]*/) {
+    __shared__ double sG[256];
+    __shared__ double s_e[256], s_n[256];
+    sG[threadIdx.x] = G[threadIdx.x];
+    __syncthreads();
+    double e = 0.0, cnt = 0.0;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npix; k += stride) {
+        const double ek = E[k];
+        for (int i = 0; i < n; ++i) {
+            const unsigned b = data[static_cast<size_t>(i) * npix + k];
+            if (b == 255u) continue;
+            const double r = __dsub_rn(sG[b], __dmul_rn(__ldg(t + i), ek));
+            if (!isfinite(r)) continue;
+            e = __dadd_rn(e, __dmul_rn(__dmul_rn(r, r), 1e-10));
+            cnt = __dadd_rn(cnt, 1.0);
+        }
+    }
+    s_e[threadIdx.x] = e; s_n[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { s_e[threadIdx.x] += s_e[threadIdx.x + s]; s_n[threadIdx.x] += s_n[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(&acc[0], s_e[0]); atomicAdd(&acc[1], s_n[0]); }
+}
+
+static unsigned rc_blocks(size_t work) {
+    size_t b = (work + 255) / 256;
+    if (b > 148u * 8u) b = 148u * 8u;
+    return static_cast<unsigned>(b < 1 ? 1 : b);
+}
+cudaError_t launch_rc_leak_padding(const uint8_t* in, uint8_t* out, int n, int w, int h, cudaStream_t s) {
+    rc_leak_padding_kernel<<<rc_blocks(static_cast<size_t>(n) * w * h), 256, 0, s>>>(in, out, n, w, h);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cudaStream_t s) {
+    rc_einit_kernel<<<(npix + 255) / 256, 256, 0, s>>>(data, n, static_cast<size_t>(npix), E);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(gsum, 0, 256 * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+    rc_gstep_finish_kernel<<<1, 32, 0, s>>>(gsum, gnum, G);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s) {
+    rc_factor_kernel<<<1, 32, 0, s>>>(G, factor);
+    rc_scale_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(E, static_cast<size_t>(npix), factor);
+    rc_scale_kernel<<<1, 256, 0, s>>>(G, 256, factor);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    rc_rmse_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, G, E, acc2);
+    return cudaGetLastError();
+}
+
 }  // namespace mdc

@@ -288,3 +288,83 @@ def test_estep_non_finite_exposure_takes_the_select_path(api, port):
     E = torch.zeros(npix, dtype=torch.float64, device="cuda")
     ctx.estep(torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda(), E)
     assert_bits_equal(E.cpu().numpy(), exp, "E-step with t=inf")
+
+
+def test_response_calib_building_blocks(api, port):
+    """leak padding / E-init / rescale bit-exact; G-step and rmse to rounding (the reference sums
+    10^5..10^9 terms sequentially, the GPU in parallel): TOL_SUM relative."""
+    TOL_SUM = 1e-10
+    rng = np.random.default_rng(21)
+    n, w, h = 23, 96, 64
+    npix = w * h
+    data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+    data[:, 100:140] = 255                          # a saturated blob
+    data[3, 0] = data[5, npix - 1] = 255            # border pixels never spread
+    t = rng.uniform(0.05, 20.0, n).astype(np.float32).astype(np.float64)
+    ctx = api.Context(None, None, 0)
+    # leak padding, 0..3 iterations
+    for iters in (1, 2, 3):
+        d = torch.from_numpy(data.copy()).cuda()
+        ctx.rc_leak_padding(d, w, h, iters)
+        exp = np.stack([port.leak_padding(data[i], w, h, iters) for i in range(n)])
+        assert np.array_equal(d.cpu().numpy(), exp), f"leak padding x{iters}"
+    padded = np.stack([port.leak_padding(data[i], w, h, 2) for i in range(n)])
+    d = torch.from_numpy(padded).cuda()
+    dt = torch.from_numpy(t).cuda()
+    # E-init
+    E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+    ctx.rc_einit(d, E)
+    E_ref = port.einit(padded)
+    assert_bits_equal(E.cpu().numpy(), E_ref, "E-init")
+    # G-step
+    G = torch.zeros(256, dtype=torch.float64, device="cuda")
+    ctx.rc_gstep(d, dt, E, G)
+    G_ref = port.gstep(padded, t, E_ref)
+    g = G.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(G_ref))
+    m = ~np.isnan(G_ref)
+    assert np.max(np.abs(g[m] - G_ref[m]) / np.maximum(np.abs(G_ref[m]), 1e-300)) < TOL_SUM
+    # rmse
+    r = ctx.rc_rmse(d, dt, G, E)
+    r_ref = port.rmse(padded, t, G_ref, E_ref)
+    assert r[1] == r_ref[1] and abs(r[0] - r_ref[0]) <= TOL_SUM * 10 * abs(r_ref[0])
+    # rescale (bit-exact on identical inputs)
+    Gc, Ec = torch.from_numpy(G_ref.copy()).cuda(), torch.from_numpy(E_ref.copy()).cuda()
+    f = ctx.rc_rescale(Ec, Gc)
+    E2, G2 = E_ref.copy(), G_ref.copy()
+    f_ref = port.rescale(E2, G2)
+    assert f == f_ref
+    assert_bits_equal(Ec.cpu().numpy(), E2, "rescaled E")
+    assert_bits_equal(Gc.cpu().numpy(), G2, "rescaled G")
+
+
+def test_response_calib_loop(api, port):
+    """mdc_response_calib = E-init + nits x {G-step, E-step, rescale} against the same loop composed from the oracle."""
+    rng = np.random.default_rng(22)
+    n, npix = 40, 4096
+    # a synthetic exposure sweep of a fixed scene through a gamma response, so that the loop converges sensibly
+    scene = rng.uniform(5.0, 120.0, npix)
+    t = np.geomspace(0.1, 8.0, n).astype(np.float32).astype(np.float64)
+    irr = np.clip(scene[None, :] * t[:, None], 0, 255.0)
+    data = np.clip(np.rint(255.0 * (irr / 255.0) ** (1 / 2.2) + rng.normal(0, 1.0, irr.shape)), 0, 255).astype(np.uint8)
+    nits = 4
+    E_ref = port.einit(data)
+    G_ref = np.zeros(256)
+    for _ in range(nits):
+        G_ref = port.gstep(data, t, E_ref)
+        E_ref = port.estep(data, t, G_ref)
+        port.rescale(E_ref, G_ref)
+    r_ref = port.rmse(data, t, G_ref, E_ref)
+    ctx = api.Context(None, None, 0)
+    d, dt = torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda()
+    E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+    G = torch.zeros(256, dtype=torch.float64, device="cuda")
+    log = ctx.response_calib(d, dt, nits, E, G)
+    g, e = G.cpu().numpy(), E.cpu().numpy()
+    m = np.isfinite(G_ref)
+    assert np.array_equal(np.isfinite(g), m)
+    assert np.max(np.abs(g[m] - G_ref[m]) / np.maximum(np.abs(G_ref[m]), 1e-12)) < 1e-8
+    me = np.isfinite(E_ref)
+    assert np.max(np.abs(e[me] - E_ref[me]) / np.maximum(np.abs(E_ref[me]), 1e-12)) < 1e-8
+    assert log.shape == (nits, 4) and abs(log[-1, 2] - r_ref[0]) <= 1e-7 * abs(r_ref[0]) and log[-1, 3] == r_ref[1]
+    assert abs(g[255] - 255.0) < 1e-9
