@@ -21,6 +21,8 @@
 #define CV_8U 0
 #define CV_16U 2
 #define CV_32F 5
+#define CV_32FC1 5
+#define CV_8UC3 16
 #define CV_LOAD_IMAGE_UNCHANGED (-1)
 #define CV_LOAD_IMAGE_GRAYSCALE 0
 
@@ -29,7 +31,14 @@ typedef unsigned short ushort;
 
 namespace cv {
 
-inline int shim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : 4); }
+inline int shim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_8UC3 ? 3 : 4)); }
+
+struct Vec3b {
+    unsigned char v[3];
+    Vec3b() { v[0] = v[1] = v[2] = 0; }
+    Vec3b(unsigned char a, unsigned char b, unsigned char c) { v[0] = a; v[1] = b; v[2] = c; }
+};
+struct Scalar { double v; Scalar(double a = 0) : v(a) {} };
 
 class Mat {
 public:
@@ -48,6 +57,10 @@ public:
     template <typename T> T& at(int i) { return ((T*)data)[i]; }
     template <typename T> const T& at(int i) const { return ((const T*)data)[i]; }
     template <typename T> T& at(int r, int c) { return ((T*)data)[(size_t)r * cols + c]; }
+    Mat& setTo(const Scalar& s) {
+        if (type_ == CV_32F) for (size_t i = 0; i < (size_t)rows * cols; i++) at<float>((int)i) = (float)s.v;
+        return *this;
+    }
 
     Mat operator*(double s) const {
         Mat m(rows, cols, type_);

@@ -37,12 +37,14 @@ def test_compat_headers_compile_and_link(compat_exe):
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/src/main_playbackDataset.cpp"), reason="reference sources not present")
-def test_reference_playback_program_links_unchanged(tmp_path):
-    """playDataset (main_playbackDataset.cpp) is the link-compat consumer.  The file
-    is copied next to nothing else so that its `#include "BenchmarkDatasetReader.h"` resolves to ours."""
-    src = tmp_path / "main_playbackDataset.cpp"
-    shutil.copy("/root/reference/src/main_playbackDataset.cpp", src)
-    compile_cpp(str(src), str(tmp_path / "playDataset"))
+@pytest.mark.parametrize("program", ["main_playbackDataset.cpp", "main_responseCalib.cpp"])
+def test_reference_programs_link_unchanged(program, tmp_path):
+    """playDataset and responseCalib are the link-compat consumers: their unmodified
+    sources must compile and link against include/compat + libmdc_b200.so.  The file is copied next to nothing
+    else so that its `#include "BenchmarkDatasetReader.h"` resolves to ours.  (vignetteCalib needs aruco.)"""
+    src = tmp_path / program
+    shutil.copy("/root/reference/src/" + program, src)
+    compile_cpp(str(src), str(tmp_path / "prog"))
 
 
 def write_sequence(d, iw, ih, ow, oh, n):
