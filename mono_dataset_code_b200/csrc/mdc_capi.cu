@@ -74,7 +74,7 @@ struct mdc_ctx {
     int map_key_frames[kMapSlots] = {};
     int map_next = 0;
     // knobs
-    int use_tma = -1, ctas_per_sm = 0, chunk_frames = 0;
+    int use_tma = -1, ctas_per_sm = 0, chunk_frames = 0, tma_stages = 0;
     // streams + host pipeline scratch
     cudaStream_t stream = nullptr;
     cudaStream_t pipe_stream[kHostPipeDepth] = {nullptr, nullptr, nullptr};
@@ -234,6 +234,8 @@ int ctx_common_init(mdc_ctx* c, int device) {
     if (e) c->ctas_per_sm = atoi(e);
     e = getenv("MDC_CHUNK_FRAMES");
     if (e) c->chunk_frames = atoi(e);
+    e = getenv("MDC_TMA_STAGES");
+    if (e) c->tma_stages = atoi(e);
     return MDC_OK;
 }
 
@@ -314,7 +316,8 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
         if (rc != MDC_OK) return rc;
     }
     const int min_ctas = (c->ctas_per_sm > 0 && c->ctas_per_sm <= 2) ? 2 : 3;   // which register budget the kernel was compiled for
-    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma, u.vig, in_kernel > 1, min_ctas);
+    p.tma_stages = c->tma_stages > 0 ? std::min(std::max(c->tma_stages, 2), kMaxStages) : fused_tma_stages(p.box_px_max, min_ctas);
+    int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma ? p.tma_stages : kLdgStages, tma, u.vig, in_kernel > 1, min_ctas);
     if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
     if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
     const long long items = static_cast<long long>(p.n_tiles) * ((n_frames + p.chunk_frames - 1) / p.chunk_frames);

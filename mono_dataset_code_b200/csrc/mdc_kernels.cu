@@ -76,7 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// Producer-side wait: the producer is always up to kTmaStages frames ahead, so it polls politely
+// Producer-side wait: the producer is always up to `tma_stages` frames ahead, so it polls politely
 // (a spinning lane would steal issue slots from the consumer warps of its scheduler).
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -152,7 +152,7 @@ __device__ __forceinline__ float lut_value(const FusedParams& p, int v) {
 template <bool kTma, bool kVig, bool kPyr, int kMinCtas>
 __global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, kMinCtas)
 fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TmaMaps maps) {
-    constexpr int kNs = kTma ? kTmaStages : kLdgStages;
+    const int kNs = kTma ? p.tma_stages : kLdgStages;   // ring depth (runtime: as many stages as fit next to 3 CTAs/SM)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // ---- shared-memory carve-up (see fused_smem_bytes)
     float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
@@ -459,9 +459,19 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
 }
 
 // smem layout (bytes): lut 32768 | items 32 | barriers 8*(2*kMaxStages+2*kItemSlots) | pad -> kSmemHeaderBytes | stages
-size_t fused_smem_bytes(int box_px_max, bool tma) {
+size_t fused_smem_bytes(int box_px_max, int stages) {
     const size_t stage = (static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u);
-    return kSmemHeaderBytes + static_cast<size_t>(tma ? kTmaStages : kLdgStages) * stage;
+    return kSmemHeaderBytes + static_cast<size_t>(stages) * stage;
+}
+
+// Deepest TMA ring (2..kMaxStages) that still lets `ctas_per_sm` CTAs share an SM's 228 KB (1 KB reserved per CTA).
+int fused_tma_stages(int box_px_max, int ctas_per_sm) {
+    const size_t stage = (static_cast<size_t>(box_px_max) + 127u) & ~static_cast<size_t>(127u);
+    const size_t per_cta = (228u * 1024u) / static_cast<size_t>(ctas_per_sm) - 1024u;
+    int s = per_cta > kSmemHeaderBytes ? static_cast<int>((per_cta - kSmemHeaderBytes) / stage) : 2;
+    if (s > kMaxStages) s = kMaxStages;
+    if (s < 2) s = 2;
+    return s;
 }
 
 typedef void (*FusedKernelFn)(const FusedParams, const TmaMaps);
@@ -478,9 +488,9 @@ static FusedKernelFn fused_variant(bool tma, bool vig, bool pyr, int min_ctas) {
     return min_ctas <= 2 ? fused_variant_t<2>(tma, vig, pyr) : fused_variant_t<3>(tma, vig, pyr);
 }
 
-int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr, int min_ctas) {
+int fused_max_ctas_per_sm(int box_px_max, int stages, bool tma, bool vig, bool pyr, int min_ctas) {
     int n = 0;
-    const int smem = static_cast<int>(fused_smem_bytes(box_px_max, tma));
+    const int smem = static_cast<int>(fused_smem_bytes(box_px_max, stages));
     FusedKernelFn fn = fused_variant(tma, vig, pyr, min_ctas);
     // the opt-in limit must be raised before the occupancy query, or it reports 0 for > 48 KB
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
@@ -490,7 +500,7 @@ int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr, int min_
 
 cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, int min_ctas, cudaStream_t stream) {
     const bool tma = maps != nullptr;
-    const size_t smem = fused_smem_bytes(p.box_px_max, tma);
+    const size_t smem = fused_smem_bytes(p.box_px_max, tma ? p.tma_stages : kLdgStages);
     FusedKernelFn fn = fused_variant(tma, p.use_vig != 0, p.levels > 1, min_ctas);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;

@@ -14,11 +14,10 @@ constexpr int kConsumers = 256;      // 8 consumer warps; warp w owns tile rows 
 constexpr int kThreads = kConsumers;
 constexpr int kInKernelLevels = 3;   // levels 0..2 come out of the fused kernel's (warp-local) epilogue; deeper levels use K2
 constexpr int kMaxBoxWordsPerThread = 8;   // LDG loader: u32 words of the input box prefetched per thread
-constexpr int kTmaStages = 3;         // TMA loader: u8 box stages in the full/empty mbarrier ring
 constexpr int kLdgStages = 2;         // LDG loader: double buffer
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kItemSlots = 4;          // work items in flight between the producer warp and the consumers
-constexpr int kSmemHeaderBytes = 33024;   // lut 32768 + item ring 32 + 16 mbarriers 128, rounded up to 128
+constexpr int kSmemHeaderBytes = 33024;   // lut 32768 + item ring 32 + 24 mbarriers 192, rounded up to 128
 constexpr int kMaxClasses = 64;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
 
 // How a tile's input pixels are fetched.
@@ -54,11 +53,13 @@ struct FusedParams {
     unsigned lut_gamma, use_vig, kill;   // sanitised unMapImage flags
     int box_px_max;              // largest staged box (pixels) -> smem carve-up
     int chunk_frames;            // frames per schedule chunk (L2 residency of the inputs)
+    int tma_stages;              // depth of the TMA stage ring (2..kMaxStages)
 };
 
-size_t fused_smem_bytes(int box_px_max, bool tma);
+size_t fused_smem_bytes(int box_px_max, int stages);
+int fused_tma_stages(int box_px_max, int ctas_per_sm);
 cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, int min_ctas, cudaStream_t stream);  // maps == nullptr: LDG loader
-int fused_max_ctas_per_sm(int box_px_max, bool tma, bool vig, bool pyr, int min_ctas);
+int fused_max_ctas_per_sm(int box_px_max, int stages, bool tma, bool vig, bool pyr, int min_ctas);
 
 cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, const float* ginv, const float* vinv,
                          unsigned kill, cudaStream_t stream);
