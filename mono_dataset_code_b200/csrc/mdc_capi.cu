@@ -315,7 +315,9 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
         int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
         if (rc != MDC_OK) return rc;
     }
-    const int min_ctas = (c->ctas_per_sm > 0 && c->ctas_per_sm <= 2) ? 2 : 3;   // which register budget the kernel was compiled for
+    // Register budget / residency the kernel variant was compiled for.  Measured optimum: 3 CTAs/SM (72 registers) for
+    // the plain variant; the pyramid variant needs ~80 registers and is faster spill-free at 2 CTAs/SM with a deeper ring.
+    const int min_ctas = c->ctas_per_sm > 0 ? (c->ctas_per_sm <= 2 ? 2 : 3) : (in_kernel > 1 ? 2 : 3);
     p.tma_stages = c->tma_stages > 0 ? std::min(std::max(c->tma_stages, 2), kMaxStages) : fused_tma_stages(p.box_px_max, min_ctas);
     int per_sm = fused_max_ctas_per_sm(p.box_px_max, tma ? p.tma_stages : kLdgStages, tma, u.vig, in_kernel > 1, min_ctas);
     if (per_sm < 1) { mdc_set_error("fused kernel does not fit on an SM (box %d px)", p.box_px_max); return MDC_ERR_CUDA; }
