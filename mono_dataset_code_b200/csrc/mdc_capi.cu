@@ -326,9 +326,16 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(items, 1)));
     CU_CHECK(launch_fused(p, maps, grid, min_ctas, stream));
     c->launches++;
-    // levels beyond the fused epilogue: stand-alone K2 chain
-    for (int l = in_kernel; l < levels; ++l) {
-        CU_CHECK(launch_pyr_down(d_out_levels[l - 1], c->out_w >> (l - 1), c->out_h >> (l - 1), d_out_levels[l], n_frames, stream));
+    // levels beyond the fused epilogue: stand-alone K2 chain, two levels per launch where possible
+    for (int l = in_kernel; l < levels;) {
+        const int sw = c->out_w >> (l - 1), sh = c->out_h >> (l - 1);
+        if (l + 1 < levels) {
+            CU_CHECK(launch_pyr_down2(d_out_levels[l - 1], sw, sh, d_out_levels[l], d_out_levels[l + 1], n_frames, stream));
+            l += 2;
+        } else {
+            CU_CHECK(launch_pyr_down(d_out_levels[l - 1], sw, sh, d_out_levels[l], n_frames, stream));
+            l += 1;
+        }
         c->launches++;
     }
     return MDC_OK;

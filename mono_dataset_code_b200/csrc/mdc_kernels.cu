@@ -612,6 +612,46 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__
     }
 }
 
+// Two levels in one pass (used for levels 3+4 behind the fused kernel): each thread owns one 2x2 block of the first
+// destination level — i.e. a 4x4 block of the source — writes those up to 4 pixels and, if complete, the pixel of the
+// second destination level.  Same arithmetic as two pyr_down_kernel passes (the intermediate values are identical).
+__global__ void __launch_bounds__(256) pyr_down2_kernel(const float* __restrict__ src, int sw, int sh, float* __restrict__ d1,
+                                                        float* __restrict__ d2, int n_frames) {
+    const int w1 = sw >> 1, h1 = sh >> 1, w2 = w1 >> 1, h2 = h1 >> 1;
+    const int bw = (w1 + 1) >> 1, bh = (h1 + 1) >> 1;
+    const size_t per = static_cast<size_t>(bw) * bh, total = per * n_frames;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t f = i / per, r = i - f * per;
+        const int by = static_cast<int>(r / bw), bx = static_cast<int>(r - static_cast<size_t>(by) * bw);
+        const float* s = src + f * static_cast<size_t>(sw) * sh;
+        float v[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int x = 2 * bx + dx, y = 2 * by + dy;
+                if (x < w1 && y < h1) {
+                    const float* q = s + static_cast<size_t>(2 * y) * sw + 2 * x;
+                    v[dy][dx] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(__ldg(q), __ldg(q + 1)), __ldg(q + sw)), __ldg(q + sw + 1)));
+                    d1[f * static_cast<size_t>(w1) * h1 + static_cast<size_t>(y) * w1 + x] = v[dy][dx];
+                }
+            }
+        if (bx < w2 && by < h2)
+            d2[f * static_cast<size_t>(w2) * h2 + static_cast<size_t>(by) * w2 + bx] =
+                __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(v[0][0], v[0][1]), v[1][0]), v[1][1]));
+    }
+}
+
+cudaError_t launch_pyr_down2(const float* src, int sw, int sh, float* d1, float* d2, int n_frames, cudaStream_t stream) {
+    const size_t total = static_cast<size_t>(((sw >> 1) + 1) >> 1) * (((sh >> 1) + 1) >> 1) * n_frames;
+    if (total == 0) return cudaSuccess;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    pyr_down2_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, sw, sh, d1, d2, n_frames);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_frames, cudaStream_t stream) {
     const size_t total = static_cast<size_t>(sw >> 1) * (sh >> 1) * n_frames;
     if (total == 0) return cudaSuccess;

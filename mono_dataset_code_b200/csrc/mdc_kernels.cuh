@@ -66,6 +66,7 @@ cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, 
 cudaError_t launch_undistort_f32(const float* in, float* out, int in_w, int n_in, int n_out, int n_frames,
                                  const float* remap_x, const float* remap_y, cudaStream_t stream);
 cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_frames, cudaStream_t stream);
+cudaError_t launch_pyr_down2(const float* src, int sw, int sh, float* d1, float* d2, int n_frames, cudaStream_t stream);
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E,
                          cudaStream_t stream);
 
