@@ -326,6 +326,13 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
     e2e = {"value": world * EB * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": EB * n_in,
            "d2h_bytes_per_step": EB * n_out * 4, "frames_per_step": EB, "steps": e2e_steps}
+    # latency of ONE frame through the same entry point (what DatasetReader::getImage does per call)
+    for _ in range(3):
+        ctx.prepare_batch_host(np_in[:1], FLAGS_ALL, [h_out.value])
+    t0 = time.perf_counter()
+    for i in range(50):
+        ctx.prepare_batch_host(np_in[i % EB:i % EB + 1], FLAGS_ALL, [h_out.value])
+    e2e["single_frame_ms"] = 1e3 * (time.perf_counter() - t0) / 50
     _lib.lib.mdc_host_free(h_in); _lib.lib.mdc_host_free(h_out)
 
     if rank == 0:
