@@ -1,20 +1,22 @@
 // DatasetReader — drop-in for the reference's sequence reader (src/BenchmarkDatasetReader.h:44-345).
 //
-// File handling (images/ folder or images.zip via libzip, times.txt, cv::imread / cv::imdecode) is
-// ordinary host code and stays as the reference has it; image decode is out of scope for the B200
-// path.  What changes is getImage(): instead of running unMapImage into a
-// temporary float image and then undistort<float> on the CPU (:222-223), the raw 8-bit frame goes to
-// the GPU once and the whole mode switch of :210-241 is one fused sm_100a kernel
-// (mdc_prepare_batch_host), bit-identical to the reference's result.
+// Public surface kept: getdir(), DatasetReader(folder), getUndistorter(), getPhotoUndistorter(), getNumImages(),
+// getTimestamp(), getExposure(), getImage(), getImageRaw_internal().  File handling (an images/ folder or
+// images.zip through libzip, times.txt, cv::imread / cv::imdecode) is ordinary host code; image decode is out
+// of scope for the B200 path.
 //
-// Same public surface: getdir(), DatasetReader(folder), getUndistorter(), getPhotoUndistorter(),
-// getNumImages(), getTimestamp(), getExposure(), getImage(), getImageRaw_internal().
+// What changes is getImage(): the reference runs unMapImage into a temporary float image and then
+// undistort<float> on the CPU (:222-223).  Here the raw 8-bit frame goes to the GPU once and the whole mode
+// switch of :210-241 is ONE fused sm_100a kernel launch (mdc_prepare_batch_host) whose result is bit-identical
+// to the reference's; all four calibration tables live in one device context owned by the reader.
 #pragma once
-#include <sstream>
-#include <fstream>
-#include <dirent.h>
 #include <algorithm>
 #include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <dirent.h>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -24,23 +26,22 @@
 
 #include "zip.h"
 
-// Lists `dir` (sorted, full paths) into `files`; -1 if the directory cannot be opened.
+// Sorted list of the entries of `dir` (full paths appended to `files`); -1 if it cannot be opened.
 inline int getdir(std::string dir, std::vector<std::string> &files)
 {
 	DIR* handle = opendir(dir.c_str());
 	if(handle == NULL) return -1;
-	for(struct dirent* entry = readdir(handle); entry != NULL; entry = readdir(handle))
+	while(struct dirent* entry = readdir(handle))
 	{
 		const std::string name(entry->d_name);
-		if(name == "." || name == "..") continue;
-		files.push_back(name);
+		if(name != "." && name != "..") files.push_back(name);
 	}
 	closedir(handle);
 	std::sort(files.begin(), files.end());
 
-	if(dir.empty() || dir[dir.length()-1] != '/') dir += "/";
-	for(size_t i=0;i<files.size();i++)
-		if(files[i].at(0) != '/') files[i] = dir + files[i];
+	if(dir.empty() || dir[dir.size()-1] != '/') dir.push_back('/');
+	for(std::vector<std::string>::iterator it = files.begin(); it != files.end(); ++it)
+		if((*it)[0] != '/') *it = dir + *it;
 	return (int)files.size();
 }
 
@@ -48,54 +49,13 @@ class DatasetReader
 {
 public:
 	DatasetReader(std::string folder)
-		: path(folder), isZipped(false), undistorter(0), photoUndistorter(0), ziparchive(0), databuffer(0), deviceContext(0)
+		: width(0), height(0), widthOrg(0), heightOrg(0), path(folder), isZipped(false),
+		  undistorter(0), photoUndistorter(0), ziparchive(0), deviceContext(0)
 	{
-		getdir(path+"images/", files);
-		if(!files.empty())
-		{
-			printf("Load Dataset %s: found %d files in folder /images; assuming that all images are there.\n",
-					path.c_str(), (int)files.size());
-		}
-		else
-		{
-			printf("Load Dataset %s: found no in folder /images; assuming that images are zipped.\n", path.c_str());
-			isZipped = true;
-			int ziperror = 0;
-			ziparchive = zip_open((path+"images.zip").c_str(), ZIP_RDONLY, &ziperror);
-			if(ziperror != 0)
-			{
-				printf("ERROR %d reading archive %s!\n", ziperror, (path+"images.zip").c_str());
-				exit(1);
-			}
-			files.clear();
-			const int numEntries = (int)zip_get_num_entries(ziparchive, 0);
-			for(int k=0;k<numEntries;k++)
-			{
-				const std::string entry(zip_get_name(ziparchive, k, ZIP_FL_ENC_STRICT));
-				if(entry == "." || entry == "..") continue;
-				files.push_back(entry);
-			}
-			printf("got %d entries and %d files from zipfile!\n", numEntries, (int)files.size());
-			std::sort(files.begin(), files.end());
-		}
-		loadTimestamps(path+"times.txt");
-
-		// calibration models (host) ...
-		undistorter = new UndistorterFOV((path+"camera.txt").c_str());
-		photoUndistorter = new PhotometricUndistorter(path+"pcalib.txt", path+"vignette.png",
-				undistorter->getInputDims()[0], undistorter->getInputDims()[1]);
-		widthOrg = undistorter->getInputDims()[0];
-		heightOrg = undistorter->getInputDims()[1];
-		width = undistorter->getOutputDims()[0];
-		height = undistorter->getOutputDims()[1];
-
-		// ... and one device context holding all four tables for the fused getImage kernel
-		if(mdc_ctx_create(UndistorterFOV::b200Device(), undistorter->b200Model(), photoUndistorter->b200Model(), &deviceContext) != MDC_OK)
-		{
-			printf("DatasetReader: cannot create the B200 device context: %s\n", mdc_last_error());
-			deviceContext = 0;
-		}
-		printf("Dataset %s: Got %d files!\n", path.c_str(), (int)getNumImages());
+		locateImages();
+		loadTimestamps(path + "times.txt");
+		loadCalibration();
+		printf("Dataset %s: Got %d files!\n", path.c_str(), getNumImages());
 	}
 	~DatasetReader()
 	{
@@ -103,16 +63,15 @@ public:
 		delete undistorter;
 		delete photoUndistorter;
 		if(ziparchive != 0) zip_close(ziparchive);
-		delete[] databuffer;
 	}
 
 	UndistorterFOV* getUndistorter() { return undistorter; }
 	PhotometricUndistorter* getPhotoUndistorter() { return photoUndistorter; }
 	int getNumImages() { return (int)files.size(); }
-	double getTimestamp(int id) { return (id < 0 || id >= (int)timestamps.size()) ? 0 : timestamps[id]; }
-	float getExposure(int id) { return (id < 0 || id >= (int)exposures.size()) ? 0 : exposures[id]; }
+	double getTimestamp(int id) { return inRange(id, timestamps.size()) ? timestamps[id] : 0; }
+	float getExposure(int id) { return inRange(id, exposures.size()) ? exposures[id] : 0; }
 
-	// Returns a heap ExposureImage the caller deletes, or 0 if the decoded frame has the wrong size/type.
+	// Heap ExposureImage the caller deletes; 0 if the decoded frame has the wrong size or type.
 	ExposureImage* getImage(int id, bool rectify, bool removeGamma, bool removeVignette, bool nanOverexposed)
 	{
 		assert(id >= 0 && id < (int)files.size());
@@ -129,62 +88,112 @@ public:
 			return 0;
 		}
 
-		const bool rectified = rectify;
-		ExposureImage* ret = new ExposureImage(rectified ? width : widthOrg, rectified ? height : heightOrg,
+		ExposureImage* result = new ExposureImage(rectify ? width : widthOrg, rectify ? height : heightOrg,
 				timestamps[id], exposures[id], id);
-		const unsigned flags = (rectify ? MDC_RECTIFY : 0u) | (removeGamma ? MDC_REMOVE_GAMMA : 0u)
-				| (removeVignette ? MDC_REMOVE_VIGNETTE : 0u) | (nanOverexposed ? MDC_NAN_OVEREXPOSED : 0u);
-		float* levels[1] = { ret->image };
-		int status = deviceContext != 0 ? mdc_prepare_batch_host(deviceContext, imageRaw.data, 1, flags, levels, 1) : MDC_ERR_CUDA;
-		if(status == MDC_ERR_INVALID_OBJECT)
-			return ret;   // invalid rectifier: like the reference, the image is returned unwritten (undistort is a no-op)
-		if(status != MDC_OK)
+		unsigned mode = 0;
+		if(rectify) mode |= MDC_RECTIFY;
+		if(removeGamma) mode |= MDC_REMOVE_GAMMA;
+		if(removeVignette) mode |= MDC_REMOVE_VIGNETTE;
+		if(nanOverexposed) mode |= MDC_NAN_OVEREXPOSED;
+		float* level0[1] = { result->image };
+		const int status = (deviceContext != 0)
+				? mdc_prepare_batch_host(deviceContext, imageRaw.data, 1, mode, level0, 1) : MDC_ERR_CUDA;
+		// an invalid rectifier leaves the image unwritten, like the reference (undistort is then a no-op)
+		if(status != MDC_OK && status != MDC_ERR_INVALID_OBJECT)
 			printf("DatasetReader::getImage: %s\n", deviceContext != 0 ? mdc_last_error() : "no device context");
-		return ret;
+		return result;
 	}
 
 	cv::Mat getImageRaw_internal(int id)
 	{
-		if(!isZipped)
-			return cv::imread(files[id], CV_LOAD_IMAGE_GRAYSCALE);
-
-		// zipped: inflate into a scratch buffer (grown once if the first guess is too small), then decode
-		long capacity = (long)widthOrg*heightOrg*6+10000;
-		if(databuffer == 0) databuffer = new char[capacity];
-		zip_file_t* entry = zip_fopen(ziparchive, files[id].c_str(), 0);
-		long readbytes = zip_fread(entry, databuffer, capacity);
-		if(readbytes > (long)widthOrg*heightOrg*6)
-		{
-			printf("read %ld/%ld bytes for file %s. increase buffer!!\n", readbytes, capacity, files[id].c_str());
-			delete[] databuffer;
-			capacity = (long)widthOrg*heightOrg*60+1000000;
-			databuffer = new char[capacity];
-			entry = zip_fopen(ziparchive, files[id].c_str(), 0);
-			readbytes = zip_fread(entry, databuffer, capacity-900000);
-			if(readbytes > capacity-990000)
-			{
-				printf("buffer still to small (read %ld/%ld). abort.\n", readbytes, capacity-900000);
-				exit(1);
-			}
-		}
-		return cv::imdecode(cv::Mat((int)readbytes, 1, CV_8U, databuffer), CV_LOAD_IMAGE_GRAYSCALE);
+		if(!isZipped) return cv::imread(files[id], CV_LOAD_IMAGE_GRAYSCALE);
+		long bytes = readArchiveEntry(id);
+		return cv::imdecode(cv::Mat((int)bytes, 1, CV_8U, &databuffer[0]), CV_LOAD_IMAGE_GRAYSCALE);
 	}
 
 private:
-	// times.txt: "id stamp [exposure_ms]" per line; on a count mismatch everything is zeroed.
-	inline void loadTimestamps(std::string timesFile)
+	static bool inRange(int id, size_t n) { return id >= 0 && id < (int)n; }
+
+	// images/ folder if it has entries, else images.zip (exit(1) if that cannot be opened, like the reference)
+	void locateImages()
 	{
-		timestamps.clear();
-		exposures.clear();
+		getdir(path + "images/", files);
+		if(!files.empty())
+		{
+			printf("Load Dataset %s: found %d files in folder /images; assuming that all images are there.\n",
+					path.c_str(), (int)files.size());
+			return;
+		}
+		printf("Load Dataset %s: found no in folder /images; assuming that images are zipped.\n", path.c_str());
+		isZipped = true;
+		const std::string archive = path + "images.zip";
+		int ziperror = 0;
+		ziparchive = zip_open(archive.c_str(), ZIP_RDONLY, &ziperror);
+		if(ziperror != 0)
+		{
+			printf("ERROR %d reading archive %s!\n", ziperror, archive.c_str());
+			exit(1);
+		}
+		const int numEntries = (int)zip_get_num_entries(ziparchive, 0);
+		for(int k = 0; k < numEntries; k++)
+		{
+			const std::string entry(zip_get_name(ziparchive, k, ZIP_FL_ENC_STRICT));
+			if(entry != "." && entry != "..") files.push_back(entry);
+		}
+		printf("got %d entries and %d files from zipfile!\n", numEntries, (int)files.size());
+		std::sort(files.begin(), files.end());
+	}
+
+	// calibration models on the host + one device context holding all four tables for the fused kernel
+	void loadCalibration()
+	{
+		undistorter = new UndistorterFOV((path + "camera.txt").c_str());
+		widthOrg = undistorter->getInputDims()[0];
+		heightOrg = undistorter->getInputDims()[1];
+		width = undistorter->getOutputDims()[0];
+		height = undistorter->getOutputDims()[1];
+		photoUndistorter = new PhotometricUndistorter(path + "pcalib.txt", path + "vignette.png", widthOrg, heightOrg);
+		if(mdc_ctx_create(UndistorterFOV::b200Device(), undistorter->b200Model(), photoUndistorter->b200Model(),
+				&deviceContext) != MDC_OK)
+		{
+			printf("DatasetReader: cannot create the B200 device context: %s\n", mdc_last_error());
+			deviceContext = 0;
+		}
+	}
+
+	// inflate entry `id` into databuffer; first guess 6 bytes/pixel, one retry at 60 bytes/pixel, then give up
+	long readArchiveEntry(int id)
+	{
+		const long pixels = (long)widthOrg * heightOrg;
+		if(databuffer.empty()) databuffer.resize(pixels*6 + 10000);
+		zip_file_t* entry = zip_fopen(ziparchive, files[id].c_str(), 0);
+		long got = zip_fread(entry, &databuffer[0], (long)databuffer.size());
+		if(got > pixels*6)
+		{
+			printf("read %ld/%ld bytes for file %s. increase buffer!!\n", got, (long)databuffer.size(), files[id].c_str());
+			databuffer.assign(pixels*60 + 1000000, 0);
+			entry = zip_fopen(ziparchive, files[id].c_str(), 0);
+			got = zip_fread(entry, &databuffer[0], pixels*60 + 100000);
+			if(got > pixels*60 + 10000)
+			{
+				printf("buffer still to small (read %ld/%ld). abort.\n", got, pixels*60 + 100000);
+				exit(1);
+			}
+		}
+		return got;
+	}
+
+	// times.txt: "id stamp [exposure_ms]" per line; on a count mismatch everything is zeroed
+	void loadTimestamps(std::string timesFile)
+	{
 		std::ifstream in(timesFile.c_str());
-		std::string line;
-		while(std::getline(in, line))
+		for(std::string line; std::getline(in, line);)
 		{
 			int id; double stamp; float exposure = 0;
-			const int got = sscanf(line.c_str(), "%d %lf %f", &id, &stamp, &exposure);
-			if(got < 2) continue;
+			const int fields = sscanf(line.c_str(), "%d %lf %f", &id, &stamp, &exposure);
+			if(fields < 2) continue;
 			timestamps.push_back(stamp);
-			exposures.push_back(got == 3 ? exposure : 0);
+			exposures.push_back(fields == 3 ? exposure : 0);
 		}
 		if((int)exposures.size() != getNumImages())
 		{
@@ -197,14 +206,14 @@ private:
 	std::vector<std::string> files;
 	std::vector<double> timestamps;
 	std::vector<float> exposures;
-	int width, height;
-	int widthOrg, heightOrg;
+	int width, height;          // rectified size
+	int widthOrg, heightOrg;    // raw size
 	std::string path;
 	bool isZipped;
 
 	UndistorterFOV* undistorter;
 	PhotometricUndistorter* photoUndistorter;
 	zip_t* ziparchive;
-	char* databuffer;
+	std::vector<char> databuffer;
 	mdc_ctx* deviceContext;
 };
