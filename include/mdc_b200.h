@@ -118,6 +118,8 @@ int mdc_ctx_create(int device, const mdc_fov* fov, const mdc_photo* photo, mdc_c
 int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h, int out_w, int out_h,
                                       const float* d_remap_x, const float* d_remap_y,
                                       const float* d_ginv256, const float* d_vinv, mdc_ctx** out);
+/* After this call the context frees (cudaFree) the tables it adopted in mdc_ctx_create_from_device_tables. */
+int mdc_ctx_take_table_ownership(mdc_ctx* c);
 void mdc_ctx_destroy(mdc_ctx* c);
 int mdc_ctx_device_tables(const mdc_ctx* c, const float** d_remap_x, const float** d_remap_y,
                           const float** d_ginv256, const float** d_vinv);

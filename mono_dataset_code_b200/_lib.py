@@ -47,6 +47,7 @@ SIGNATURES = {
     "mdc_photo_vignette_map_inv": (_f32p, [_vp]),
     "mdc_ctx_create": (C.c_int, [C.c_int, _vp, _vp, C.POINTER(_vp)]),
     "mdc_ctx_create_from_device_tables": (C.c_int, [C.c_int] * 5 + [_vp] * 4 + [C.POINTER(_vp)]),
+    "mdc_ctx_take_table_ownership": (C.c_int, [_vp]),
     "mdc_ctx_destroy": (None, [_vp]),
     "mdc_ctx_device_tables": (C.c_int, [_vp] + [C.POINTER(_vp)] * 4),
     "mdc_ctx_level_dims": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -63,6 +63,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     if force or rebuilt or _newer(LIB, objs):
         _run([nvcc, "-ccbin", gxx, *GENCODE, "-shared", "-o", LIB, *objs, "-lz", "-cudart", "static"], log)
+    # optional native-NCCL init helper for C++ hosts (needs the system libnccl + nccl.h; skipped silently otherwise)
+    nccl_src = os.path.join(CSRC, "mdc_nccl.cu")
+    nccl_lib = os.path.join(LIB_DIR, "libmdc_b200_nccl.so")
+    if os.path.exists("/usr/include/nccl.h") and (force or _newer(nccl_lib, [nccl_src, LIB] + headers)):
+        _run([nvcc, "-ccbin", gxx, *GENCODE, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", *inc, "-shared", "-o", nccl_lib, nccl_src,
+              "-L" + LIB_DIR, "-lmdc_b200", "-lnccl", "-Xlinker", "-rpath=$ORIGIN", "-cudart", "static"], log)
     if verbose:
         sys.stderr.write("".join(log))
     return LIB

@@ -426,6 +426,12 @@ extern "C" int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h,
     return MDC_OK;
 }
 
+extern "C" int mdc_ctx_take_table_ownership(mdc_ctx* c) {
+    if (!c) return MDC_ERR_INVALID_ARG;
+    c->owns_tables = true;
+    return MDC_OK;
+}
+
 extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
