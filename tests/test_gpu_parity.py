@@ -368,3 +368,28 @@ def test_response_calib_loop(api, port):
     assert np.max(np.abs(e[me] - E_ref[me]) / np.maximum(np.abs(E_ref[me]), 1e-12)) < 1e-8
     assert log.shape == (nits, 4) and abs(log[-1, 2] - r_ref[0]) <= 1e-7 * abs(r_ref[0]) and log[-1, 3] == r_ref[1]
     assert abs(g[255] - 255.0) < 1e-9
+
+
+@pytest.mark.parametrize("cfg", [
+    (1280, 1024, 64, 48, "crop", S.TUM_CALIB),          # 20x minification: boxes far too large to stage -> direct global-gather tiles
+    (800, 608, 96, 40, "0.9 1.2 0.5 0.5 0", S.TUM_CALIB),   # mixed: some tiles staged, some direct, some black
+    (64, 48, 1, 1, "crop", S.TUM_CALIB),                # single output pixel
+    (16, 2, 33, 7, "crop", (0.5, 0.5, 0.5, 0.5, 0.3)),  # degenerate input height (only row 0..1 usable)
+], ids=["minify20", "mixed_modes", "one_pixel", "thin_input"])
+def test_unusual_geometries(cfg, api, port, dataset_dir):
+    iw, ih, ow, oh, mode, calib = cfg
+    files = dataset_dir(cfg)
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(5, iw, ih)
+    d = torch.from_numpy(frames).cuda()
+    for use_tma in (-1, 0):
+        prep.ctx.configure(use_tma=use_tma)
+        for flags in ((1, 1, 1, 1), (1, 0, 0, 0), (1, 1, 0, 1)):
+            levels = 4
+            outs = [o.cpu().numpy() for o in prep.prepare_device(d, *flags, levels=levels)]
+            for i in range(frames.shape[0]):
+                exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], *flags), ow, oh, levels)
+                for l in range(levels):
+                    assert_bits_equal(outs[l][i], exp[l], f"{cfg[:4]} tma={use_tma} flags={flags} frame={i} level={l}")
