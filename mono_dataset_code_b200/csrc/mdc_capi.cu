@@ -542,10 +542,12 @@ extern "C" int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_fram
         mdc_set_error("mdc_prepare_batch: bad argument");
         return MDC_ERR_INVALID_ARG;
     }
-    for (int l = 0; l < levels; ++l)
-        if (!d_out_levels[l]) { mdc_set_error("mdc_prepare_batch: output level %d is NULL", l); return MDC_ERR_INVALID_ARG; }
     if (c->in_w < 1) { mdc_set_error("mdc_prepare_batch: context has no image geometry"); return MDC_ERR_INVALID_OBJECT; }
     const bool rectify = (flags & MDC_RECTIFY) != 0;
+    for (int l = 0; l < levels; ++l) {   // a level that has no pixels (tiny images) may legitimately be a NULL buffer
+        const int lw = (rectify ? c->out_w : c->in_w) >> l, lh = (rectify ? c->out_h : c->in_h) >> l;
+        if (!d_out_levels[l] && lw > 0 && lh > 0) { mdc_set_error("mdc_prepare_batch: output level %d is NULL", l); return MDC_ERR_INVALID_ARG; }
+    }
     if (rectify && !c->have_fov) { mdc_set_error("getImage(rectify) on an invalid rectifier"); return MDC_ERR_INVALID_OBJECT; }
     if (n_frames == 0) return MDC_OK;
     CU_CHECK(cudaSetDevice(c->device));
