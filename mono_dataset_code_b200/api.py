@@ -55,9 +55,9 @@ class UndistorterFOV:
     def __del__(self):
         if getattr(self, "_ctx", None) is not None:
             self._ctx.close()
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.mdc_fov_destroy(self._h)
-            self._h = None
+        self._h = None
 
     # ---- getters (FOVUndistorter.h:49-83)
     def isValid(self) -> bool:
@@ -160,9 +160,9 @@ class PhotometricUndistorter:
     def __del__(self):
         if getattr(self, "_ctx", None) is not None:
             self._ctx.close()
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.mdc_photo_destroy(self._h)
-            self._h = None
+        self._h = None
 
     @property
     def validGamma(self) -> bool:
@@ -221,9 +221,9 @@ class Context:
         return cls(None, None, device, _adopt=((in_w, in_h, out_w, out_h), (rx, ry, ginv, vinv)))
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:   # `lib` is already gone during interpreter shutdown
             lib.mdc_ctx_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()
