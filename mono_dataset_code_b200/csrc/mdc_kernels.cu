@@ -662,105 +662,86 @@ cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_
 }
 
 // =====================================================================================
-// K3: responseCalib E-step.  One lane per 4 adjacent pixels (32-bit loads), sequential over the n exposures in
-// the reference's order, fp64 with explicit non-fused multiplies/adds  ->  bit-identical to
-// main_responseCalib.cpp:324-338.
+// K3: responseCalib E-step.  One lane per pixel, sequential over the n exposures in the reference's order, fp64
+// with explicit non-fused multiplies/adds  ->  bit-identical to main_responseCalib.cpp:324-338.
 //
-// Layout of the work: a warp-task is 128 contiguous pixels; persistent warps take tasks round-robin.  The
-// launcher picks the number of resident warps so that tasks/warp is just below an integer (the work per task
-// is uniform, so quantisation is the only imbalance).  Loads are software-pipelined: while the 8 exposures of
-// one group are accumulated, the 8 words of the next group are already in flight in registers.
+// Layout of the work: a warp-task is 32 contiguous pixels (one 32-byte sector per exposure); persistent warps take
+// tasks round-robin.  The work per task is uniform, so the only imbalance is quantisation — ceil(tasks/warps) —
+// which small tasks keep at a few per cent (a 4-pixel-per-lane version lost 30-50 % to it).  Loads are
+// software-pipelined: while the 8 exposures of one group are accumulated, the 8 bytes of the next group are in flight.
 // =====================================================================================
 constexpr int kEstepGroup = 8;       // exposures per software-pipeline stage
-constexpr int kEstepMaxN = 2048;     // exposure times (t, t*t) cached in shared memory up to this n; beyond, read through L1
-
-__device__ __forceinline__ void estep_accumulate(uint32_t v, double ti, double tt, const double* gl, bool exact_zero_ok, double esum[4], double enumr[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const unsigned b = (v >> (8 * j)) & 0xffu;
-        const double prod = __dmul_rn(gl[b << 4], ti);
-        if (exact_zero_ok) {
-            // saturated samples contribute exact zeros (table entry 255 == +0.0, t*t selected to +0.0): adding a signed
-            // zero cannot change these sums (they start at +0.0 and RN addition yields -0.0 only from two -0.0 operands)
-            enumr[j] = __dadd_rn(enumr[j], b != 255u ? tt : 0.0);
-            esum[j] = __dadd_rn(esum[j], prod);
-        } else if (b != 255u) {          // main_responseCalib.cpp:329
-            enumr[j] = __dadd_rn(enumr[j], tt);
-            esum[j] = __dadd_rn(esum[j], prod);
-        }
-    }
-}
+constexpr int kEstepMaxN = 1024;     // (t, t*t) pairs cached in shared memory up to this n; beyond, read through L1
 
 __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
                                                     const double* __restrict__ t, const double* __restrict__ G,
-                                                    double* __restrict__ E, int vec_ok) {
+                                                    double* __restrict__ E) {
     extern __shared__ __align__(16) double smem_d[];
     // G[256] replicated 16x (slot = lane & 15): a 64-bit shared load is served per half-warp, so with one slot per lane
     // of the half-warp the data-dependent lookup is bank-conflict-free.
-    double* sG = smem_d;                      // [256*16]
-    double* sT = smem_d + 256 * 16;           // [min(n, kEstepMaxN)] t[i]
-    double* sTT = sT + kEstepMaxN;            // [min(n, kEstepMaxN)] t[i]*t[i]
+    double* sG = smem_d;                                              // [256*16]
+    double2* sT = reinterpret_cast<double2*>(smem_d + 256 * 16);      // [min(n, kEstepMaxN)] {t[i], t[i]*t[i]}
     int bad = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double ti = t[i];
         bad |= !isfinite(ti);
-        if (i < kEstepMaxN) { sT[i] = ti; sTT[i] = __dmul_rn(ti, ti); }
+        if (i < kEstepMaxN) sT[i] = make_double2(ti, __dmul_rn(ti, ti));
     }
-    // fast path needs every t[i] finite (0*inf = NaN would leak out of the zeroed table entry)
+    // Saturated samples (b == 255) are skipped in the reference (:329).  Fast path: give them exact-zero contributions
+    // instead — table entry 255 := +0.0 (so G[255]*t = +-0) and t*t selected to +0.0 — because adding a signed zero
+    // cannot change these sums (they start at +0.0 and RN addition yields -0.0 only from two -0.0 operands).  That needs
+    // every t[i] finite (0*inf = NaN); otherwise the branchy path is taken.
     const bool exact_zero_ok = __syncthreads_or(bad) == 0;
     for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = (exact_zero_ok && (i >> 4) == 255) ? 0.0 : G[i >> 4];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const double* gl = sG + (lane & 15);
-    const size_t n_tasks = (npix + 127) / 128;
+    const size_t n_tasks = (npix + 31) / 32;
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
     for (size_t task = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += warps_total) {
-        const size_t k0 = task * 128 + static_cast<size_t>(lane) * 4;
-        if (k0 >= npix) continue;
-        const int npx = static_cast<int>(npix - k0 < 4 ? npix - k0 : 4);      // ragged tail of the image
-        const bool vec = vec_ok && npx == 4;
-        const uint8_t* col = data + k0;
-        auto load = [&](int i) -> uint32_t {
-            if (i >= n) return 0u;
-            const uint8_t* a = col + static_cast<size_t>(i) * npix;
-            if (vec) return __ldg(reinterpret_cast<const uint32_t*>(a));
-            uint32_t v = __ldg(a);
-            if (npx > 1) v |= static_cast<uint32_t>(__ldg(a + 1)) << 8;
-            if (npx > 2) v |= static_cast<uint32_t>(__ldg(a + 2)) << 16;
-            if (npx > 3) v |= static_cast<uint32_t>(__ldg(a + 3)) << 24;
-            return v;
-        };
-        double esum[4] = {0.0, 0.0, 0.0, 0.0}, enumr[4] = {0.0, 0.0, 0.0, 0.0};
-        uint32_t cur[kEstepGroup], nxt[kEstepGroup];
+        const size_t k = task * 32 + lane;
+        if (k >= npix) continue;
+        const uint8_t* col = data + k;
+        double esum = 0.0, enumr = 0.0;
+        unsigned cur[kEstepGroup], nxt[kEstepGroup];
 #pragma unroll
-        for (int j = 0; j < kEstepGroup; ++j) cur[j] = load(j);
+        for (int j = 0; j < kEstepGroup; ++j) cur[j] = j < n ? __ldg(col + static_cast<size_t>(j) * npix) : 0u;
         for (int i0 = 0; i0 < n; i0 += kEstepGroup) {
 #pragma unroll
-            for (int j = 0; j < kEstepGroup; ++j) nxt[j] = load(i0 + kEstepGroup + j);     // next group in flight
+            for (int j = 0; j < kEstepGroup; ++j) {                   // next group in flight
+                const int i = i0 + kEstepGroup + j;
+                nxt[j] = i < n ? __ldg(col + static_cast<size_t>(i) * npix) : 0u;
+            }
 #pragma unroll
             for (int j = 0; j < kEstepGroup; ++j) {
                 const int i = i0 + j;
                 if (i < n) {
-                    const double ti = i < kEstepMaxN ? sT[i] : __ldg(t + i);
-                    const double tt = i < kEstepMaxN ? sTT[i] : __dmul_rn(ti, ti);
-                    estep_accumulate(cur[j], ti, tt, gl, exact_zero_ok, esum, enumr);
+                    double2 tp;
+                    if (i < kEstepMaxN) tp = sT[i];
+                    else { tp.x = __ldg(t + i); tp.y = __dmul_rn(tp.x, tp.x); }
+                    const unsigned b = cur[j];
+                    const double prod = __dmul_rn(gl[b << 4], tp.x);
+                    if (exact_zero_ok) {
+                        enumr = __dadd_rn(enumr, b != 255u ? tp.y : 0.0);
+                        esum = __dadd_rn(esum, prod);
+                    } else if (b != 255u) {
+                        enumr = __dadd_rn(enumr, tp.y);
+                        esum = __dadd_rn(esum, prod);
+                    }
                 }
             }
 #pragma unroll
             for (int j = 0; j < kEstepGroup; ++j) cur[j] = nxt[j];
         }
-        for (int j = 0; j < npx; ++j) {
-            double e = __ddiv_rn(esum[j], enumr[j]);
-            if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
-            E[k0 + j] = e;
-        }
+        double e = __ddiv_rn(esum, enumr);
+        if (e < 0) e = 0;              // 0/0 = NaN survives the clamp, as in the reference
+        E[k] = e;
     }
 }
 
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E, cudaStream_t stream) {
     if (npix <= 0) return cudaSuccess;
-    const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
-    const size_t smem = (256 * 16 + 2 * kEstepMaxN) * sizeof(double);      // 64 KB
+    const size_t smem = (256 * 16 + 2 * kEstepMaxN) * sizeof(double);      // 48 KB
     cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148, per_sm = 0;
@@ -769,19 +750,17 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_kernel, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    // resident warps per SM (multiples of 8 = one CTA) minimising the quantisation loss ceil(tasks/warps)*warps/tasks
-    const long long tasks = (static_cast<long long>(npix) + 127) / 128;
-    int best_ctas = per_sm;
-    double best_waste = 1e30;
-    for (int c = per_sm; c >= 1; --c) {
+    // resident CTAs per SM: full occupancy unless one CTA less rounds tasks/warps noticeably better
+    const long long tasks = (static_cast<long long>(npix) + 31) / 32;
+    auto waste = [&](int c) {
         const long long warps = static_cast<long long>(sms) * c * 8;
-        const long long rounds = (tasks + warps - 1) / warps;
-        const double waste = static_cast<double>(rounds * warps) / static_cast<double>(tasks) + 0.01 * (per_sm - c);   // mild preference for occupancy
-        if (waste < best_waste) { best_waste = waste; best_ctas = c; }
-    }
-    long long grid = static_cast<long long>(sms) * best_ctas;
+        return static_cast<double>(((tasks + warps - 1) / warps) * warps) / static_cast<double>(tasks);
+    };
+    int ctas = per_sm;
+    if (per_sm > 2 && waste(per_sm - 1) < waste(per_sm) - 0.05) ctas = per_sm - 1;
+    long long grid = static_cast<long long>(sms) * ctas;
     if (grid * 8 > tasks) grid = (tasks + 7) / 8;
-    estep_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E, vec_ok);
+    estep_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E);
     return cudaGetLastError();
 }
 
