@@ -662,20 +662,89 @@ cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_
 }
 
 // =====================================================================================
-// K3: responseCalib E-step.  One lane per pixel, sequential over the n exposures in the reference's order, fp64
-// with explicit non-fused multiplies/adds  ->  bit-identical to main_responseCalib.cpp:324-338.
+// K3: responseCalib E-step.  One lane per 4 adjacent pixels (one 32-bit load per exposure), sequential over the n
+// exposures in the reference's order, fp64 with explicit non-fused multiplies/adds  ->  bit-identical to
+// main_responseCalib.cpp:324-338.
 //
-// Layout of the work: a warp-task is 32 contiguous pixels (one 32-byte sector per exposure); persistent warps take
-// tasks round-robin.  The work per task is uniform, so the only imbalance is quantisation — ceil(tasks/warps) —
-// which small tasks keep at a few per cent (a 4-pixel-per-lane version lost 30-50 % to it).  Loads are
-// software-pipelined: while the 8 exposures of one group are accumulated, the 8 bytes of the next group are in flight.
+// Layout of the work: a warp-task is 128 contiguous pixels; persistent warps (full occupancy) take tasks round-robin.
+// Loads are software-pipelined with two register buffers of 8 exposures: while one group is accumulated, the next
+// is in flight, so the kernel is issue-bound rather than latency-bound.  {t[i], t[i]^2} pairs sit in shared memory.
 // =====================================================================================
 constexpr int kEstepGroup = 8;       // exposures per software-pipeline stage
-constexpr int kEstepMaxN = 1024;     // (t, t*t) pairs cached in shared memory up to this n; beyond, read through L1
+constexpr int kEstepMaxN = 1024;     // {t, t*t} pairs cached in shared memory up to this n; beyond, read through L1
 
-__global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
+template <bool kExactZero, bool kVec>
+__device__ __forceinline__ void estep_word(uint32_t v, double ti, double tt, const double* gl, double esum[4], double enumr[4], int npx) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!kVec && j >= npx) break;
+        const unsigned b = (v >> (8 * j)) & 0xffu;
+        const double prod = __dmul_rn(gl[b << 4], ti);
+        if (kExactZero) {
+            // saturated samples contribute exact zeros (table entry 255 == +0.0, t*t selected to +0.0): adding a signed
+            // zero cannot change these sums (they start at +0.0 and RN addition yields -0.0 only from two -0.0 operands)
+            enumr[j] = __dadd_rn(enumr[j], b != 255u ? tt : 0.0);
+            esum[j] = __dadd_rn(esum[j], prod);
+        } else if (b != 255u) {          // main_responseCalib.cpp:329
+            enumr[j] = __dadd_rn(enumr[j], tt);
+            esum[j] = __dadd_rn(esum[j], prod);
+        }
+    }
+}
+
+template <bool kExactZero, bool kVec>
+__device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int n, size_t npix, int npx, const double* __restrict__ t,
+                                           const double2* sT, const double* gl, double* __restrict__ Eout) {
+    double esum[4] = {0.0, 0.0, 0.0, 0.0}, enumr[4] = {0.0, 0.0, 0.0, 0.0};
+    auto load = [&](int i) -> uint32_t {
+        const uint8_t* a = col + static_cast<size_t>(i) * npix;
+        if (kVec) return __ldg(reinterpret_cast<const uint32_t*>(a));
+        uint32_t v = __ldg(a);
+        if (npx > 1) v |= static_cast<uint32_t>(__ldg(a + 1)) << 8;
+        if (npx > 2) v |= static_cast<uint32_t>(__ldg(a + 2)) << 16;
+        return v;
+    };
+    auto tpair = [&](int i) -> double2 {
+        if (i < kEstepMaxN) return sT[i];
+        const double ti = __ldg(t + i);
+        return make_double2(ti, __dmul_rn(ti, ti));
+    };
+    auto acc8 = [&](const uint32_t (&buf)[kEstepGroup], int base) {
+#pragma unroll
+        for (int j = 0; j < kEstepGroup; ++j) {
+            const double2 tp = tpair(base + j);
+            estep_word<kExactZero, kVec>(buf[j], tp.x, tp.y, gl, esum, enumr, npx);
+        }
+    };
+    auto load8 = [&](uint32_t (&buf)[kEstepGroup], int base) {
+#pragma unroll
+        for (int j = 0; j < kEstepGroup; ++j) buf[j] = load(base + j);
+    };
+    uint32_t a[kEstepGroup], b[kEstepGroup];
+    int i0 = 0;
+    if (n >= kEstepGroup) load8(a, 0);
+    // invariant at the loop head: `a` holds exposures [i0, i0+8)
+    for (; i0 + 2 * kEstepGroup <= n; i0 += 2 * kEstepGroup) {
+        load8(b, i0 + kEstepGroup);
+        acc8(a, i0);
+        if (i0 + 3 * kEstepGroup <= n) load8(a, i0 + 2 * kEstepGroup);
+        acc8(b, i0 + kEstepGroup);
+    }
+    if (i0 + kEstepGroup <= n) { acc8(a, i0); i0 += kEstepGroup; }
+    for (; i0 < n; ++i0) {
+        const double2 tp = tpair(i0);
+        estep_word<kExactZero, kVec>(load(i0), tp.x, tp.y, gl, esum, enumr, npx);
+    }
+    for (int j = 0; j < npx; ++j) {
+        double e = __ddiv_rn(esum[j], enumr[j]);
+        if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
+        Eout[j] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256, 3) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
                                                     const double* __restrict__ t, const double* __restrict__ G,
-                                                    double* __restrict__ E) {
+                                                    double* __restrict__ E, int vec_ok) {
     extern __shared__ __align__(16) double smem_d[];
     // G[256] replicated 16x (slot = lane & 15): a 64-bit shared load is served per half-warp, so with one slot per lane
     // of the half-warp the data-dependent lookup is bank-conflict-free.
@@ -687,60 +756,31 @@ __global__ void __launch_bounds__(256) estep_kernel(const uint8_t* __restrict__ 
         bad |= !isfinite(ti);
         if (i < kEstepMaxN) sT[i] = make_double2(ti, __dmul_rn(ti, ti));
     }
-    // Saturated samples (b == 255) are skipped in the reference (:329).  Fast path: give them exact-zero contributions
-    // instead — table entry 255 := +0.0 (so G[255]*t = +-0) and t*t selected to +0.0 — because adding a signed zero
-    // cannot change these sums (they start at +0.0 and RN addition yields -0.0 only from two -0.0 operands).  That needs
-    // every t[i] finite (0*inf = NaN); otherwise the branchy path is taken.
+    // the exact-zero fast path needs every t[i] finite (0*inf = NaN would leak out of the zeroed table entry)
     const bool exact_zero_ok = __syncthreads_or(bad) == 0;
     for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = (exact_zero_ok && (i >> 4) == 255) ? 0.0 : G[i >> 4];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const double* gl = sG + (lane & 15);
-    const size_t n_tasks = (npix + 31) / 32;
+    const size_t n_tasks = (npix + 127) / 128;
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
     for (size_t task = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += warps_total) {
-        const size_t k = task * 32 + lane;
-        if (k >= npix) continue;
-        const uint8_t* col = data + k;
-        double esum = 0.0, enumr = 0.0;
-        unsigned cur[kEstepGroup], nxt[kEstepGroup];
-#pragma unroll
-        for (int j = 0; j < kEstepGroup; ++j) cur[j] = j < n ? __ldg(col + static_cast<size_t>(j) * npix) : 0u;
-        for (int i0 = 0; i0 < n; i0 += kEstepGroup) {
-#pragma unroll
-            for (int j = 0; j < kEstepGroup; ++j) {                   // next group in flight
-                const int i = i0 + kEstepGroup + j;
-                nxt[j] = i < n ? __ldg(col + static_cast<size_t>(i) * npix) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < kEstepGroup; ++j) {
-                const int i = i0 + j;
-                if (i < n) {
-                    double2 tp;
-                    if (i < kEstepMaxN) tp = sT[i];
-                    else { tp.x = __ldg(t + i); tp.y = __dmul_rn(tp.x, tp.x); }
-                    const unsigned b = cur[j];
-                    const double prod = __dmul_rn(gl[b << 4], tp.x);
-                    if (exact_zero_ok) {
-                        enumr = __dadd_rn(enumr, b != 255u ? tp.y : 0.0);
-                        esum = __dadd_rn(esum, prod);
-                    } else if (b != 255u) {
-                        enumr = __dadd_rn(enumr, tp.y);
-                        esum = __dadd_rn(esum, prod);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kEstepGroup; ++j) cur[j] = nxt[j];
+        const size_t k0 = task * 128 + static_cast<size_t>(lane) * 4;
+        if (k0 >= npix) continue;
+        const int npx = static_cast<int>(npix - k0 < 4 ? npix - k0 : 4);      // ragged tail of the image
+        const uint8_t* col = data + k0;
+        if (vec_ok && npx == 4) {
+            if (exact_zero_ok) estep_task<true, true>(col, n, npix, 4, t, sT, gl, E + k0);
+            else estep_task<false, true>(col, n, npix, 4, t, sT, gl, E + k0);
+        } else {
+            estep_task<false, false>(col, n, npix, npx, t, sT, gl, E + k0);
         }
-        double e = __ddiv_rn(esum, enumr);
-        if (e < 0) e = 0;              // 0/0 = NaN survives the clamp, as in the reference
-        E[k] = e;
     }
 }
 
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E, cudaStream_t stream) {
     if (npix <= 0) return cudaSuccess;
+    const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
     const size_t smem = (256 * 16 + 2 * kEstepMaxN) * sizeof(double);      // 48 KB
     cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -750,17 +790,10 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_kernel, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    // resident CTAs per SM: full occupancy unless one CTA less rounds tasks/warps noticeably better
-    const long long tasks = (static_cast<long long>(npix) + 31) / 32;
-    auto waste = [&](int c) {
-        const long long warps = static_cast<long long>(sms) * c * 8;
-        return static_cast<double>(((tasks + warps - 1) / warps) * warps) / static_cast<double>(tasks);
-    };
-    int ctas = per_sm;
-    if (per_sm > 2 && waste(per_sm - 1) < waste(per_sm) - 0.05) ctas = per_sm - 1;
-    long long grid = static_cast<long long>(sms) * ctas;
+    const long long tasks = (static_cast<long long>(npix) + 127) / 128;
+    long long grid = static_cast<long long>(sms) * per_sm;
     if (grid * 8 > tasks) grid = (tasks + 7) / 8;
-    estep_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E);
+    estep_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E, vec_ok);
     return cudaGetLastError();
 }
 
