@@ -702,6 +702,7 @@ __device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int 
         uint32_t v = __ldg(a);
         if (npx > 1) v |= static_cast<uint32_t>(__ldg(a + 1)) << 8;
         if (npx > 2) v |= static_cast<uint32_t>(__ldg(a + 2)) << 16;
+        if (npx > 3) v |= static_cast<uint32_t>(__ldg(a + 3)) << 24;
         return v;
     };
     auto tpair = [&](int i) -> double2 {
