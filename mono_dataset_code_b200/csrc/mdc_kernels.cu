@@ -332,12 +332,10 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         // pyramid levels 1-2: per-item output pointers and store predicates (advanced by one image per frame)
         float *o1 = nullptr, *o2 = nullptr;
         uint32_t o1_step = 0, o2_step = 0;   // elements per image of level 1 / 2 (< 2^31)
-        bool st1a = false, st1b = false, st2 = false;
+        bool st1 = false, st2 = false;
         if (kPyr) {
-            const int X1 = (tx0 >> 1) + (lane >> 1), Y1 = (ty0 >> 1) + 2 * warp;
-            const bool own1 = (lane & 1) == 0 && X1 < p.lw[1];
-            st1a = own1 && Y1 < p.lh[1];
-            st1b = own1 && Y1 + 1 < p.lh[1];
+            const int X1 = (tx0 >> 1) + (lane >> 1), Y1 = (ty0 >> 1) + 2 * warp + (lane & 1);   // even lane: upper block, odd lane: lower block
+            st1 = X1 < p.lw[1] && Y1 < p.lh[1];
             o1_step = static_cast<uint32_t>(p.lw[1]) * static_cast<uint32_t>(p.lh[1]);
             o1 = p.out[1] + static_cast<size_t>(f_begin) * o1_step + static_cast<size_t>(Y1) * p.lw[1] + X1;
             if (p.levels > 2) {
@@ -422,21 +420,25 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             }
             o0 += o0_step;
 
-            // ---- pyramid epilogue: dst = 0.25f*(((a+b)+c)+d), a=(2x,2y) b=(2x+1,2y) c=(2x,2y+1) d=(2x+1,2y+1)
+            // ---- pyramid epilogue: dst = 0.25f*(((a+b)+c)+d), a=(2x,2y) b=(2x+1,2y) c=(2x,2y+1) d=(2x+1,2y+1).
+            // A lane pair (x even / x odd) owns two 2x2 blocks (rows 0-1 and rows 2-3); the even lane finishes the upper
+            // one, the odd lane the lower one, so each lane sends exactly the two values its partner lacks: 2 shuffles
+            // and ONE store instruction for level 1 (instead of 4 and 2).
             if (kPyr) {
-                float l1[2];
-#pragma unroll
-                for (int rp = 0; rp < 2; ++rp) {
-                    const float a = px[2 * rp], c = px[2 * rp + 1];
-                    const float bb = __shfl_xor_sync(0xffffffffu, a, 1), d = __shfl_xor_sync(0xffffffffu, c, 1);
-                    l1[rp] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(a, bb), c), d));   // meaningful on even lanes
-                }
-                if (st1a) stg_cs(o1, l1[0]);
-                if (st1b) stg_cs(o1 + p.lw[1], l1[1]);
+                const bool odd = (lane & 1) != 0;
+                const float r1 = __shfl_xor_sync(0xffffffffu, odd ? px[0] : px[2], 1);
+                const float r2 = __shfl_xor_sync(0xffffffffu, odd ? px[1] : px[3], 1);
+                const float pa = odd ? r1 : px[0], pb = odd ? px[2] : r1, pc = odd ? r2 : px[1], pd = odd ? px[3] : r2;
+                const float l1 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(pa, pb), pc), pd));
+                if (st1) stg_cs(o1, l1);
                 o1 += o1_step;
                 if (p.levels > 2) {
-                    const float bb = __shfl_down_sync(0xffffffffu, l1[0], 2), d = __shfl_down_sync(0xffffffffu, l1[1], 2);
-                    const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1[0], bb), l1[1]), d));   // lanes = 0 mod 4
+                    // level-2 pixel of lanes 4m..4m+3: a = lane 4m (upper, X even), c = lane 4m+1 (lower, X even),
+                    // b = lane 4m+2 (upper, X odd), d = lane 4m+3 (lower, X odd)
+                    const float c2 = __shfl_down_sync(0xffffffffu, l1, 1);
+                    const float b2 = __shfl_down_sync(0xffffffffu, l1, 2);
+                    const float d2 = __shfl_down_sync(0xffffffffu, l1, 3);
+                    const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1, b2), c2), d2));   // lanes = 0 mod 4
                     if (st2) stg_cs(o2, l2);
                     o2 += o2_step;
                 }
