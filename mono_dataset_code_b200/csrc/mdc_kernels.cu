@@ -668,38 +668,57 @@ cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_
 // exposures in the reference's order, fp64 with explicit non-fused multiplies/adds  ->  bit-identical to
 // main_responseCalib.cpp:324-338.
 //
-// Layout of the work: a warp-task is 128 contiguous pixels; persistent warps (full occupancy) take tasks round-robin.
-// Loads are software-pipelined with two register buffers of 8 exposures: while one group is accumulated, the next
-// is in flight, so the kernel is issue-bound rather than latency-bound.  {t[i], t[i]^2} pairs sit in shared memory.
+// Layout of the work: a warp-task is 128 contiguous pixels; persistent warps take tasks round-robin.  Loads are
+// software-pipelined with two register buffers of 8 exposures: while one group is accumulated, the next is in flight.
+// Per sample the inner loop is six instructions:
+//   PRMT   a = (byte << 8) | lane*8         one byte-permute builds the whole table address (the table row of a value is
+//                                           256 bytes = 32 lane slots of one double, so every lookup is conflict-free)
+//   LDS.64 g = G[byte]   ·  DMUL prod = g*t  ·  ISETP p = a < 0xff00 (byte != 255, main_responseCalib.cpp:329)
+//   @p DADD ENum += t*t  ·  @p DADD ESum += prod        (predicated, so saturated samples are skipped like the reference's `continue`)
+// The exposure times sit in shared memory next to the table (one broadcast 64-bit load + one DMUL for t*t per exposure).
 // =====================================================================================
-constexpr int kEstepGroup = 8;       // exposures per software-pipeline stage
-constexpr int kEstepMaxN = 1024;     // {t, t*t} pairs cached in shared memory up to this n; beyond, read through L1
+constexpr int kEstepGroup = 8;        // exposures per software-pipeline stage
+constexpr int kEstepMaxN = 4096;      // exposure times cached in shared memory up to this n; beyond, read through L1
+constexpr int kEstepThreads = 384;    // 12 warps; two CTAs per SM share 2 x 96 KB of shared memory
+constexpr int kEstepTableBytes = 256 * 256;
 
-template <bool kExactZero, bool kVec>
-__device__ __forceinline__ void estep_word(uint32_t v, double ti, double tt, const double* gl, double esum[4], double enumr[4], int npx) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (!kVec && j >= npx) break;
-        const unsigned b = (v >> (8 * j)) & 0xffu;
-        const double prod = __dmul_rn(gl[b << 4], ti);
-        if (kExactZero) {
-            // saturated samples contribute exact zeros (table entry 255 == +0.0, t*t selected to +0.0): adding a signed
-            // zero cannot change these sums (they start at +0.0 and RN addition yields -0.0 only from two -0.0 operands)
-            enumr[j] = __dadd_rn(enumr[j], b != 255u ? tt : 0.0);
-            esum[j] = __dadd_rn(esum[j], prod);
-        } else if (b != 255u) {          // main_responseCalib.cpp:329
-            enumr[j] = __dadd_rn(enumr[j], tt);
-            esum[j] = __dadd_rn(esum[j], prod);
-        }
-    }
+// one sample: `a` = table byte offset built by PRMT; both sums only move when the sample is not saturated
+__device__ __forceinline__ void estep_sample(uint32_t table, uint32_t a, double ti, double tt, double& esum, double& enumr) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f64 g, pr;\n\t"
+        ".reg .u32 ad;\n\t"
+        "add.u32 ad, %2, %3;\n\t"
+        "ld.shared.f64 g, [ad];\n\t"
+        "mul.rn.f64 pr, g, %4;\n\t"
+        "setp.lt.u32 p, %3, 0xff00;\n\t"
+        "@!p bra SKIP;\n\t"
+        "add.rn.f64 %1, %1, %5;\n\t"
+        "add.rn.f64 %0, %0, pr;\n\t"
+        "SKIP:\n\t"
+        "}"
+        : "+d"(esum), "+d"(enumr)
+        : "r"(table), "r"(a), "d"(ti), "d"(tt));
 }
 
-template <bool kExactZero, bool kVec>
-__device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int n, size_t npix, int npx, const double* __restrict__ t,
-                                           const double2* sT, const double* gl, double* __restrict__ Eout) {
+template <bool kVec>
+__device__ __forceinline__ void estep_word(uint32_t v, double ti, double tt, uint32_t table, uint32_t lane8, double esum[4],
+                                           double enumr[4], int npx) {
+    // PRMT selectors: result byte 0 = lane8 (lane*8 < 256), byte 1 = byte j of v, bytes 2..3 = 0 (upper bytes of lane8)
+    estep_sample(table, __byte_perm(v, lane8, 0x5504), ti, tt, esum[0], enumr[0]);
+    if (kVec || npx > 1) estep_sample(table, __byte_perm(v, lane8, 0x5514), ti, tt, esum[1], enumr[1]);
+    if (kVec || npx > 2) estep_sample(table, __byte_perm(v, lane8, 0x5524), ti, tt, esum[2], enumr[2]);
+    if (kVec || npx > 3) estep_sample(table, __byte_perm(v, lane8, 0x5534), ti, tt, esum[3], enumr[3]);
+}
+
+template <bool kVec, bool kTimesInSmem>
+__device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int n, uint32_t npix, int npx, const double* __restrict__ t,
+                                           const double* sT, uint32_t table, uint32_t lane8, double* __restrict__ Eout) {
     double esum[4] = {0.0, 0.0, 0.0, 0.0}, enumr[4] = {0.0, 0.0, 0.0, 0.0};
-    auto load = [&](int i) -> uint32_t {
-        const uint8_t* a = col + static_cast<size_t>(i) * npix;
+    const uint8_t* next = col;          // the loads walk down the column of this lane's 4 pixels, one exposure per step
+    auto load = [&]() -> uint32_t {
+        const uint8_t* a = next;
+        next += npix;
         if (kVec) return __ldg(reinterpret_cast<const uint32_t*>(a));
         uint32_t v = __ldg(a);
         if (npx > 1) v |= static_cast<uint32_t>(__ldg(a + 1)) << 8;
@@ -707,37 +726,30 @@ __device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int 
         if (npx > 3) v |= static_cast<uint32_t>(__ldg(a + 3)) << 24;
         return v;
     };
-    auto tpair = [&](int i) -> double2 {
-        if (i < kEstepMaxN) return sT[i];
-        const double ti = __ldg(t + i);
-        return make_double2(ti, __dmul_rn(ti, ti));
+    auto acc = [&](uint32_t v, int i) {
+        const double ti = kTimesInSmem ? sT[i] : __ldg(t + i);
+        estep_word<kVec>(v, ti, __dmul_rn(ti, ti), table, lane8, esum, enumr, npx);
     };
     auto acc8 = [&](const uint32_t (&buf)[kEstepGroup], int base) {
 #pragma unroll
-        for (int j = 0; j < kEstepGroup; ++j) {
-            const double2 tp = tpair(base + j);
-            estep_word<kExactZero, kVec>(buf[j], tp.x, tp.y, gl, esum, enumr, npx);
-        }
+        for (int j = 0; j < kEstepGroup; ++j) acc(buf[j], base + j);
     };
-    auto load8 = [&](uint32_t (&buf)[kEstepGroup], int base) {
+    auto load8 = [&](uint32_t (&buf)[kEstepGroup]) {
 #pragma unroll
-        for (int j = 0; j < kEstepGroup; ++j) buf[j] = load(base + j);
+        for (int j = 0; j < kEstepGroup; ++j) buf[j] = load();
     };
     uint32_t a[kEstepGroup], b[kEstepGroup];
     int i0 = 0;
-    if (n >= kEstepGroup) load8(a, 0);
-    // invariant at the loop head: `a` holds exposures [i0, i0+8)
+    if (n >= kEstepGroup) load8(a);
+    // invariant at the loop head: `a` holds exposures [i0, i0+8), `next` points at exposure i0+8
     for (; i0 + 2 * kEstepGroup <= n; i0 += 2 * kEstepGroup) {
-        load8(b, i0 + kEstepGroup);
+        load8(b);
         acc8(a, i0);
-        if (i0 + 3 * kEstepGroup <= n) load8(a, i0 + 2 * kEstepGroup);
+        if (i0 + 3 * kEstepGroup <= n) load8(a);
         acc8(b, i0 + kEstepGroup);
     }
     if (i0 + kEstepGroup <= n) { acc8(a, i0); i0 += kEstepGroup; }
-    for (; i0 < n; ++i0) {
-        const double2 tp = tpair(i0);
-        estep_word<kExactZero, kVec>(load(i0), tp.x, tp.y, gl, esum, enumr, npx);
-    }
+    for (; i0 < n; ++i0) acc(load(), i0);
     for (int j = 0; j < npx; ++j) {
         double e = __ddiv_rn(esum[j], enumr[j]);
         if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
@@ -745,26 +757,23 @@ __device__ __forceinline__ void estep_task(const uint8_t* __restrict__ col, int 
     }
 }
 
-__global__ void __launch_bounds__(256, 3) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
-                                                    const double* __restrict__ t, const double* __restrict__ G,
-                                                    double* __restrict__ E, int vec_ok) {
+__global__ void __launch_bounds__(kEstepThreads, 2) estep_kernel(const uint8_t* __restrict__ data, int n, size_t npix,
+                                                                const double* __restrict__ t, const double* __restrict__ G,
+                                                                double* __restrict__ E, int vec_ok) {
     extern __shared__ __align__(16) double smem_d[];
-    // G[256] replicated 16x (slot = lane & 15): a 64-bit shared load is served per half-warp, so with one slot per lane
-    // of the half-warp the data-dependent lookup is bank-conflict-free.
-    double* sG = smem_d;                                              // [256*16]
-    double2* sT = reinterpret_cast<double2*>(smem_d + 256 * 16);      // [min(n, kEstepMaxN)] {t[i], t[i]*t[i]}
-    int bad = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double ti = t[i];
-        bad |= !isfinite(ti);
-        if (i < kEstepMaxN) sT[i] = make_double2(ti, __dmul_rn(ti, ti));
-    }
-    // the exact-zero fast path needs every t[i] finite (0*inf = NaN would leak out of the zeroed table entry)
-    const bool exact_zero_ok = __syncthreads_or(bad) == 0;
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) sG[i] = (exact_zero_ok && (i >> 4) == 255) ? 0.0 : G[i >> 4];
+    // G[256], one 256-byte row per value holding 32 copies (slot = lane): a 64-bit shared load is served per half-warp
+    // and every lane reads its own slot, so the data-dependent lookup is bank-conflict-free
+    double* sG = smem_d;                                                      // [256][32]
+    double* sT = smem_d + kEstepTableBytes / 8;                               // [min(n, kEstepMaxN)] exposure times
+    const bool times_in_smem = n <= kEstepMaxN;
+    if (times_in_smem)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sT[i] = t[i];
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) sG[i] = G[i >> 5];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const double* gl = sG + (lane & 15);
+    const uint32_t table = static_cast<uint32_t>(__cvta_generic_to_shared(sG));
+    const uint32_t lane8 = static_cast<uint32_t>(lane) * 8u;
+    const uint32_t npix32 = static_cast<uint32_t>(npix);                     // launch_estep takes an int
     const size_t n_tasks = (npix + 127) / 128;
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
     for (size_t task = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += warps_total) {
@@ -773,30 +782,154 @@ __global__ void __launch_bounds__(256, 3) estep_kernel(const uint8_t* __restrict
         const int npx = static_cast<int>(npix - k0 < 4 ? npix - k0 : 4);      // ragged tail of the image
         const uint8_t* col = data + k0;
         if (vec_ok && npx == 4) {
-            if (exact_zero_ok) estep_task<true, true>(col, n, npix, 4, t, sT, gl, E + k0);
-            else estep_task<false, true>(col, n, npix, 4, t, sT, gl, E + k0);
+            if (times_in_smem) estep_task<true, true>(col, n, npix32, 4, t, sT, table, lane8, E + k0);
+            else estep_task<true, false>(col, n, npix32, 4, t, sT, table, lane8, E + k0);
         } else {
-            estep_task<false, false>(col, n, npix, npx, t, sT, gl, E + k0);
+            estep_task<false, false>(col, n, npix32, npx, t, sT, table, lane8, E + k0);
         }
     }
 }
 
+// ---- K3, bulk-copy loader (image sizes that are a multiple of 16 pixels): the same arithmetic, but the u8 planes come in
+// through the async proxy.  A CTA owns a tile of 12 x 128 pixels; a producer warp streams it plane by plane with 1-D
+// cp.async.bulk copies (1536 contiguous bytes each, 8 planes per stage) into a shared-memory ring, full/empty mbarriers
+// connect it to the 12 consumer warps (warp = 128 pixels, lane = 4 pixels, one LDS.32 per exposure).  The ring keeps
+// 24 planes x 1.5 KB per CTA in flight without holding a register, runs ahead across tile boundaries, and DRAM sees
+// 1.5 KB bursts instead of independent 128-byte requests.
+constexpr int kEbWarps = 12;
+constexpr int kEbThreads = (kEbWarps + 1) * 32;
+constexpr int kEbTile = kEbWarps * 128;          // pixels (= bytes) of one plane per stage row
+constexpr int kEbPlanes = 8;                     // exposures per stage
+constexpr int kEbStages = 3;
+constexpr int kEbMaxN = 1024;                    // exposure times cached in shared memory up to this n
+constexpr int kEbStageBytes = kEbPlanes * kEbTile;
+constexpr int kEbSmemBytes = kEstepTableBytes + kEbMaxN * 8 + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool kTimesInSmem>
+__device__ __forceinline__ void estep_bulk_consume(int n, uint32_t npix, uint32_t n_tiles, const double* __restrict__ t, const double* sT,
+                                                   uint32_t table, uint32_t stages, uint32_t bar_full, uint32_t bar_empty,
+                                                   double* __restrict__ E) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane8 = lane * 8u;
+    const uint32_t mine = stages + warp * 128u + lane * 4u;
+    const int n_groups = (n + kEbPlanes - 1) / kEbPlanes;
+    uint32_t s = 0, ph = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        double esum[4] = {0.0, 0.0, 0.0, 0.0}, enumr[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int g = 0; g < n_groups; ++g) {
+            mbar_wait(bar_full + 8u * s, ph);
+            const uint32_t src = mine + s * static_cast<uint32_t>(kEbStageBytes);
+            const int i0 = g * kEbPlanes;
+            auto plane = [&](int p) {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + static_cast<uint32_t>(p) * kEbTile));
+                const double ti = kTimesInSmem ? sT[i0 + p] : __ldg(t + i0 + p);
+                estep_word<true>(v, ti, __dmul_rn(ti, ti), table, lane8, esum, enumr, 4);
+            };
+            if (i0 + kEbPlanes <= n) {
+#pragma unroll
+                for (int p = 0; p < kEbPlanes; ++p) plane(p);
+            } else {
+                for (int p = 0; i0 + p < n; ++p) plane(p);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8u * s);
+            if (++s == kEbStages) { s = 0; ph ^= 1u; }
+        }
+        const size_t k0 = static_cast<size_t>(tile) * kEbTile + warp * 128u + lane * 4u;
+        if (k0 < npix) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double e = __ddiv_rn(esum[j], enumr[j]);
+                if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
+                E[k0 + j] = e;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEbThreads, 2) estep_bulk_kernel(const uint8_t* __restrict__ data, int n, uint32_t npix,
+                                                                  const double* __restrict__ t, const double* __restrict__ G,
+                                                                  double* __restrict__ E) {
+    extern __shared__ __align__(128) uint8_t smem_b[];
+    double* sG = reinterpret_cast<double*>(smem_b);                                   // [256][32], as in estep_kernel
+    double* sT = reinterpret_cast<double*>(smem_b + kEstepTableBytes);                // [min(n, kEbMaxN)]
+    const uint32_t stages = smem_u32(smem_b + kEstepTableBytes + kEbMaxN * 8);        // [kEbStages][kEbPlanes][kEbTile]
+    const uint32_t bar_full = stages + kEbStages * kEbStageBytes, bar_empty = bar_full + 8u * kEbStages;
+    const bool times_in_smem = n <= kEbMaxN;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, kEbWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (times_in_smem)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sT[i] = t[i];
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) sG[i] = G[i >> 5];
+    __syncthreads();
+    const uint32_t n_tiles = (npix + kEbTile - 1) / kEbTile;
+    if ((threadIdx.x >> 5) == kEbWarps) {
+        if ((threadIdx.x & 31) != 0) return;
+        // producer: one lane streams this CTA's tiles, plane group by plane group, as far ahead as the ring allows
+        const int n_groups = (n + kEbPlanes - 1) / kEbPlanes;
+        uint32_t s = 0, ph = 0, it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t k0 = tile * kEbTile;
+            const uint32_t bytes = npix - k0 < static_cast<uint32_t>(kEbTile) ? npix - k0 : kEbTile;      // multiple of 16 (npix is)
+            const uint8_t* src = data + k0;
+            for (int g = 0; g < n_groups; ++g, ++it) {
+                if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
+                const int planes = n - g * kEbPlanes < kEbPlanes ? n - g * kEbPlanes : kEbPlanes;
+                mbar_expect_tx(bar_full + 8u * s, static_cast<uint32_t>(planes) * bytes);
+                const uint32_t dst = stages + s * static_cast<uint32_t>(kEbStageBytes);
+                for (int p = 0; p < planes; ++p) {
+                    bulk_load_1d(dst + static_cast<uint32_t>(p) * kEbTile, src, bytes, bar_full + 8u * s);
+                    src += npix;
+                }
+                if (++s == kEbStages) { s = 0; ph ^= 1u; }
+            }
+            src = nullptr;
+        }
+        return;
+    }
+    const uint32_t table = smem_u32(sG);
+    if (times_in_smem) estep_bulk_consume<true>(n, npix, n_tiles, t, sT, table, stages, bar_full, bar_empty, E);
+    else estep_bulk_consume<false>(n, npix, n_tiles, t, sT, table, stages, bar_full, bar_empty, E);
+}
+
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E, cudaStream_t stream) {
     if (npix <= 0) return cudaSuccess;
-    const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
-    const size_t smem = (256 * 16 + 2 * kEstepMaxN) * sizeof(double);      // 48 KB
-    cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
     int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_kernel, 256, smem);
+    static const bool allow_bulk = [] { const char* e = getenv("MDC_ESTEP_BULK"); return !(e && e[0] == '0'); }();      // A/B knob
+    if (allow_bulk && npix % 16 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
+        cudaError_t e = cudaFuncSetAttribute(estep_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_bulk_kernel, kEbThreads, kEbSmemBytes);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const long long tiles = (static_cast<long long>(npix) + kEbTile - 1) / kEbTile;
+        long long grid = static_cast<long long>(sms) * per_sm;
+        if (grid > tiles) grid = tiles;
+        estep_bulk_kernel<<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(data, n, static_cast<uint32_t>(npix), t, G, E);
+        return cudaGetLastError();
+    }
+    const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
+    const size_t smem = kEstepTableBytes + static_cast<size_t>(kEstepMaxN) * sizeof(double);      // 96 KB
+    cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_kernel, kEstepThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    const int warps = kEstepThreads / 32;
     const long long tasks = (static_cast<long long>(npix) + 127) / 128;
     long long grid = static_cast<long long>(sms) * per_sm;
-    if (grid * 8 > tasks) grid = (tasks + 7) / 8;
-    estep_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E, vec_ok);
+    if (grid * warps > tasks) grid = (tasks + warps - 1) / warps;
+    estep_kernel<<<static_cast<unsigned>(grid), kEstepThreads, smem, stream>>>(data, n, static_cast<size_t>(npix), t, G, E, vec_ok);
     return cudaGetLastError();
 }
 

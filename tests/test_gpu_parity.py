@@ -202,7 +202,9 @@ def test_full_size_configs(name, api, port, dataset_dir):
 
 def test_estep_bit_exact(api, port):
     rng = np.random.default_rng(11)
-    for n, npix in [(37, 4096), (20, 1001), (64, 12 * 1024)]:
+    # (4100, 640): more exposures than the kernel caches in shared memory -> times come through L1; (5, 130): shorter than one
+    # software-pipeline group; 1001 / 130: image sizes that are not a multiple of 4 (byte-wise tail path)
+    for n, npix in [(37, 4096), (20, 1001), (64, 12 * 1024), (4100, 640), (5, 130), (27, 1536 * 300 + 16)]:
         data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
         data[:, 5] = 255                       # never-valid pixel -> 0/0 = NaN survives the clamp
         data[:, 7] = 0
@@ -215,6 +217,13 @@ def test_estep_bit_exact(api, port):
         ctx.estep(torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda(), E)
         assert_bits_equal(E.cpu().numpy(), exp, f"E-step n={n} npix={npix}")
         assert np.isnan(exp[5])
+        # the same planes at a base address that is 4- but not 16-byte aligned: the bulk-copy loader does not apply,
+        # the register-pipelined loader must give the same bits
+        shifted = torch.empty(n * npix + 4, dtype=torch.uint8, device="cuda")[4:].view(n, npix)
+        shifted.copy_(torch.from_numpy(data))
+        E.zero_()
+        ctx.estep(shifted, torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda(), E)
+        assert_bits_equal(E.cpu().numpy(), exp, f"E-step (unaligned base) n={n} npix={npix}")
 
 
 def test_multi_gpu_style_adopted_tables(api, port, dataset_dir):
@@ -274,15 +283,17 @@ def test_many_frames_cross_chunk_boundaries(api, port, dataset_dir):
                 assert_bits_equal(lv[l][i], exp[l], f"tma={use_tma} frame={i} level={l}")
 
 
-def test_estep_non_finite_exposure_takes_the_select_path(api, port):
-    """t[i] = inf would turn the fast path's exact-zero trick (0*inf) into NaN; the kernel must detect it and
-    reproduce the reference's skip semantics instead."""
+def test_estep_non_finite_and_negative_exposures(api, port):
+    """Saturated samples are skipped, never multiplied: t[i] = inf, a negative t[i] and a NaN table entry must come out
+    exactly as the reference's `continue` leaves them (main_responseCalib.cpp:329)."""
     rng = np.random.default_rng(12)
     n, npix = 9, 2048
     data = rng.integers(250, 256, (n, npix), dtype=np.uint8)       # many saturated samples
     t = rng.uniform(0.5, 2.0, n)
     t[4] = np.inf
+    t[6] = -1.25
     G = np.linspace(0.0, 255.0, 256)
+    G[255] = np.nan                                                # only ever met by saturated samples
     exp = port.estep(data, t, G)
     ctx = api.Context(None, None, 0)
     E = torch.zeros(npix, dtype=torch.float64, device="cuda")
