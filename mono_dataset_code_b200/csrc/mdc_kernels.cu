@@ -796,6 +796,9 @@ __global__ void __launch_bounds__(kEstepThreads, 2) estep_kernel(const uint8_t* 
 // connect it to the 12 consumer warps (warp = 128 pixels, lane = 4 pixels, one LDS.32 per exposure).  The ring keeps
 // 24 planes x 1.5 KB per CTA in flight without holding a register, runs ahead across tile boundaries, and DRAM sees
 // 1.5 KB bursts instead of independent 128-byte requests.
+//
+// The streaming skeleton is shared by the three passes of the calibrator that walk the whole image stack (E-step,
+// G-step, rmse); what happens to a word of 4 samples is the `Op`.
 constexpr int kEbWarps = 12;
 constexpr int kEbThreads = (kEbWarps + 1) * 32;
 constexpr int kEbTile = kEbWarps * 128;          // pixels (= bytes) of one plane per stage row
@@ -803,24 +806,49 @@ constexpr int kEbPlanes = 8;                     // exposures per stage
 constexpr int kEbStages = 3;
 constexpr int kEbMaxN = 1024;                    // exposure times cached in shared memory up to this n
 constexpr int kEbStageBytes = kEbPlanes * kEbTile;
-constexpr int kEbSmemBytes = kEstepTableBytes + kEbMaxN * 8 + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
+constexpr int kEbRegionBytes = kEstepTableBytes; // op-specific region: lookup table (E-step, rmse) or histograms (G-step)
+constexpr int kEbSmemBytes = kEbRegionBytes + kEbMaxN * 8 + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
+
+struct StreamArgs { const uint8_t* data; int n; uint32_t npix; const double* t; };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void stream_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEbWarps * 32) : "memory"); }
 
-template <bool kTimesInSmem>
-__device__ __forceinline__ void estep_bulk_consume(int n, uint32_t npix, uint32_t n_tiles, const double* __restrict__ t, const double* sT,
-                                                   uint32_t table, uint32_t stages, uint32_t bar_full, uint32_t bar_empty,
-                                                   double* __restrict__ E) {
+// producer lane: streams this CTA's tiles, plane group by plane group, as far ahead as the ring allows
+__device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_tiles, uint32_t stages, uint32_t bar_full, uint32_t bar_empty) {
+    const int n_groups = (a.n + kEbPlanes - 1) / kEbPlanes;
+    uint32_t s = 0, ph = 0, it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t k0 = tile * kEbTile;
+        const uint32_t bytes = a.npix - k0 < static_cast<uint32_t>(kEbTile) ? a.npix - k0 : kEbTile;      // multiple of 16 (npix is)
+        const uint8_t* src = a.data + k0;
+        for (int g = 0; g < n_groups; ++g, ++it) {
+            if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
+            const int planes = a.n - g * kEbPlanes < kEbPlanes ? a.n - g * kEbPlanes : kEbPlanes;
+            mbar_expect_tx(bar_full + 8u * s, static_cast<uint32_t>(planes) * bytes);
+            const uint32_t dst = stages + s * static_cast<uint32_t>(kEbStageBytes);
+            for (int p = 0; p < planes; ++p) {
+                bulk_load_1d(dst + static_cast<uint32_t>(p) * kEbTile, src, bytes, bar_full + 8u * s);
+                src += a.npix;
+            }
+            if (++s == kEbStages) { s = 0; ph ^= 1u; }
+        }
+    }
+}
+
+template <class Op, bool kTimesInSmem>
+__device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_tiles, const double* sT, uint32_t stages, uint32_t bar_full,
+                                               uint32_t bar_empty, Op& op) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lane8 = lane * 8u;
     const uint32_t mine = stages + warp * 128u + lane * 4u;
-    const int n_groups = (n + kEbPlanes - 1) / kEbPlanes;
+    const int n_groups = (a.n + kEbPlanes - 1) / kEbPlanes;
     uint32_t s = 0, ph = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        double esum[4] = {0.0, 0.0, 0.0, 0.0}, enumr[4] = {0.0, 0.0, 0.0, 0.0};
+        const size_t k0 = static_cast<size_t>(tile) * kEbTile + warp * 128u + lane * 4u;
+        op.begin_tile(k0, k0 < a.npix);
         for (int g = 0; g < n_groups; ++g) {
             mbar_wait(bar_full + 8u * s, ph);
             const uint32_t src = mine + s * static_cast<uint32_t>(kEbStageBytes);
@@ -828,76 +856,210 @@ __device__ __forceinline__ void estep_bulk_consume(int n, uint32_t npix, uint32_
             auto plane = [&](int p) {
                 uint32_t v;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + static_cast<uint32_t>(p) * kEbTile));
-                const double ti = kTimesInSmem ? sT[i0 + p] : __ldg(t + i0 + p);
-                estep_word<true>(v, ti, __dmul_rn(ti, ti), table, lane8, esum, enumr, 4);
+                op.word(v, kTimesInSmem ? sT[i0 + p] : __ldg(a.t + i0 + p));
             };
-            if (i0 + kEbPlanes <= n) {
+            if (i0 + kEbPlanes <= a.n) {
+                if (Op::kUnroll) {
 #pragma unroll
-                for (int p = 0; p < kEbPlanes; ++p) plane(p);
+                    for (int p = 0; p < kEbPlanes; ++p) plane(p);
+                } else {
+#pragma unroll 1
+                    for (int p = 0; p < kEbPlanes; ++p) plane(p);
+                }
             } else {
-                for (int p = 0; i0 + p < n; ++p) plane(p);
+                for (int p = 0; i0 + p < a.n; ++p) plane(p);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
             if (++s == kEbStages) { s = 0; ph ^= 1u; }
         }
-        const size_t k0 = static_cast<size_t>(tile) * kEbTile + warp * 128u + lane * 4u;
-        if (k0 < npix) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double e = __ddiv_rn(esum[j], enumr[j]);
-                if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
-                E[k0 + j] = e;
-            }
-        }
+        op.end_tile(k0, k0 < a.npix);
     }
 }
 
-__global__ void __launch_bounds__(kEbThreads, 2) estep_bulk_kernel(const uint8_t* __restrict__ data, int n, uint32_t npix,
-                                                                  const double* __restrict__ t, const double* __restrict__ G,
-                                                                  double* __restrict__ E) {
+template <class Op>
+__global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, typename Op::Params prm) {
     extern __shared__ __align__(128) uint8_t smem_b[];
-    double* sG = reinterpret_cast<double*>(smem_b);                                   // [256][32], as in estep_kernel
-    double* sT = reinterpret_cast<double*>(smem_b + kEstepTableBytes);                // [min(n, kEbMaxN)]
-    const uint32_t stages = smem_u32(smem_b + kEstepTableBytes + kEbMaxN * 8);        // [kEbStages][kEbPlanes][kEbTile]
+    double* sT = reinterpret_cast<double*>(smem_b + kEbRegionBytes);                  // [min(n, kEbMaxN)]
+    const uint32_t stages = smem_u32(smem_b + kEbRegionBytes + kEbMaxN * 8);          // [kEbStages][kEbPlanes][kEbTile]
     const uint32_t bar_full = stages + kEbStages * kEbStageBytes, bar_empty = bar_full + 8u * kEbStages;
-    const bool times_in_smem = n <= kEbMaxN;
+    const bool times_in_smem = a.n <= kEbMaxN;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, kEbWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (times_in_smem)
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sT[i] = t[i];
-    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) sG[i] = G[i >> 5];
+        for (int i = threadIdx.x; i < a.n; i += blockDim.x) sT[i] = a.t[i];
+    Op::prologue(smem_b, prm);
     __syncthreads();
-    const uint32_t n_tiles = (npix + kEbTile - 1) / kEbTile;
+    const uint32_t n_tiles = (a.npix + kEbTile - 1) / kEbTile;
     if ((threadIdx.x >> 5) == kEbWarps) {
-        if ((threadIdx.x & 31) != 0) return;
-        // producer: one lane streams this CTA's tiles, plane group by plane group, as far ahead as the ring allows
-        const int n_groups = (n + kEbPlanes - 1) / kEbPlanes;
-        uint32_t s = 0, ph = 0, it = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint32_t k0 = tile * kEbTile;
-            const uint32_t bytes = npix - k0 < static_cast<uint32_t>(kEbTile) ? npix - k0 : kEbTile;      // multiple of 16 (npix is)
-            const uint8_t* src = data + k0;
-            for (int g = 0; g < n_groups; ++g, ++it) {
-                if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
-                const int planes = n - g * kEbPlanes < kEbPlanes ? n - g * kEbPlanes : kEbPlanes;
-                mbar_expect_tx(bar_full + 8u * s, static_cast<uint32_t>(planes) * bytes);
-                const uint32_t dst = stages + s * static_cast<uint32_t>(kEbStageBytes);
-                for (int p = 0; p < planes; ++p) {
-                    bulk_load_1d(dst + static_cast<uint32_t>(p) * kEbTile, src, bytes, bar_full + 8u * s);
-                    src += npix;
-                }
-                if (++s == kEbStages) { s = 0; ph ^= 1u; }
-            }
-            src = nullptr;
-        }
+        if ((threadIdx.x & 31) == 0) stream_produce(a, n_tiles, stages, bar_full, bar_empty);
         return;
     }
-    const uint32_t table = smem_u32(sG);
-    if (times_in_smem) estep_bulk_consume<true>(n, npix, n_tiles, t, sT, table, stages, bar_full, bar_empty, E);
-    else estep_bulk_consume<false>(n, npix, n_tiles, t, sT, table, stages, bar_full, bar_empty, E);
+    Op op(smem_b, prm);
+    if (times_in_smem) stream_consume<Op, true>(a, n_tiles, sT, stages, bar_full, bar_empty, op);
+    else stream_consume<Op, false>(a, n_tiles, sT, stages, bar_full, bar_empty, op);
+    op.epilogue(smem_b, prm);
+}
+
+// G[256] -> one 256-byte row per value holding 32 copies (see estep_kernel)
+__device__ __forceinline__ void fill_lane_table(uint8_t* region, const double* __restrict__ G) {
+    double* sG = reinterpret_cast<double*>(region);
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) sG[i] = G[i >> 5];
+}
+
+// E-step (main_responseCalib.cpp:324-338)
+struct EstepOp {
+    struct Params { const double* G; double* E; };
+    static constexpr bool kUnroll = true;
+    static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
+    uint32_t table, lane8;
+    double* E;
+    double esum[4], enumr[4];
+    __device__ __forceinline__ EstepOp(uint8_t* region, const Params& p) : table(smem_u32(region)), lane8((threadIdx.x & 31) * 8u), E(p.E) {}
+    __device__ __forceinline__ void begin_tile(size_t, bool) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { esum[j] = 0.0; enumr[j] = 0.0; }
+    }
+    __device__ __forceinline__ void word(uint32_t v, double ti) { estep_word<true>(v, ti, __dmul_rn(ti, ti), table, lane8, esum, enumr, 4); }
+    __device__ __forceinline__ void end_tile(size_t k0, bool active) {
+        if (!active) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double e = __ddiv_rn(esum[j], enumr[j]);
+            if (e < 0) e = 0;          // 0/0 = NaN survives the clamp, as in the reference
+            E[k0 + j] = e;
+        }
+    }
+    __device__ __forceinline__ void epilogue(uint8_t*, const Params&) {}
+};
+
+// G-step accumulation (main_responseCalib.cpp:290-299): GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.  Every consumer warp
+// owns a private 256-bin histogram in shared memory (fp64 sums + 32-bit counts), so the atomics only ever collide between
+// lanes of one warp; the 12 histograms are folded in a fixed order and flushed with one global atomic per bin per CTA.
+struct GstepOp {
+    struct Params { const double* E; double* gsum; unsigned long long* gnum; };
+    static constexpr bool kUnroll = false;
+    static __device__ __forceinline__ void prologue(uint8_t* region, const Params&) {
+        uint32_t* z = reinterpret_cast<uint32_t*>(region);
+        for (int i = threadIdx.x; i < kEbWarps * 256 * 3; i += blockDim.x) z[i] = 0u;
+    }
+    double* hsum;          // [256] of this warp
+    unsigned* hcnt;        // [256] of this warp
+    const double* E;
+    double e[4];
+    bool active;
+    __device__ __forceinline__ GstepOp(uint8_t* region, const Params& p)
+        : hsum(reinterpret_cast<double*>(region) + (threadIdx.x >> 5) * 256),
+          hcnt(reinterpret_cast<unsigned*>(region + kEbWarps * 256 * 8) + (threadIdx.x >> 5) * 256), E(p.E), active(false) {}
+    __device__ __forceinline__ void begin_tile(size_t k0, bool act) {
+        active = act;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = act ? E[k0 + j] : 0.0;
+    }
+    __device__ __forceinline__ void word(uint32_t v, double ti) {
+        if (!active) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned b = (v >> (8 * j)) & 0xffu;
+            if (b == 255u) continue;
+            atomicAdd(hsum + b, __dmul_rn(e[j], ti));
+            atomicAdd(hcnt + b, 1u);
+        }
+    }
+    __device__ __forceinline__ void end_tile(size_t, bool) {}
+    __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
+        stream_consumer_barrier();
+        const double* hs = reinterpret_cast<const double*>(region);
+        const unsigned* hc = reinterpret_cast<const unsigned*>(region + kEbWarps * 256 * 8);
+        for (int b = threadIdx.x; b < 256; b += kEbWarps * 32) {
+            double sum = 0.0;
+            unsigned long long cnt = 0ull;
+            for (int w = 0; w < kEbWarps; ++w) { sum = __dadd_rn(sum, hs[w * 256 + b]); cnt += hc[w * 256 + b]; }
+            atomicAdd(p.gsum + b, sum);
+            atomicAdd(p.gnum + b, cnt);
+        }
+    }
+};
+
+// rmse() (main_responseCalib.cpp:50-69): e = sum (G[b] - t*E)^2 * 1e-10 over finite residuals of unsaturated samples, num = count
+struct RmseOp {
+    struct Params { const double* G; const double* E; double* acc; };
+    static constexpr bool kUnroll = true;
+    static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
+    uint32_t table, lane8;
+    const double* E;
+    double e[4];
+    double err;
+    unsigned cnt;
+    unsigned long long cnt_total;
+    bool active;
+    __device__ __forceinline__ RmseOp(uint8_t* region, const Params& p)
+        : table(smem_u32(region)), lane8((threadIdx.x & 31) * 8u), E(p.E), err(0.0), cnt(0u), cnt_total(0ull), active(false) {}
+    __device__ __forceinline__ void begin_tile(size_t k0, bool act) {
+        active = act;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = act ? E[k0 + j] : 0.0;
+    }
+    __device__ __forceinline__ void sample(uint32_t a, double ek, double ti) {
+        double g;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(g) : "r"(table + a));
+        const double r = __dsub_rn(g, __dmul_rn(ti, ek));
+        const bool ok = a < 0xff00u && (static_cast<uint32_t>(__double2hiint(r)) & 0x7ff00000u) != 0x7ff00000u;   // :58, :60
+        if (ok) {
+            err = __dadd_rn(err, __dmul_rn(__dmul_rn(r, r), 1e-10));
+            ++cnt;
+        }
+    }
+    __device__ __forceinline__ void word(uint32_t v, double ti) {
+        if (!active) return;
+        sample(__byte_perm(v, lane8, 0x5504), e[0], ti);
+        sample(__byte_perm(v, lane8, 0x5514), e[1], ti);
+        sample(__byte_perm(v, lane8, 0x5524), e[2], ti);
+        sample(__byte_perm(v, lane8, 0x5534), e[3], ti);
+    }
+    __device__ __forceinline__ void end_tile(size_t, bool) { cnt_total += cnt; cnt = 0u; }
+    __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
+        double c = static_cast<double>(cnt_total);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            err = __dadd_rn(err, __shfl_xor_sync(0xffffffffu, err, o));
+            c = __dadd_rn(c, __shfl_xor_sync(0xffffffffu, c, o));
+        }
+        stream_consumer_barrier();                      // every warp is done with the lookup table: reuse its first bytes
+        double* part = reinterpret_cast<double*>(region);
+        if ((threadIdx.x & 31) == 0) { part[2 * (threadIdx.x >> 5)] = err; part[2 * (threadIdx.x >> 5) + 1] = c; }
+        stream_consumer_barrier();
+        if (threadIdx.x == 0) {
+            double se = 0.0, sc = 0.0;
+            for (int w = 0; w < kEbWarps; ++w) { se = __dadd_rn(se, part[2 * w]); sc = __dadd_rn(sc, part[2 * w + 1]); }
+            atomicAdd(p.acc, se);
+            atomicAdd(p.acc + 1, sc);
+        }
+    }
+};
+
+template <class Op>
+static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params& prm, cudaStream_t stream) {
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(rc_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rc_stream_kernel<Op>, kEbThreads, kEbSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (static_cast<long long>(a.npix) + kEbTile - 1) / kEbTile;
+    long long grid = static_cast<long long>(sms) * per_sm;
+    if (grid > tiles) grid = tiles;
+    rc_stream_kernel<Op><<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(a, prm);
+    return cudaGetLastError();
+}
+// the bulk-copy loader needs 16-byte aligned rows
+static bool stream_ok(const uint8_t* data, int npix) {
+    static const bool allow = [] { const char* e = getenv("MDC_ESTEP_BULK"); return !(e && e[0] == '0'); }();      // A/B knob
+    return allow && npix % 16 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0;
 }
 
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E, cudaStream_t stream) {
@@ -905,19 +1067,8 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
     int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static const bool allow_bulk = [] { const char* e = getenv("MDC_ESTEP_BULK"); return !(e && e[0] == '0'); }();      // A/B knob
-    if (allow_bulk && npix % 16 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
-        cudaError_t e = cudaFuncSetAttribute(estep_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbSmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_bulk_kernel, kEbThreads, kEbSmemBytes);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        const long long tiles = (static_cast<long long>(npix) + kEbTile - 1) / kEbTile;
-        long long grid = static_cast<long long>(sms) * per_sm;
-        if (grid > tiles) grid = tiles;
-        estep_bulk_kernel<<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(data, n, static_cast<uint32_t>(npix), t, G, E);
-        return cudaGetLastError();
-    }
+    if (stream_ok(data, npix))
+        return launch_stream<EstepOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, EstepOp::Params{G, E}, stream);
     const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
     const size_t smem = kEstepTableBytes + static_cast<size_t>(kEstepMaxN) * sizeof(double);      // 96 KB
     cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1057,7 +1208,12 @@ cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* 
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+    if (stream_ok(data, npix)) {
+        e = launch_stream<GstepOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, GstepOp::Params{E, gsum, gnum}, s);
+        if (e != cudaSuccess) return e;
+    } else {
+        rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+    }
     rc_gstep_finish_kernel<<<1, 32, 0, s>>>(gsum, gnum, G);
     return cudaGetLastError();
 }
@@ -1070,6 +1226,7 @@ cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cu
 cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s);
     if (e != cudaSuccess) return e;
+    if (stream_ok(data, npix)) return launch_stream<RmseOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, RmseOp::Params{G, E, acc2}, s);
     rc_rmse_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, G, E, acc2);
     return cudaGetLastError();
 }

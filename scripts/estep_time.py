@@ -22,8 +22,23 @@ def main():
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in ev]
     alg = n * npix + 8 * npix
+
+    def time_it(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    G2 = G.clone()
+    gstep_ms = time_it(lambda: ctx.rc_gstep(data, t, E, G2))
+    rmse_ms = time_it(lambda: ctx.rc_rmse(data, t, G, E))
+    einit_ms = time_it(lambda: ctx.rc_einit(data, E.clone()))
     print(json.dumps({"ms": float(np.mean(ms)), "min_ms": float(np.min(ms)), "gbs": alg / (np.mean(ms) * 1e-3) / 1e9,
-                      "checksum": float(torch.nansum(E).item()),
+                      "checksum": float(torch.nansum(E).item()), "gstep_ms": gstep_ms, "rmse_ms": rmse_ms, "einit_ms": einit_ms,
+                      "gstep_checksum": float(torch.nansum(G2).item()),
                       "env": {k: v for k, v in os.environ.items() if k.startswith("MDC_")}}), flush=True)
 
 if __name__ == "__main__":

@@ -301,12 +301,13 @@ def test_estep_non_finite_and_negative_exposures(api, port):
     assert_bits_equal(E.cpu().numpy(), exp, "E-step with t=inf")
 
 
-def test_response_calib_building_blocks(api, port):
+@pytest.mark.parametrize("w,h", [(96, 64), (50, 30)], ids=["bulk_loader_16px_multiple", "generic_size"])
+def test_response_calib_building_blocks(api, port, w, h):
     """leak padding / E-init / rescale bit-exact; G-step and rmse to rounding (the reference sums
     10^5..10^9 terms sequentially, the GPU in parallel): TOL_SUM relative."""
     TOL_SUM = 1e-10
     rng = np.random.default_rng(21)
-    n, w, h = 23, 96, 64
+    n = 23
     npix = w * h
     data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
     data[:, 100:140] = 255                          # a saturated blob
