@@ -300,6 +300,20 @@ def run_gpu_arm(args):
         alg = n_img * npix + 8 * npix
         estep = {"ms_per_pass": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
                  "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "workload": "n=1000 x 1 MP u8 -> f64 E[1 MP]"}
+        # the other passes of the calibrator over the same stack, and one whole iteration of its loop
+        # (G-step, E-step, rescale, 3 x rmse; main_responseCalib.cpp:281-362)
+
+        def ms_of(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        G_new = torch.zeros_like(G_tab)
+        estep["gstep_ms"] = ms_of(lambda: ctx.rc_gstep(data, t_exp, E_out, G_new))
+        estep["rmse_ms"] = ms_of(lambda: ctx.rc_rmse(data, t_exp, G_tab, E_out))
         del data, E_out
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)

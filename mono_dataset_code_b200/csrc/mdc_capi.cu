@@ -608,13 +608,19 @@ extern "C" int mdc_rc_einit(mdc_ctx* c, const uint8_t* d_data, int n, int npix, 
     return finish(c, stream, s);
 }
 
-extern "C" int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, mdc_stream stream) {
+// reuse_counts: GNum[] (the histogram of the unsaturated samples) is still in the context's scratch from the previous G-step over
+// the SAME images, so only the sums are accumulated
+static int rc_gstep_impl(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, bool reuse_counts,
+                         mdc_stream stream) {
     if (!c || !d_data || !d_t || !d_E || !d_G || n < 0 || npix < 0) { mdc_set_error("mdc_rc_gstep: bad argument"); return MDC_ERR_INVALID_ARG; }
     CU_CHECK(cudaSetDevice(c->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    CU_CHECK(launch_rc_gstep(d_data, n, npix, d_t, d_E, c->d_rc, reinterpret_cast<unsigned long long*>(c->d_rc + 256), d_G, s));
+    CU_CHECK(launch_rc_gstep(d_data, n, npix, d_t, d_E, c->d_rc, reinterpret_cast<unsigned long long*>(c->d_rc + 256), d_G, reuse_counts, s));
     c->launches += 2;
     return finish(c, stream, s);
+}
+extern "C" int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, mdc_stream stream) {
+    return rc_gstep_impl(c, d_data, n, npix, d_t, d_E, d_G, false, stream);
 }
 
 extern "C" int mdc_rc_rescale(mdc_ctx* c, int npix, double* d_E, double* d_G, double* factor_host) {
@@ -647,7 +653,7 @@ extern "C" int mdc_response_calib(mdc_ctx* c, const uint8_t* d_data, int n, int 
     CU_CHECK(cudaMemsetAsync(d_G, 0, 256 * sizeof(double), c->stream));
     for (int it = 0; it < nits; ++it) {
         double r[2], row[4] = {0, 0, 0, 0};
-        if ((rc = mdc_rc_gstep(c, d_data, n, npix, d_t, d_E, d_G, c->stream)) != MDC_OK) return rc;
+        if ((rc = rc_gstep_impl(c, d_data, n, npix, d_t, d_E, d_G, /*reuse_counts=*/it > 0, c->stream)) != MDC_OK) return rc;
         if ((rc = mdc_rc_rmse(c, d_data, n, npix, d_t, d_G, d_E, r)) != MDC_OK) return rc;
         row[0] = r[0];
         printf("optG RMSE = %f! \t", r[0]);

@@ -935,50 +935,59 @@ struct EstepOp {
     __device__ __forceinline__ void epilogue(uint8_t*, const Params&) {}
 };
 
-// G-step accumulation (main_responseCalib.cpp:290-299): GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.  Every consumer warp
-// owns a private 256-bin histogram in shared memory (fp64 sums + 32-bit counts), so the atomics only ever collide between
-// lanes of one warp; the 12 histograms are folded in a fixed order and flushed with one global atomic per bin per CTA.
+// G-step accumulation (main_responseCalib.cpp:290-299): GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.  The CTA keeps one
+// histogram in shared memory, laid out like the lookup table: one 256-byte row per value = 16 fp64 sum slots (slot =
+// lane & 15, so the two half-warps of a 64-bit access each touch 16 different bank pairs) followed by 32 u32 count slots
+// (slot = lane).  Shared-memory atomics are therefore bank-conflict-free and only collide when two threads hit the same
+// (value, slot) at the same moment; one PRMT builds each address.  The slots are folded in a fixed order at the end and
+// flushed with one global atomic per bin per CTA.  kCount = false: the caller already holds GNum (it depends on the images only,
+// so the optimisation loop computes it once).
+template <bool kCount>
 struct GstepOp {
     struct Params { const double* E; double* gsum; unsigned long long* gnum; };
     static constexpr bool kUnroll = false;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params&) {
         uint32_t* z = reinterpret_cast<uint32_t*>(region);
-        for (int i = threadIdx.x; i < kEbWarps * 256 * 3; i += blockDim.x) z[i] = 0u;
+        for (int i = threadIdx.x; i < kEbRegionBytes / 4; i += blockDim.x) z[i] = 0u;
     }
-    double* hsum;          // [256] of this warp
-    unsigned* hcnt;        // [256] of this warp
+    uint8_t* hist;
+    uint32_t lane_sum, lane_cnt;      // byte offsets of this lane's slots inside a row
     const double* E;
     double e[4];
     bool active;
     __device__ __forceinline__ GstepOp(uint8_t* region, const Params& p)
-        : hsum(reinterpret_cast<double*>(region) + (threadIdx.x >> 5) * 256),
-          hcnt(reinterpret_cast<unsigned*>(region + kEbWarps * 256 * 8) + (threadIdx.x >> 5) * 256), E(p.E), active(false) {}
+        : hist(region), lane_sum((threadIdx.x & 15) * 8u), lane_cnt(128u + (threadIdx.x & 31) * 4u), E(p.E), active(false) {}
     __device__ __forceinline__ void begin_tile(size_t k0, bool act) {
         active = act;
 #pragma unroll
         for (int j = 0; j < 4; ++j) e[j] = act ? E[k0 + j] : 0.0;
     }
+    __device__ __forceinline__ void sample(uint32_t a_sum, uint32_t a_cnt, double ek, double ti) {
+        if (a_sum >= 0xff00u) return;      // saturated, :293
+        atomicAdd(reinterpret_cast<double*>(hist + a_sum), __dmul_rn(ek, ti));
+        if (kCount) atomicAdd(reinterpret_cast<unsigned*>(hist + a_cnt), 1u);
+    }
     __device__ __forceinline__ void word(uint32_t v, double ti) {
         if (!active) return;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned b = (v >> (8 * j)) & 0xffu;
-            if (b == 255u) continue;
-            atomicAdd(hsum + b, __dmul_rn(e[j], ti));
-            atomicAdd(hcnt + b, 1u);
-        }
+        sample(__byte_perm(v, lane_sum, 0x5504), __byte_perm(v, lane_cnt, 0x5504), e[0], ti);
+        sample(__byte_perm(v, lane_sum, 0x5514), __byte_perm(v, lane_cnt, 0x5514), e[1], ti);
+        sample(__byte_perm(v, lane_sum, 0x5524), __byte_perm(v, lane_cnt, 0x5524), e[2], ti);
+        sample(__byte_perm(v, lane_sum, 0x5534), __byte_perm(v, lane_cnt, 0x5534), e[3], ti);
     }
     __device__ __forceinline__ void end_tile(size_t, bool) {}
     __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
         stream_consumer_barrier();
-        const double* hs = reinterpret_cast<const double*>(region);
-        const unsigned* hc = reinterpret_cast<const unsigned*>(region + kEbWarps * 256 * 8);
-        for (int b = threadIdx.x; b < 256; b += kEbWarps * 32) {
+        for (int b = threadIdx.x; b < 255; b += kEbWarps * 32) {
+            const double* hs = reinterpret_cast<const double*>(region + b * 256);
+            const unsigned* hc = reinterpret_cast<const unsigned*>(region + b * 256 + 128);
             double sum = 0.0;
             unsigned long long cnt = 0ull;
-            for (int w = 0; w < kEbWarps; ++w) { sum = __dadd_rn(sum, hs[w * 256 + b]); cnt += hc[w * 256 + b]; }
+            for (int q = 0; q < 16; ++q) sum = __dadd_rn(sum, hs[q]);
             atomicAdd(p.gsum + b, sum);
-            atomicAdd(p.gnum + b, cnt);
+            if (kCount) {
+                for (int q = 0; q < 32; ++q) cnt += hc[q];
+                if (cnt) atomicAdd(p.gnum + b, cnt);
+            }
         }
     }
 };
@@ -1203,13 +1212,20 @@ cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cud
     rc_einit_kernel<<<(npix + 255) / 256, 256, 0, s>>>(data, n, static_cast<size_t>(npix), E);
     return cudaGetLastError();
 }
-cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G, cudaStream_t s) {
+cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G,
+                            bool reuse_counts, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(gsum, 0, 256 * sizeof(double), s);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
-    if (stream_ok(data, npix)) {
-        e = launch_stream<GstepOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, GstepOp::Params{E, gsum, gnum}, s);
+    const bool stream = stream_ok(data, npix);
+    reuse_counts = reuse_counts && stream;
+    if (!reuse_counts) {
+        e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return e;
+    }
+    if (stream) {
+        const StreamArgs a{data, n, static_cast<uint32_t>(npix), t};
+        e = reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, gsum, gnum}, s)
+                         : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, gsum, gnum}, s);
         if (e != cudaSuccess) return e;
     } else {
         rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);

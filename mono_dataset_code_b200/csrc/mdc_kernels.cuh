@@ -73,7 +73,7 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
 cudaError_t launch_rc_leak_padding(const uint8_t* in, uint8_t* out, int n, int w, int h, cudaStream_t s);
 cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cudaStream_t s);
 cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
-                            double* G, cudaStream_t s);
+                            double* G, bool reuse_counts, cudaStream_t s);
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s);
 cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s);
 

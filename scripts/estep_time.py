@@ -36,8 +36,14 @@ def main():
     gstep_ms = time_it(lambda: ctx.rc_gstep(data, t, E, G2))
     rmse_ms = time_it(lambda: ctx.rc_rmse(data, t, G, E))
     einit_ms = time_it(lambda: ctx.rc_einit(data, E.clone()))
+    import time
+    E3, G3 = torch.empty_like(E), torch.zeros_like(G)
+    ctx.response_calib(data, t, 1, E3, G3)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ctx.response_calib(data, t, 5, E3, G3)
+    torch.cuda.synchronize(); calib_ms = (time.perf_counter() - t0) * 1e3 / 5
     print(json.dumps({"ms": float(np.mean(ms)), "min_ms": float(np.min(ms)), "gbs": alg / (np.mean(ms) * 1e-3) / 1e9,
-                      "checksum": float(torch.nansum(E).item()), "gstep_ms": gstep_ms, "rmse_ms": rmse_ms, "einit_ms": einit_ms,
+                      "checksum": float(torch.nansum(E).item()), "gstep_ms": gstep_ms, "rmse_ms": rmse_ms, "einit_ms": einit_ms, "calib_ms_per_iteration": calib_ms,
                       "gstep_checksum": float(torch.nansum(G2).item()),
                       "env": {k: v for k, v in os.environ.items() if k.startswith("MDC_")}}), flush=True)
 
