@@ -78,6 +78,15 @@ float mdc_fov_omega(const mdc_fov* f);                               /* getOmega
 int mdc_fov_original_calibration(const mdc_fov* f, float v[5]);      /* getOriginalCalibration(), :61-70 */
 /* distortCoordinates(float*, float*, int), FOVUndistorter.cpp:280-319 (host, in place). */
 int mdc_fov_distort_coordinates(const mdc_fov* f, float* x, float* y, int n);
+/* The same function on the GPU, in place on DEVICE arrays of n points (n up to 2^63; vignetteCalib calls it with 10^6-point
+ * grids per image, main_vignetteCalib.cpp:284).  Bit-identical to the host version: sqrtf and the divisions are IEEE
+ * operations, and atanf is a restatement of glibc 2.39's algorithm that matches this platform's libm on every float
+ * (csrc/mdc_atanf.h).  `device` = CUDA ordinal the arrays live on, `stream` as for mdc_prepare_batch. */
+int mdc_fov_distort_coordinates_device(const mdc_fov* f, float* d_x, float* d_y, size_t n, int device, mdc_stream stream);
+/* The restated atanf alone, so that a deployment can check it against ITS libm: out[i] = atanf(in[i]) evaluated on the host
+ * (mdc_atanf_host) or on the GPU (mdc_atanf_device, device pointers). */
+void mdc_atanf_host(const float* in, float* out, size_t n);
+int mdc_atanf_device(const float* d_in, float* d_out, size_t n, int device, mdc_stream stream);
 /* remapX / remapY (out_w*out_h floats each; NULL for an invalid object) — private in the
  * reference (FOVUndistorter.h:92-93); exposed for bit-compare and for NCCL broadcast. */
 const float* mdc_fov_remap_x(const mdc_fov* f);

@@ -34,6 +34,9 @@ SIGNATURES = {
     "mdc_fov_omega": (C.c_float, [_vp]),
     "mdc_fov_original_calibration": (C.c_int, [_vp, _f32p]),
     "mdc_fov_distort_coordinates": (C.c_int, [_vp, _f32p, _f32p, C.c_int]),
+    "mdc_fov_distort_coordinates_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "mdc_atanf_host": (None, [_f32p, _f32p, C.c_size_t]),
+    "mdc_atanf_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp]),
     "mdc_fov_remap_x": (_f32p, [_vp]),
     "mdc_fov_remap_y": (_f32p, [_vp]),
     "mdc_photo_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),

@@ -112,6 +112,20 @@ class UndistorterFOV:
             return
         lib.mdc_fov_distort_coordinates(self._h, in_x.ctypes.data_as(_f32p), in_y.ctypes.data_as(_f32p), n)
 
+    def distortCoordinatesDevice(self, x, y) -> None:
+        """distortCoordinates in place on float32 CUDA tensors (any number of points); bit-identical to the host version."""
+        import torch
+        assert x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32
+        assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel() and x.device == y.device
+        if not self._h:
+            print("ERROR: invalid UndistorterFOV!")
+            return
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = lib.mdc_fov_distort_coordinates_device(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), x.numel(),
+                                                    x.device.index or 0, C.c_void_p(stream))
+        if rc not in (0, 4):        # 4 = MDC_ERR_INVALID_OBJECT: printed, like the reference
+            check(rc, "mdc_fov_distort_coordinates_device")
+
     # ---- per-frame operator (FOVUndistorter.cpp:322-370)
     def _context(self, device=0):
         if self._ctx is None:
@@ -381,3 +395,21 @@ class FramePreparer:
             out = [torch.empty((n, w * h), dtype=torch.float32, device=frames.device) for (w, h) in self.level_shapes(rectify, levels)]
         self.ctx.prepare_batch(frames, _flags(rectify, removeGamma, removeVignette, nanOverexposed), out)
         return out
+
+
+def atanf_host(x: np.ndarray) -> np.ndarray:
+    """The restated glibc atanf (csrc/mdc_atanf.h) evaluated on the host."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib.mdc_atanf_host(x.ctypes.data_as(_f32p), out.ctypes.data_as(_f32p), x.size)
+    return out
+
+
+def atanf_device(x):
+    """The same function evaluated by the GPU (float32 CUDA tensor in, new tensor out)."""
+    import torch
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty_like(x)
+    check(lib.mdc_atanf_device(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), x.numel(), x.device.index or 0,
+                               C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mdc_atanf_device")
+    return out

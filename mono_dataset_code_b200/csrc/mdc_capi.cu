@@ -571,6 +571,30 @@ extern "C" int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_fram
     return finish(c, stream, s);
 }
 
+extern "C" int mdc_fov_distort_coordinates_device(const mdc_fov* f, float* d_x, float* d_y, size_t n, int device, mdc_stream stream) {
+    if (!f || (n && (!d_x || !d_y))) { mdc_set_error("mdc_fov_distort_coordinates_device: bad argument"); return MDC_ERR_INVALID_ARG; }
+    if (!f->valid) {
+        printf("ERROR: invalid UndistorterFOV!\n");          // FOVUndistorter.cpp:282-286
+        mdc_set_error("distortCoordinates on an invalid rectifier");
+        return MDC_ERR_INVALID_OBJECT;
+    }
+    CU_CHECK(cudaSetDevice(device));
+    mdc_distort_constants h;
+    mdc_fov_distort_constants(f, &h);
+    const DistortConstants k{h.ocx, h.ocy, h.ofx, h.ofy, h.d2t, h.omega, h.fx, h.fy, h.cx, h.cy};
+    CU_CHECK(launch_fov_distort(d_x, d_y, n, k, static_cast<cudaStream_t>(stream)));
+    if (!stream) CU_CHECK(cudaStreamSynchronize(nullptr));
+    return MDC_OK;
+}
+
+extern "C" int mdc_atanf_device(const float* d_in, float* d_out, size_t n, int device, mdc_stream stream) {
+    if (n && (!d_in || !d_out)) { mdc_set_error("mdc_atanf_device: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(device));
+    CU_CHECK(launch_atanf(d_in, d_out, n, static_cast<cudaStream_t>(stream)));
+    if (!stream) CU_CHECK(cudaStreamSynchronize(nullptr));
+    return MDC_OK;
+}
+
 extern "C" int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, double* d_E, mdc_stream stream) {
     if (!c || !d_data || !d_t || !d_G || !d_E || n < 0 || npix < 0) { mdc_set_error("mdc_estep: bad argument"); return MDC_ERR_INVALID_ARG; }
     CU_CHECK(cudaSetDevice(c->device));

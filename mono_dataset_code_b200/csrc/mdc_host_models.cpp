@@ -22,6 +22,7 @@
 #include <fstream>
 #include <sstream>
 
+#include "mdc_atanf.h"
 #include "mdc_internal.h"
 
 // ------------------------------------------------------------------------- error slot
@@ -76,25 +77,37 @@ Intrinsics input_intrinsics(const mdc_fov* f) {
 
 }  // namespace
 
-void mdc_fov_distort(const mdc_fov* f, float* xs, float* ys, int n) {
+// the ten per-calibration constants of distortCoordinates, evaluated exactly like the reference does (FOVUndistorter.cpp:286-301)
+void mdc_fov_distort_constants(const mdc_fov* f, mdc_distort_constants* k) {
     const MathSel m{f->float_math};
-    const float omega = f->in_calib[4];
-    const float d2t = m.d2t(omega);
+    k->omega = f->in_calib[4];
+    k->d2t = m.d2t(k->omega);
     const Intrinsics in = input_intrinsics(f);
+    k->fx = in.fx; k->fy = in.fy; k->cx = in.cx; k->cy = in.cy;
     // note: here the reference subtracts a FLOAT 0.5f (FOVUndistorter.cpp:300-301)
-    const float ofx = f->out_calib[0] * f->out_w;
-    const float ofy = f->out_calib[1] * f->out_h;
-    const float ocx = f->out_calib[2] * f->out_w - 0.5f;
-    const float ocy = f->out_calib[3] * f->out_h - 0.5f;
+    k->ofx = f->out_calib[0] * f->out_w;
+    k->ofy = f->out_calib[1] * f->out_h;
+    k->ocx = f->out_calib[2] * f->out_w - 0.5f;
+    k->ocy = f->out_calib[3] * f->out_h - 0.5f;
+}
+
+void mdc_fov_distort(const mdc_fov* f, float* xs, float* ys, int n) {
+    mdc_distort_constants k;
+    mdc_fov_distort_constants(f, &k);
     for (int i = 0; i < n; ++i) {
-        float nx = (xs[i] - ocx) / ofx;
-        float ny = (ys[i] - ocy) / ofy;
+        float nx = (xs[i] - k.ocx) / k.ofx;
+        float ny = (ys[i] - k.ocy) / k.ofy;
         float rad = sqrtf(nx * nx + ny * ny);
         float scale = 1;
-        if (!(rad == 0 || omega == 0)) scale = atanf(rad * d2t) / (omega * rad);
-        xs[i] = in.fx * scale * nx + in.cx;
-        ys[i] = in.fy * scale * ny + in.cy;
+        if (!(rad == 0 || k.omega == 0)) scale = atanf(rad * k.d2t) / (k.omega * rad);
+        xs[i] = k.fx * scale * nx + k.cx;
+        ys[i] = k.fy * scale * ny + k.cy;
     }
+}
+
+// the restated atanf (mdc_atanf.h) evaluated on the host, so that it can be compared with the platform's libm without a GPU
+extern "C" void mdc_atanf_host(const float* in, float* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) out[i] = mdc_atanf(in[i]);
 }
 
 void mdc_fov_build(mdc_fov* f, int mode, const float out_calib_in[5]) {

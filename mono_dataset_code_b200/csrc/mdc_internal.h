@@ -41,6 +41,8 @@ bool mdc_read_gray_image(const std::string& path, mdc_gray_image* out);
 
 // Table builders (strict IEEE float; see mdc_host_models.cpp).
 void mdc_fov_build(mdc_fov* f, int mode, const float out_calib_in[5]);
+struct mdc_distort_constants { float ocx, ocy, ofx, ofy, d2t, omega, fx, fy, cx, cy; };
+void mdc_fov_distort_constants(const mdc_fov* f, mdc_distort_constants* k);
 void mdc_fov_distort(const mdc_fov* f, float* xs, float* ys, int n);
 bool mdc_photo_set_gamma(mdc_photo* p, const float raw[256]);
 void mdc_photo_set_vignette(mdc_photo* p, const void* pixels, int depth);

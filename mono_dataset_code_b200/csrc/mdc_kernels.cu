@@ -21,6 +21,7 @@
 
 #include <type_traits>
 
+#include "mdc_atanf.h"
 #include "mdc_kernels.cuh"
 
 namespace mdc {
@@ -660,6 +661,42 @@ cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_
     size_t blocks = (total + 255) / 256;
     if (blocks > 148u * 16u) blocks = 148u * 16u;
     pyr_down_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, sw, sh, dst, n_frames);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// distortCoordinates on the device (FOVUndistorter.cpp:280-319), in place, bit-identical to the host: explicit IEEE
+// operations in the reference's order, atanf restated from glibc (mdc_atanf.h).
+// =====================================================================================
+__global__ void __launch_bounds__(256) fov_distort_kernel(float* __restrict__ xs, float* __restrict__ ys, size_t n, DistortConstants k) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float nx = __fdiv_rn(__fsub_rn(xs[i], k.ocx), k.ofx);
+        const float ny = __fdiv_rn(__fsub_rn(ys[i], k.ocy), k.ofy);
+        const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)));
+        float scale = 1.0f;
+        if (!(rad == 0.0f || k.omega == 0.0f)) scale = __fdiv_rn(mdc_atanf(__fmul_rn(rad, k.d2t)), __fmul_rn(k.omega, rad));
+        xs[i] = __fadd_rn(__fmul_rn(__fmul_rn(k.fx, scale), nx), k.cx);
+        ys[i] = __fadd_rn(__fmul_rn(__fmul_rn(k.fy, scale), ny), k.cy);
+    }
+}
+__global__ void __launch_bounds__(256) atanf_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = mdc_atanf(in[i]);
+}
+static unsigned stream_blocks(size_t n) {
+    size_t b = (n + 255) / 256;
+    if (b > 148u * 16u) b = 148u * 16u;
+    return static_cast<unsigned>(b < 1 ? 1 : b);
+}
+cudaError_t launch_fov_distort(float* xs, float* ys, size_t n, const DistortConstants& k, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fov_distort_kernel<<<stream_blocks(n), 256, 0, stream>>>(xs, ys, n, k);
+    return cudaGetLastError();
+}
+cudaError_t launch_atanf(const float* in, float* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    atanf_kernel<<<stream_blocks(n), 256, 0, stream>>>(in, out, n);
     return cudaGetLastError();
 }
 

@@ -67,6 +67,10 @@ cudaError_t launch_undistort_f32(const float* in, float* out, int in_w, int n_in
                                  const float* remap_x, const float* remap_y, cudaStream_t stream);
 cudaError_t launch_pyr_down(const float* src, int sw, int sh, float* dst, int n_frames, cudaStream_t stream);
 cudaError_t launch_pyr_down2(const float* src, int sw, int sh, float* d1, float* d2, int n_frames, cudaStream_t stream);
+// per-calibration constants of distortCoordinates (same ten floats as mdc_distort_constants on the host side)
+struct DistortConstants { float ocx, ocy, ofx, ofy, d2t, omega, fx, fy, cx, cy; };
+cudaError_t launch_fov_distort(float* xs, float* ys, size_t n, const DistortConstants& k, cudaStream_t stream);
+cudaError_t launch_atanf(const float* in, float* out, size_t n, cudaStream_t stream);
 cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, const double* G, double* E,
                          cudaStream_t stream);
 

@@ -200,6 +200,65 @@ def test_full_size_configs(name, api, port, dataset_dir):
             assert np.array_equal(a.view(np.uint32), np.broadcast_to(a[:1], a.shape).view(np.uint32)), f"batch position dependence, level {l}"
 
 
+def test_batch_beyond_4gb_and_2g_elements(api, port, dataset_dir):
+    """1700 C2 frames in ONE call: 2.2 GB of input, level 0 alone is 8.9 GB = 2.2e9 floats, so every frame offset past
+    ~frame 1638 needs 64-bit element arithmetic (and every one past ~819 64-bit byte arithmetic).  Frames repeat with period 4:
+    the first four are checked against the oracle, all others against those, on the device."""
+    name = "c2_crop_1280"
+    iw, ih, ow, oh, mode, calib = BIG_CALIBS[name]
+    files = dataset_dir(name)
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(4, iw, ih)
+    n = 1700
+    big = torch.from_numpy(frames).cuda().repeat(n // 4, 1)
+    assert big.shape == (n, iw * ih)
+    for use_tma in (-1, 0):
+        prep.ctx.configure(use_tma=use_tma)
+        outs = prep.prepare_device(big, 1, 1, 1, 1, levels=3)
+        for i in range(4):
+            exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], 1, 1, 1, 1), ow, oh, 3)
+            for l in range(3):
+                assert_bits_equal(outs[l][i].cpu().numpy(), exp[l], f"tma={use_tma} frame={i} level={l}")
+        for l in range(3):
+            a = outs[l].view(torch.int32).view(n // 4, 4, -1)
+            for lo in range(0, n // 4, 25):      # compare in slabs to bound the temporaries
+                assert bool((a[lo:lo + 25] == a[:1]).all()), f"tma={use_tma} level {l}: frames {4 * lo}.. differ from their replicas"
+        del outs
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name", list(CALIBS))
+def test_distort_coordinates_on_device_is_bit_identical(name, api, dataset_dir):
+    """distortCoordinates (FOVUndistorter.cpp:280-319) as a batched device op, against the host version
+    (which is itself pinned against the reference build in the CPU suite)."""
+    iw, ih, ow, oh, mode, calib = CALIBS[name]
+    files = dataset_dir(name)
+    u = api.UndistorterFOV(files["camera"])
+    rng = np.random.default_rng(31)
+    n = 200_003
+    x = rng.uniform(-0.5 * ow, 1.5 * ow, n).astype(np.float32)
+    y = rng.uniform(-0.5 * oh, 1.5 * oh, n).astype(np.float32)
+    x[:4] = [0.0, ow - 1.0, u.getK_rect()[0, 2], -0.0]
+    y[:4] = [0.0, oh - 1.0, u.getK_rect()[1, 2], 3.0]        # includes the principal point (radius 0 -> scale 1)
+    hx, hy = x.copy(), y.copy()
+    u.distortCoordinates(hx, hy)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    u.distortCoordinatesDevice(dx, dy)
+    assert_bits_equal(dx.cpu().numpy(), hx, f"{name} x")
+    assert_bits_equal(dy.cpu().numpy(), hy, f"{name} y")
+    # the identity grid reproduces the remap tables before clamping/blackening: compare where the table keeps the value
+    gx, gy = np.meshgrid(np.arange(ow, dtype=np.float32), np.arange(oh, dtype=np.float32))
+    dgx, dgy = torch.from_numpy(gx.ravel().copy()).cuda(), torch.from_numpy(gy.ravel().copy()).cuda()
+    u.distortCoordinatesDevice(dgx, dgy)
+    rx, ry = u.remap_tables()
+    keep = (rx > 0.011) & (ry > 0.011) & (rx < iw - 1.011) & (ry < ih - 1.011)
+    assert keep.any() or name == "full_wrap"
+    assert np.array_equal(dgx.cpu().numpy()[keep].view(np.uint32), rx[keep].view(np.uint32))
+    assert np.array_equal(dgy.cpu().numpy()[keep].view(np.uint32), ry[keep].view(np.uint32))
+
+
 def test_estep_bit_exact(api, port):
     rng = np.random.default_rng(11)
     # (4100, 640): more exposures than the kernel caches in shared memory -> times come through L1; (5, 130): shorter than one
