@@ -4,8 +4,9 @@
 // This is init-time code (tens of milliseconds once per sequence), deliberately kept on the
 // CPU: the tables must be BIT-IDENTICAL to the reference's, and they depend on glibc's
 // atanf/tan/sqrtf and on the exact float/double promotion pattern of the reference's
-// expressions (SURVEY.md §3.4, §7 "bit-exact tables are toolchain-sensitive").  CUDA's
-// atanf is not glibc's.  Compile with -ffp-contract=off and no -ffast-math/-march.
+// expressions (SURVEY.md §3.4, §7 "bit-exact tables are toolchain-sensitive").  CUDA's own
+// atanf is not glibc's (the device-side distortCoordinates uses the restatement in mdc_atanf.h,
+// which is).  Compile with -ffp-contract=off and no -ffast-math/-march.
 //
 // Behaviour mirrored (file:line in /root/reference/src):
 //   camera.txt parsing and validity rules ......... FOVUndistorter.cpp:55-126
