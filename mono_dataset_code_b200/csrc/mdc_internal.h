@@ -46,3 +46,8 @@ void mdc_fov_distort_constants(const mdc_fov* f, mdc_distort_constants* k);
 void mdc_fov_distort(const mdc_fov* f, float* xs, float* ys, int n);
 bool mdc_photo_set_gamma(mdc_photo* p, const float raw[256]);
 void mdc_photo_set_vignette(mdc_photo* p, const void* pixels, int depth);
+
+// Context accessors for translation units that do not see the context's layout (mdc_vignette_calib.cu).
+int mdc_ctx_device_ordinal(const mdc_ctx* c);
+void* mdc_ctx_stream_handle(mdc_ctx* c);          // the context's own cudaStream_t
+void mdc_ctx_add_launches(mdc_ctx* c, int n);

@@ -130,3 +130,42 @@ def write_dataset_dir(path: str, in_w: int, in_h: int, out_w: int, out_h: int, m
         write_pgm(files["vignette_pgm"], vig)
     files["vignette_pixels"] = vig
     return files
+
+
+def vignette_calib_problem(n: int, gw: int, gh: int, wI: int, hI: int, seed: int = 0, noise: float = 0.5):
+    """A synthetic vignetteCalib state (what main_vignetteCalib.cpp holds at :395): a textured plane seen from n poses through
+    a camera with a known vignette.  Returns dict(images [n, wI*hI], p2x, p2y [n, gw*gh] float32 with NaNs, true_vignette
+    [wI*hI], true_plane [gw*gh]).  The maps are smooth projective warps; entries whose rounded position is not strictly inside
+    (1, wI-2) x (1, hI-2) are NaN, as the reference makes them (:352-356); a few image pixels are NaN (:300-310)."""
+    rng = np.random.default_rng(seed)
+    gy, gx = np.mgrid[0:gh, 0:gw].astype(np.float64)
+    plane = (110.0 + 60.0 * np.sin(gx * (9.0 / gw)) * np.cos(gy * (7.0 / gh)) + 25.0 * ((gx // max(gw // 8, 1) + gy // max(gh // 8, 1)) % 2)).ravel()
+    yy, xx = np.mgrid[0:hI, 0:wI].astype(np.float64)
+    r2 = ((xx - wI / 2) ** 2 + (yy - hI / 2) ** 2) / ((wI / 2) ** 2 + (hI / 2) ** 2)
+    vig = (1.0 - 0.55 * r2).ravel()
+    images = np.empty((n, wI * hI), np.float32)
+    p2x = np.empty((n, gw * gh), np.float32)
+    p2y = np.empty((n, gw * gh), np.float32)
+    u, v = gx / gw - 0.5, gy / gh - 0.5
+    for i in range(n):
+        ang = rng.uniform(-0.5, 0.5)
+        sc = rng.uniform(0.45, 0.8) * min(wI, hI)
+        tx, ty = wI / 2 + rng.uniform(-0.2, 0.2) * wI, hI / 2 + rng.uniform(-0.2, 0.2) * hI
+        px_, py_ = rng.uniform(-0.15, 0.15, 2)                      # mild perspective
+        den = 1.0 + px_ * u + py_ * v
+        X = (tx + sc * (np.cos(ang) * u - np.sin(ang) * v) / den).astype(np.float32).ravel()
+        Y = (ty + sc * (np.sin(ang) * u + np.cos(ang) * v) / den).astype(np.float32).ravel()
+        ui, vi = (X + np.float32(0.5)).astype(np.int64), (Y + np.float32(0.5)).astype(np.int64)
+        bad = ~((ui > 1) & (vi > 1) & (ui < wI - 2) & (vi < hI - 2))
+        X[bad] = np.nan
+        Y[bad] = np.nan
+        p2x[i], p2y[i] = X, Y
+        # render: every image pixel takes the plane colour of the nearest plane point that projects onto it (good enough
+        # for a parity fixture; uncovered pixels keep a flat background), times the vignette, plus noise
+        img = np.full(wI * hI, 90.0)
+        ok = ~bad
+        img[vi[ok] * wI + ui[ok]] = plane[ok]
+        img = img * vig + rng.normal(0.0, noise, wI * hI)
+        img[rng.integers(0, wI * hI, max(wI * hI // 200, 1))] = np.nan
+        images[i] = img.astype(np.float32)
+    return dict(images=images, p2x=p2x, p2y=p2y, true_vignette=vig.astype(np.float32), true_plane=plane.astype(np.float32))

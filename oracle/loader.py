@@ -223,6 +223,9 @@ class PortOracle:
         L.oport_rescale.argtypes = [C.c_int, _f64p, _f64p]
         L.oport_rescale.restype = C.c_double
         L.oport_leak_padding.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int]
+        L.oport_vc_plane_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_double, _f32p, _f32p, _f64p]
+        L.oport_vc_vignette_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_double, _f32p, _f32p, _f64p]
+        L.oport_vc_smooth.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p]
         L.oport_time_frames.restype = C.c_double
         L.oport_time_frames.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _u8p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -366,6 +369,30 @@ class PortOracle:
         tmp = np.zeros_like(img)
         self.lib.oport_leak_padding(_p(img, _u8p), _p(tmp, _u8p), w, h, iters)
         return img
+
+    # ---- vignetteCalib optimiser (main_vignetteCalib.cpp:395-585)
+    def vc_plane_step(self, images, p2x, p2y, wI, hI, vignette, plane_color, oth2):
+        """Returns (new plane colour, FF, FC, (E, R)); images [n, wI*hI], p2x/p2y [n, gw*gh] float32."""
+        n, gwgh = p2x.shape
+        pc = np.ascontiguousarray(plane_color, np.float32).copy()
+        ff, fc, st = np.zeros(gwgh, np.float32), np.zeros(gwgh, np.float32), np.zeros(2, np.float64)
+        self.lib.oport_vc_plane_step(_p(images, _f32p), _p(p2x, _f32p), _p(p2y, _f32p), n, gwgh, wI, hI, _p(vignette, _f32p), _p(pc, _f32p),
+                                     float(oth2), _p(ff, _f32p), _p(fc, _f32p), _p(st, _f64p))
+        return pc, ff, fc, st
+
+    def vc_vignette_step(self, images, p2x, p2y, wI, hI, plane_color, vignette, oth2):
+        """Returns (new normalised vignette, TT, CT, (E, R))."""
+        n, gwgh = p2x.shape
+        v = np.ascontiguousarray(vignette, np.float32).copy()
+        tt, ct, st = np.zeros(wI * hI, np.float32), np.zeros(wI * hI, np.float32), np.zeros(2, np.float64)
+        self.lib.oport_vc_vignette_step(_p(images, _f32p), _p(p2x, _f32p), _p(p2y, _f32p), n, gwgh, wI, hI, _p(plane_color, _f32p), _p(v, _f32p),
+                                        float(oth2), _p(tt, _f32p), _p(ct, _f32p), _p(st, _f64p))
+        return v, tt, ct, st
+
+    def vc_smooth(self, vignette, wI, hI, iters=4):
+        out, tmp = np.zeros(wI * hI, np.float32), np.zeros(wI * hI, np.float32)
+        self.lib.oport_vc_smooth(_p(np.ascontiguousarray(vignette, np.float32), _f32p), wI, hI, iters, _p(out, _f32p), _p(tmp, _f32p))
+        return out
 
     def time_frames(self, rx, ry, in_w, in_h, out_w, out_h, ginv, vinv, frames, n_frames, threads, flags=3, levels=1):
         frames = np.ascontiguousarray(frames, np.uint8)

@@ -360,6 +360,127 @@ void oport_leak_padding(unsigned char* img, unsigned char* tmp, int w, int h, in
     }
 }
 
+/* ------------------------------------------------- vignetteCalib optimiser
+ *
+ * Restatement of the alternating optimisation of main_vignetteCalib.cpp:395-585 (inline in main(), no compilable unit; the
+ * front end — aruco detection, homography, image loading — is not part of it).  Inputs as the reference holds them at :395:
+ *   images [n][wI*hI] float (NaN = invalidated pixel), p2x/p2y [n][gw*gh] float plane-to-image maps (NaN = not visible; the
+ *   reference guarantees 1 < x+0.5 < wI-2 for finite entries, :352-356, so all four bilinear taps are in bounds),
+ *   plane_color [gw*gh], vignette [wI*hI].
+ * One deviation: the reference reads plane_color UNINITIALISED in its first plane step (new float[] at :381, first use :425);
+ * here the caller supplies the starting values. */
+
+/* getInterpolatedElement, main_vignetteCalib.cpp:52-70 */
+static float oport_vc_interp(const float* mat, float x, float y, int width) {
+    int ix = (int)x, iy = (int)y;
+    float dx = x - ix, dy = y - iy, dxdy = dx * dy;
+    const float* bp = mat + ix + iy * width;
+    return dxdy * bp[1 + width] + (dy - dxdy) * bp[width] + (dx - dxdy) * bp[1] + (1 - dx - dy + dxdy) * bp[0];
+}
+
+/* "optimize planeColor", :400-446.  stats[0] = E, stats[1] = R.  ff/fc: gw*gh floats scratch (planeColorFF/FC). */
+void oport_vc_plane_step(const float* images, const float* p2x, const float* p2y, int n, int gwgh, int wI, int hI,
+                         const float* vignette, float* plane_color, double oth2, float* ff, float* fc, double stats[2]) {
+    double E = 0, R = 0;
+    size_t npx = (size_t)wI * hI;
+    memset(ff, 0, (size_t)gwgh * sizeof(float));
+    memset(fc, 0, (size_t)gwgh * sizeof(float));
+    for (int img = 0; img < n; img++) {
+        const float* mx = p2x + (size_t)img * gwgh;
+        const float* my = p2y + (size_t)img * gwgh;
+        const float* image = images + (size_t)img * npx;
+        for (int pi = 0; pi < gwgh; pi++) {
+            if (isnan(mx[pi])) continue;
+            float color = oport_vc_interp(image, mx[pi], my[pi], wI);
+            float fac = oport_vc_interp(vignette, mx[pi], my[pi], wI);
+            if (isnan(fac)) continue;
+            if (isnan(color)) continue;
+            double residual = (double)((color - plane_color[pi] * fac) * (color - plane_color[pi] * fac));
+            if (fabs(residual) > oth2) { E += oth2; R++; continue; }
+            ff[pi] += fac * fac;
+            fc[pi] += color * fac;
+            if (isnan(plane_color[pi])) continue;
+            E += residual;
+            R++;
+        }
+    }
+    for (int pi = 0; pi < gwgh; pi++) plane_color[pi] = (ff[pi] < 1) ? NAN : fc[pi] / ff[pi];
+    stats[0] = E; stats[1] = R;
+}
+
+/* "optimize vignette", :458-533 incl. the normalisation to max factor 1.  tt/ct: wI*hI floats scratch (vignetteFactorTT/CT). */
+void oport_vc_vignette_step(const float* images, const float* p2x, const float* p2y, int n, int gwgh, int wI, int hI,
+                            const float* plane_color, float* vignette, double oth2, float* tt, float* ct, double stats[2]) {
+    double E = 0, R = 0;
+    size_t npx = (size_t)wI * hI;
+    memset(tt, 0, npx * sizeof(float));
+    memset(ct, 0, npx * sizeof(float));
+    for (int img = 0; img < n; img++) {
+        const float* mx = p2x + (size_t)img * gwgh;
+        const float* my = p2y + (size_t)img * gwgh;
+        const float* image = images + (size_t)img * npx;
+        for (int pi = 0; pi < gwgh; pi++) {
+            if (isnan(mx[pi])) continue;
+            float x = mx[pi], y = my[pi];
+            float colorImage = oport_vc_interp(image, x, y, wI);
+            float fac = oport_vc_interp(vignette, x, y, wI);
+            float colorPlane = plane_color[pi];
+            if (isnan(colorPlane)) continue;
+            if (isnan(colorImage)) continue;
+            double residual = (double)((colorImage - colorPlane * fac) * (colorImage - colorPlane * fac));
+            if (fabs(residual) > oth2) { E += oth2; R++; continue; }
+            int ix = (int)x, iy = (int)y;
+            float dx = x - ix, dy = y - iy, dxdy = dx * dy;
+            size_t b = (size_t)ix + (size_t)iy * wI;
+            tt[b] += (1 - dx - dy + dxdy) * colorPlane * colorPlane;
+            tt[b + 1] += (dx - dxdy) * colorPlane * colorPlane;
+            tt[b + wI] += (dy - dxdy) * colorPlane * colorPlane;
+            tt[b + 1 + wI] += dxdy * colorPlane * colorPlane;
+            ct[b] += (1 - dx - dy + dxdy) * colorImage * colorPlane;
+            ct[b + 1] += (dx - dxdy) * colorImage * colorPlane;
+            ct[b + wI] += (dy - dxdy) * colorImage * colorPlane;
+            ct[b + 1 + wI] += dxdy * colorImage * colorPlane;
+            if (isnan(fac)) continue;
+            E += residual;
+            R++;
+        }
+    }
+    float maxFac = 0;
+    for (size_t i = 0; i < npx; i++) {
+        if (tt[i] < 1) vignette[i] = NAN;
+        else {
+            vignette[i] = ct[i] / tt[i];
+            if (vignette[i] > maxFac) maxFac = vignette[i];
+        }
+    }
+    for (size_t i = 0; i < npx; i++) vignette[i] /= maxFac;
+    stats[0] = E; stats[1] = R;
+}
+
+/* "dilate & smoothe vignette", :542-566: `iters` rounds of a NaN-aware 3x3 mean.  out and tmp: wI*hI floats. */
+void oport_vc_smooth(const float* vignette, int wI, int hI, int iters, float* out, float* tmp) {
+    size_t npx = (size_t)wI * hI;
+    memcpy(out, vignette, npx * sizeof(float));
+    for (int it = 0; it < iters; it++) {
+        memcpy(tmp, out, npx * sizeof(float));
+        for (int y = 0; y < hI; y++)
+            for (int x = 0; x < wI; x++) {
+                int idx = x + y * wI;
+                float sum = 0, num = 0;
+                if (x < wI - 1 && y < hI - 1 && !isnan(tmp[idx + 1 + wI])) { sum += tmp[idx + 1 + wI]; num++; }
+                if (x < wI - 1 && !isnan(tmp[idx + 1])) { sum += tmp[idx + 1]; num++; }
+                if (x < wI - 1 && y > 0 && !isnan(tmp[idx + 1 - wI])) { sum += tmp[idx + 1 - wI]; num++; }
+                if (y < hI - 1 && !isnan(tmp[idx + wI])) { sum += tmp[idx + wI]; num++; }
+                if (!isnan(tmp[idx])) { sum += tmp[idx]; num++; }
+                if (y > 0 && !isnan(tmp[idx - wI])) { sum += tmp[idx - wI]; num++; }
+                if (y < hI - 1 && x > 0 && !isnan(tmp[idx - 1 + wI])) { sum += tmp[idx - 1 + wI]; num++; }
+                if (x > 0 && !isnan(tmp[idx - 1])) { sum += tmp[idx - 1]; num++; }
+                if (y > 0 && x > 0 && !isnan(tmp[idx - 1 - wI])) { sum += tmp[idx - 1 - wI]; num++; }
+                if (num > 0) out[idx] = sum / num;
+            }
+    }
+}
+
 /* ------------------------------------------------- CPU timing loops (bench only) */
 
 static double now_s(void) {
