@@ -1,5 +1,6 @@
 #!/bin/bash
-# compute-sanitizer passes over a small K1 workload (both loaders, pyramid on) + E-step: memcheck, racecheck, synccheck.
+# compute-sanitizer passes over a small K1 workload (both loaders, pyramid on), the responseCalib streaming kernels (E-step, G-step,
+# rmse: bulk-copy ring and generic loaders), device distortCoordinates and the vignetteCalib kernels: memcheck, racecheck, synccheck.
 set -u
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
@@ -17,9 +18,22 @@ for tma in (1, 0):
         out = prep.prepare_device(fr, True, True, True, True, levels=lv)
 torch.cuda.synchronize()
 ctx = api.Context(None, None, 0)
-data = torch.randint(0, 256, (9, 4096), dtype=torch.uint8, device="cuda")
-E = torch.zeros(4096, dtype=torch.float64, device="cuda")
-ctx.estep(data, torch.linspace(0.1, 2, 9, dtype=torch.float64, device="cuda"), torch.linspace(0, 255, 256, dtype=torch.float64, device="cuda"), E)
+for n, npix in ((21, 1536 * 3 + 48), (9, 1001)):          # bulk-copy ring (3 full tiles + a partial one), generic loader
+    data = torch.randint(0, 256, (n, npix), dtype=torch.uint8, device="cuda")
+    t = torch.linspace(0.1, 2, n, dtype=torch.float64, device="cuda")
+    G = torch.linspace(0, 255, 256, dtype=torch.float64, device="cuda")
+    E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+    ctx.estep(data, t, G, E)
+    G2 = torch.zeros_like(G)
+    ctx.rc_gstep(data, t, E, G2)
+    ctx.rc_rmse(data, t, G, E)
+    ctx.response_calib(data, t, 2, E, G2)
+x = torch.rand(5000, device="cuda") * 300; y = torch.rand(5000, device="cuda") * 200
+fov.distortCoordinatesDevice(x, y)
+pr = S.vignette_calib_problem(5, 48, 40, 64, 56, seed=1)
+d = {k: torch.from_numpy(pr[k]).cuda() for k in ("images", "p2x", "p2y")}
+pc, v = torch.zeros(48 * 40, device="cuda"), torch.ones(64 * 56, device="cuda")
+ctx.vignette_calib(d["images"], d["p2x"], d["p2y"], 48, 40, 64, 56, 2, 15, pc, v)
 torch.cuda.synchronize()
 print("done")
 PY
