@@ -65,7 +65,21 @@ Mat imread(const std::string& path, int flags) {
     return Mat();
 }
 Mat imdecode(const Mat&, int) { return Mat(); }
-bool imwrite(const std::string&, const Mat&) { return true; }
+// No encoder here.  With MDC_SHIM_DUMP_DIR set, the pixels are dumped raw instead (int32 rows, cols, type; then the data) under the
+// file's base name, so that a test can look at what a reference program wanted to save.
+bool imwrite(const std::string& path, const Mat& m) {
+    const char* dir = getenv("MDC_SHIM_DUMP_DIR");
+    if (!dir || !m.data) return true;
+    const size_t slash = path.find_last_of('/');
+    const std::string out = std::string(dir) + "/" + (slash == std::string::npos ? path : path.substr(slash + 1)) + ".raw";
+    FILE* f = fopen(out.c_str(), "wb");
+    if (!f) return false;
+    const int head[3] = {m.rows, m.cols, m.type()};
+    fwrite(head, sizeof head, 1, f);
+    fwrite(m.data, (size_t)m.rows * m.cols * shim_elem_size(m.type()), 1, f);
+    fclose(f);
+    return true;
+}
 void imshow(const std::string&, const Mat&) {}
 int waitKey(int) { return ' '; }
 }  // namespace cv
