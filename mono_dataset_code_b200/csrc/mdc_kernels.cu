@@ -1189,14 +1189,24 @@ __global__ void __launch_bounds__(256) rc_gstep_accum_kernel(const uint8_t* __re
     atomicAdd(&gnum[threadIdx.x], s_num[threadIdx.x]);
 }
 
-// G[i] = GSum[i]/GNum[i]; non-finite entries (empty bins) with i > 1 are extrapolated linearly, :300-304.  One thread: sequential.
-__global__ void rc_gstep_finish_kernel(const double* __restrict__ gsum, const unsigned long long* __restrict__ gnum, double* __restrict__ G) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int i = 0; i < 256; ++i) {
-        double g = __ddiv_rn(gsum[i], static_cast<double>(gnum[i]));
-        if (!isfinite(g) && i > 1) g = __dadd_rn(G[i - 1], __dsub_rn(G[i - 1], G[i - 2]));
-        G[i] = g;
-    }
+// G[i] = GSum[i]/GNum[i]; non-finite entries (empty bins) with i > 1 are extrapolated linearly from the two entries below, :300-304.
+// The divisions run in parallel (one thread per bin, launch with 256 threads); the extrapolation is sequential in i like the
+// reference's loop (an extrapolated entry feeds the next one) and is done by one thread in shared memory.
+__global__ void __launch_bounds__(256) rc_gstep_finish_kernel(const double* __restrict__ gsum, const unsigned long long* __restrict__ gnum, double* __restrict__ G) {
+    __shared__ double g[256];
+    __shared__ int any_gap;
+    const int i = threadIdx.x;
+    if (i == 0) any_gap = 0;
+    __syncthreads();
+    const double v = __ddiv_rn(gsum[i], static_cast<double>(gnum[i]));
+    g[i] = v;
+    if (!isfinite(v) && i > 1) any_gap = 1;
+    __syncthreads();
+    if (i == 0 && any_gap)
+        for (int k = 2; k < 256; ++k)
+            if (!isfinite(g[k])) g[k] = __dadd_rn(g[k - 1], __dsub_rn(g[k - 1], g[k - 2]));
+    __syncthreads();
+    G[i] = g[i];
 }
 
 // Rescale so that G[255] = 255, :350-355.  `factor` is 255.0 / G[255] evaluated BEFORE G is touched.
@@ -1267,7 +1277,7 @@ cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* 
     } else {
         rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
     }
-    rc_gstep_finish_kernel<<<1, 32, 0, s>>>(gsum, gnum, G);
+    rc_gstep_finish_kernel<<<1, 256, 0, s>>>(gsum, gnum, G);
     return cudaGetLastError();
 }
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s) {

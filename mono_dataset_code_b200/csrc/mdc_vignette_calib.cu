@@ -91,28 +91,35 @@ __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__
     for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < gwgh; pi += stride) {
         const float pc = plane_color[pi];
         float ff = 0.0f, fc = 0.0f;
-        for (int img0 = 0; img0 < n; img0 += kVcBatch) {
-            float color[kVcBatch], fac[kVcBatch];
-            bool seen[kVcBatch];
+        // software pipeline: the maps of the NEXT batch of images are requested before the taps of the current batch are gathered,
+        // so a batch costs one memory round trip instead of two dependent ones
+        float mx[kVcBatch], my[kVcBatch];
+        auto fetch_maps = [&](int img0, float (&x)[kVcBatch], float (&y)[kVcBatch]) {
 #pragma unroll
             for (int j = 0; j < kVcBatch; ++j) {
                 const int img = img0 + j;
-                seen[j] = false;
+                const bool in = img < n;
+                x[j] = in ? __ldg(p2x + static_cast<size_t>(img) * gwgh + pi) : __int_as_float(0x7fc00000);
+                y[j] = in ? __ldg(p2y + static_cast<size_t>(img) * gwgh + pi) : 0.0f;
+            }
+        };
+        fetch_maps(0, mx, my);
+        for (int img0 = 0; img0 < n; img0 += kVcBatch) {
+            float nx[kVcBatch], ny[kVcBatch];
+            fetch_maps(img0 + kVcBatch, nx, ny);
+            float color[kVcBatch], fac[kVcBatch];
+#pragma unroll
+            for (int j = 0; j < kVcBatch; ++j) {
                 color[j] = fac[j] = 0.0f;
-                if (img < n) {
-                    const float x = __ldg(p2x + static_cast<size_t>(img) * gwgh + pi);
-                    if (!isnan(x)) {                                                       // :414
-                        const float y = __ldg(p2y + static_cast<size_t>(img) * gwgh + pi);
-                        const Taps t = vc_taps(x, y, wI);
-                        color[j] = vc_blend(images + static_cast<size_t>(img) * npx, t, wI);
-                        fac[j] = vc_blend(vignette, t, wI);
-                        seen[j] = true;
-                    }
+                if (!isnan(mx[j])) {                                                       // :414
+                    const Taps t = vc_taps(mx[j], my[j], wI);
+                    color[j] = vc_blend(images + static_cast<size_t>(img0 + j) * npx, t, wI);
+                    fac[j] = vc_blend(vignette, t, wI);
                 }
             }
 #pragma unroll
             for (int j = 0; j < kVcBatch; ++j) {
-                if (!seen[j] || isnan(fac[j]) || isnan(color[j])) continue;               // :420-421
+                if (isnan(mx[j]) || isnan(fac[j]) || isnan(color[j])) continue;            // :414, :420-421
                 const float d = __fsub_rn(color[j], __fmul_rn(pc, fac[j]));
                 const double residual = static_cast<double>(__fmul_rn(d, d));
                 if (fabs(residual) > oth2) { e_sum += oth2; r_cnt += 1.0; continue; }      // :424-429
@@ -122,6 +129,8 @@ __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__
                 e_sum += residual;
                 r_cnt += 1.0;
             }
+#pragma unroll
+            for (int j = 0; j < kVcBatch; ++j) { mx[j] = nx[j]; my[j] = ny[j]; }
         }
         plane_color[pi] = (ff < 1.0f) ? __int_as_float(0x7fc00000) : __fdiv_rn(fc, ff);    // :441-445
     }
