@@ -151,3 +151,32 @@ def test_invalid_photo_files(tmp_path, dataset_dir, capfd):
     rgb = str(tmp_path / "rgb.png")
     cv2.imwrite(rgb, np.zeros((480, 640, 3), np.uint8))
     assert not api.PhotometricUndistorter(files["pcalib"], rgb, 640, 480).validVignette
+
+
+def test_argument_validation_of_the_device_entry_points_needs_no_gpu(dataset_dir, capfd):
+    """Bad arguments are rejected before any CUDA call, with the C ABI's status codes (include/mdc_b200.h:28-35)."""
+    import ctypes as C
+    from mono_dataset_code_b200 import _lib
+    L = _lib.lib
+    null = C.c_void_p()
+    st = (C.c_double * 2)()
+    # no context
+    assert L.mdc_vc_plane_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, st) == 1
+    assert L.mdc_vc_vignette_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, st) == 1
+    assert L.mdc_vc_smooth(null, null, 8, 8, 4, null) == 1
+    assert L.mdc_vignette_calib(null, null, null, null, 1, 4, 4, 8, 8, 2, 15, null, null, null, None) == 1
+    assert b"bad argument" in L.mdc_last_error()
+    assert L.mdc_estep(null, null, 1, 16, null, null, null, null) == 1
+    assert L.mdc_rc_gstep(null, null, 1, 16, null, null, null, null) == 1
+    # distortCoordinates on the device: NULL model / NULL arrays are argument errors, an invalid model prints like the reference
+    assert L.mdc_fov_distort_coordinates_device(null, null, null, 0, 0, null) == 1
+    files = dataset_dir("c1_crop_640")
+    u = api.UndistorterFOV(files["camera"])
+    assert L.mdc_fov_distort_coordinates_device(u._h, null, null, 5, 0, null) == 1
+    bad = C.c_void_p()
+    L.mdc_fov_create(b"/nonexistent/camera.txt", C.byref(bad))
+    capfd.readouterr()
+    assert L.mdc_fov_distort_coordinates_device(bad, C.c_void_p(16), C.c_void_p(16), 5, 0, null) == 4       # MDC_ERR_INVALID_OBJECT
+    assert "ERROR: invalid UndistorterFOV!" in capfd.readouterr().out
+    L.mdc_fov_destroy(bad)
+    assert L.mdc_atanf_device(null, null, 3, 0, null) == 1
