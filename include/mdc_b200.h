@@ -174,22 +174,26 @@ int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_
  *   d_plane_color [gw*gh], d_vignette [wI*hI].  The aruco / homography front end stays with the caller; the maps are
  *   distortCoordinates of the projected grid (mdc_fov_distort_coordinates_device).
  * Unlike the reference, which reads planeColor uninitialised in its first pass (:381, :425), the caller provides it.
+ * integer_abs: the reference's outlier test is `abs(residual) > oth2` on a double (:423, :481).  1 = the residual is truncated to
+ *   int first, which is what that line does when only `int abs(int)` is visible to unqualified lookup (libstdc++ before GCC 6,
+ *   i.e. the reference's era; also how the unmodified program builds against this repo's oracle headers); 0 = fabs(residual).
  * ===================================================================================== */
 /* "optimize planeColor" (:400-446): d_plane_color is read (residual test) and overwritten with sum(color*fac)/sum(fac*fac),
  * NaN where sum(fac*fac) < 1.  Bit-identical to the reference.  stats_host = {E, R} (E: fp64 sum, order-dependent). */
 int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                      const float* d_vignette, float* d_plane_color, double outlier_th2, double stats_host[2]);
+                      const float* d_vignette, float* d_plane_color, double outlier_th2, int integer_abs, double stats_host[2]);
 /* "optimize vignette" (:458-523) including the normalisation to maximum factor 1: d_vignette is read and overwritten.
  * The bilinear scatter-add runs on fp32 atomics, so sums match the reference's sequential ones to rounding only. */
 int mdc_vc_vignette_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                         const float* d_plane_color, float* d_vignette, double outlier_th2, double stats_host[2]);
+                         const float* d_plane_color, float* d_vignette, double outlier_th2, int integer_abs, double stats_host[2]);
 /* "dilate & smoothe" (:542-566): `iterations` rounds (the reference: 4) of the NaN-aware 3x3 mean.  Bit-identical. */
 int mdc_vc_smooth(mdc_ctx* c, const float* d_vignette, int wI, int hI, int iterations, float* d_out);
 /* The loop itself: max_iterations x {plane step, vignette step}, outlier threshold outlier_th^2 in the second half of the
  * iterations and 10000^2 before (:397-398); d_smoothed (may be NULL) receives the 4x smoothed result of the last iteration.
  * log_host (may be NULL): [max_iterations][4] = {E, R} of the plane step, {E, R} of the vignette step. */
 int mdc_vignette_calib(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                       int max_iterations, int outlier_th, float* d_plane_color, float* d_vignette, float* d_smoothed, double* log_host);
+                       int max_iterations, int outlier_th, int integer_abs, float* d_plane_color, float* d_vignette, float* d_smoothed,
+                       double* log_host);
 
 /* responseCalib E-step, main_responseCalib.cpp:317-346 (kernel K3):
  *   d_data [n][npix] u8 image-major, d_t [n] f64 exposure times, d_G [256] f64 -> d_E [npix] f64.

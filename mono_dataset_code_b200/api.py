@@ -331,24 +331,24 @@ class Context:
             assert t_.is_cuda and t_.dtype == torch.float32 and t_.is_contiguous() and tuple(t_.shape) == (n, cols)
         return n
 
-    def vc_plane_step(self, images, p2x, p2y, gw, gh, wI, hI, vignette, plane_color, oth2):
+    def vc_plane_step(self, images, p2x, p2y, gw, gh, wI, hI, vignette, plane_color, oth2, integer_abs=True):
         """plane_color is updated in place; returns (E, R)."""
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
         torch.cuda.current_stream(images.device).synchronize()
         st = (C.c_double * 2)()
         check(lib.mdc_vc_plane_step(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,
-                                    C.c_void_p(vignette.data_ptr()), C.c_void_p(plane_color.data_ptr()), float(oth2), st), "mdc_vc_plane_step")
+                                    C.c_void_p(vignette.data_ptr()), C.c_void_p(plane_color.data_ptr()), float(oth2), int(integer_abs), st), "mdc_vc_plane_step")
         return st[0], st[1]
 
-    def vc_vignette_step(self, images, p2x, p2y, gw, gh, wI, hI, plane_color, vignette, oth2):
+    def vc_vignette_step(self, images, p2x, p2y, gw, gh, wI, hI, plane_color, vignette, oth2, integer_abs=True):
         """vignette is updated in place (normalised to maximum 1); returns (E, R)."""
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
         torch.cuda.current_stream(images.device).synchronize()
         st = (C.c_double * 2)()
         check(lib.mdc_vc_vignette_step(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,
-                                       C.c_void_p(plane_color.data_ptr()), C.c_void_p(vignette.data_ptr()), float(oth2), st), "mdc_vc_vignette_step")
+                                       C.c_void_p(plane_color.data_ptr()), C.c_void_p(vignette.data_ptr()), float(oth2), int(integer_abs), st), "mdc_vc_vignette_step")
         return st[0], st[1]
 
     def vc_smooth(self, vignette, wI, hI, iterations=4):
@@ -358,7 +358,7 @@ class Context:
         check(lib.mdc_vc_smooth(self._h, C.c_void_p(vignette.data_ptr()), wI, hI, iterations, C.c_void_p(out.data_ptr())), "mdc_vc_smooth")
         return out
 
-    def vignette_calib(self, images, p2x, p2y, gw, gh, wI, hI, max_iterations, outlier_th, plane_color, vignette):
+    def vignette_calib(self, images, p2x, p2y, gw, gh, wI, hI, max_iterations, outlier_th, plane_color, vignette, integer_abs=True):
         """The reference's optimisation loop; plane_color / vignette updated in place.  Returns (smoothed vignette, log [its, 4])."""
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
@@ -366,7 +366,7 @@ class Context:
         smoothed = torch.empty_like(vignette)
         log = np.zeros((max(max_iterations, 1), 4), np.float64)
         check(lib.mdc_vignette_calib(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,
-                                     max_iterations, outlier_th, C.c_void_p(plane_color.data_ptr()), C.c_void_p(vignette.data_ptr()),
+                                     max_iterations, outlier_th, int(integer_abs), C.c_void_p(plane_color.data_ptr()), C.c_void_p(vignette.data_ptr()),
                                      C.c_void_p(smoothed.data_ptr()), log.ctypes.data_as(C.POINTER(C.c_double))), "mdc_vignette_calib")
         return smoothed, log[:max_iterations]
 

@@ -79,13 +79,22 @@ __device__ __forceinline__ void vc_flush_stats(double e, double r, double* __res
     }
 }
 
+// The reference's outlier test `abs(residual) > oth2` (:423, :481) on a double residual: with only `int abs(int)` visible to
+// unqualified lookup (libstdc++ before GCC 6 - the reference's era - and the oracle build) the residual is truncated to int first;
+// with <cmath>'s overloads in the global namespace it is fabs.  integer_abs != 0 reproduces the former: residuals are squares
+// (>= 0) or NaN, and an out-of-range / NaN conversion yields INT_MIN on x86, which is never an outlier.
+__device__ __forceinline__ bool vc_outlier(double residual, double oth2, int integer_abs) {
+    if (!integer_abs) return fabs(residual) > oth2;
+    return residual < 2147483648.0 && static_cast<double>(__double2int_rz(residual)) > oth2;
+}
+
 constexpr int kVcBatch = 4;      // images whose maps and taps are fetched together (memory-level parallelism)
 
 // ---- plane step: for each plane point the optimum is sum(color*fac) / sum(fac*fac) over the images that see it
 __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__ images, const float* __restrict__ p2x,
                                                        const float* __restrict__ p2y, int n, int gwgh, int wI, size_t npx,
                                                        const float* __restrict__ vignette, float* __restrict__ plane_color,
-                                                       double oth2, double* __restrict__ stats) {
+                                                       double oth2, int integer_abs, double* __restrict__ stats) {
     double e_sum = 0.0, r_cnt = 0.0;
     const int stride = gridDim.x * blockDim.x;
     for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < gwgh; pi += stride) {
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__
                 if (isnan(mx[j]) || isnan(fac[j]) || isnan(color[j])) continue;            // :414, :420-421
                 const float d = __fsub_rn(color[j], __fmul_rn(pc, fac[j]));
                 const double residual = static_cast<double>(__fmul_rn(d, d));
-                if (fabs(residual) > oth2) { e_sum += oth2; r_cnt += 1.0; continue; }      // :424-429
+                if (vc_outlier(residual, oth2, integer_abs)) { e_sum += oth2; r_cnt += 1.0; continue; }      // :424-429
                 ff = __fadd_rn(ff, __fmul_rn(fac[j], fac[j]));
                 fc = __fadd_rn(fc, __fmul_rn(color[j], fac[j]));
                 if (isnan(pc)) continue;
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) vc_vignette_kernel(const float* __restrict__ images, const float* __restrict__ p2x,
                                                           const float* __restrict__ p2y, size_t total, int gwgh, int wI, size_t npx,
                                                           const float* __restrict__ plane_color, const float* __restrict__ vignette,
-                                                          float* __restrict__ tt, float* __restrict__ ct, double oth2,
+                                                          float* __restrict__ tt, float* __restrict__ ct, double oth2, int integer_abs,
                                                           double* __restrict__ stats) {
     double e_sum = 0.0, r_cnt = 0.0;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256) vc_vignette_kernel(const float* __restric
         const float fac = vc_blend(vignette, t, wI);
         const float d = __fsub_rn(cI, __fmul_rn(cP, fac));
         const double residual = static_cast<double>(__fmul_rn(d, d));
-        if (fabs(residual) > oth2) { e_sum += oth2; r_cnt += 1.0; continue; }              // :481-486
+        if (vc_outlier(residual, oth2, integer_abs)) { e_sum += oth2; r_cnt += 1.0; continue; }              // :481-486
         float* a = tt + t.base;
         float* b = ct + t.base;
         atomicAdd(a, __fmul_rn(__fmul_rn(t.w00, cP), cP));
@@ -261,21 +270,21 @@ int alloc_scratch(Scratch* s, size_t acc_elems) {
     return MDC_OK;
 }
 
-int plane_step(mdc_ctx* c, const Problem& p, const float* d_vignette, float* d_plane_color, double oth2, double* d_stats, cudaStream_t s) {
+int plane_step(mdc_ctx* c, const Problem& p, const float* d_vignette, float* d_plane_color, double oth2, int integer_abs, double* d_stats, cudaStream_t s) {
     VC_CHECK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(double), s));
     vc_plane_kernel<<<vc_blocks(static_cast<size_t>(p.gwgh)), 256, 0, s>>>(p.images, p.p2x, p.p2y, p.n, p.gwgh, p.wI, static_cast<size_t>(p.wI) * p.hI,
-                                                                           d_vignette, d_plane_color, oth2, d_stats);
+                                                                           d_vignette, d_plane_color, oth2, integer_abs, d_stats);
     VC_CHECK(cudaGetLastError());
     mdc_ctx_add_launches(c, 1);
     return MDC_OK;
 }
 
-int vignette_step(mdc_ctx* c, const Problem& p, const float* d_plane_color, float* d_vignette, double oth2, const Scratch& sc, cudaStream_t s) {
+int vignette_step(mdc_ctx* c, const Problem& p, const float* d_plane_color, float* d_vignette, double oth2, int integer_abs, const Scratch& sc, cudaStream_t s) {
     const size_t npx = static_cast<size_t>(p.wI) * p.hI, total = static_cast<size_t>(p.n) * p.gwgh;
     VC_CHECK(cudaMemsetAsync(sc.base, 0, 64 + 2 * npx * sizeof(float), s));
     if (total) {
         vc_vignette_kernel<<<vc_blocks(total), 256, 0, s>>>(p.images, p.p2x, p.p2y, total, p.gwgh, p.wI, npx, d_plane_color, d_vignette, sc.acc0,
-                                                            sc.acc1, oth2, sc.stats);
+                                                            sc.acc1, oth2, integer_abs, sc.stats);
         VC_CHECK(cudaGetLastError());
     }
     vc_divide_kernel<<<vc_blocks(npx), 256, 0, s>>>(sc.acc0, sc.acc1, npx, d_vignette, sc.max_bits);
@@ -300,7 +309,7 @@ int smooth(mdc_ctx* c, const float* d_vignette, int wI, int hI, int iterations, 
 }  // namespace
 
 extern "C" int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                                 const float* d_vignette, float* d_plane_color, double outlier_th2, double stats_host[2]) {
+                                 const float* d_vignette, float* d_plane_color, double outlier_th2, int integer_abs, double stats_host[2]) {
     const Problem p{d_images, d_p2x, d_p2y, n, gw * gh, wI, hI};
     int rc = check_problem("mdc_vc_plane_step", c, p, d_vignette, d_plane_color);
     if (rc != MDC_OK) return rc;
@@ -308,7 +317,7 @@ extern "C" int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float*
     cudaStream_t s = static_cast<cudaStream_t>(mdc_ctx_stream_handle(c));
     double* d_stats = nullptr;
     VC_CHECK(cudaMalloc(&d_stats, 2 * sizeof(double)));
-    rc = plane_step(c, p, d_vignette, d_plane_color, outlier_th2, d_stats, s);
+    rc = plane_step(c, p, d_vignette, d_plane_color, outlier_th2, integer_abs, d_stats, s);
     double st[2] = {0, 0};
     if (rc == MDC_OK && cudaMemcpyAsync(st, d_stats, sizeof st, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == MDC_OK) { mdc_set_error("mdc_vc_plane_step: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
@@ -318,7 +327,7 @@ extern "C" int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float*
 }
 
 extern "C" int mdc_vc_vignette_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                                    const float* d_plane_color, float* d_vignette, double outlier_th2, double stats_host[2]) {
+                                    const float* d_plane_color, float* d_vignette, double outlier_th2, int integer_abs, double stats_host[2]) {
     const Problem p{d_images, d_p2x, d_p2y, n, gw * gh, wI, hI};
     int rc = check_problem("mdc_vc_vignette_step", c, p, d_plane_color, d_vignette);
     if (rc != MDC_OK) return rc;
@@ -326,7 +335,7 @@ extern "C" int mdc_vc_vignette_step(mdc_ctx* c, const float* d_images, const flo
     cudaStream_t s = static_cast<cudaStream_t>(mdc_ctx_stream_handle(c));
     Scratch sc;
     if ((rc = alloc_scratch(&sc, static_cast<size_t>(wI) * hI)) != MDC_OK) return rc;
-    rc = vignette_step(c, p, d_plane_color, d_vignette, outlier_th2, sc, s);
+    rc = vignette_step(c, p, d_plane_color, d_vignette, outlier_th2, integer_abs, sc, s);
     double st[2] = {0, 0};
     if (rc == MDC_OK && cudaMemcpyAsync(st, sc.stats, sizeof st, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == MDC_OK) { mdc_set_error("mdc_vc_vignette_step: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
@@ -350,7 +359,7 @@ extern "C" int mdc_vc_smooth(mdc_ctx* c, const float* d_vignette, int wI, int hI
 // The reference's loop (:395-585): per iteration plane step, vignette step (+ normalisation), smoothed copy for output.
 // log_host, if given, receives [max_iterations][4] = {E_plane, R_plane, E_vignette, R_vignette}.
 extern "C" int mdc_vignette_calib(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
-                                  int max_iterations, int outlier_th, float* d_plane_color, float* d_vignette, float* d_smoothed,
+                                  int max_iterations, int outlier_th, int integer_abs, float* d_plane_color, float* d_vignette, float* d_smoothed,
                                   double* log_host) {
     const Problem p{d_images, d_p2x, d_p2y, n, gw * gh, wI, hI};
     int rc = check_problem("mdc_vignette_calib", c, p, d_plane_color, d_vignette);
@@ -367,9 +376,9 @@ extern "C" int mdc_vignette_calib(mdc_ctx* c, const float* d_images, const float
         double oth2 = static_cast<double>(outlier_th) * outlier_th;           // :397-398 (int arithmetic in the reference)
         if (it < max_iterations / 2) oth2 = 10000.0 * 10000.0;
         double ps[2] = {0, 0}, vs[2] = {0, 0};
-        rc = plane_step(c, p, d_vignette, d_plane_color, oth2, d_pstats, s);
+        rc = plane_step(c, p, d_vignette, d_plane_color, oth2, integer_abs, d_pstats, s);
         if (rc == MDC_OK && cudaMemcpyAsync(ps, d_pstats, sizeof ps, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
-        if (rc == MDC_OK) rc = vignette_step(c, p, d_plane_color, d_vignette, oth2, sc, s);
+        if (rc == MDC_OK) rc = vignette_step(c, p, d_plane_color, d_vignette, oth2, integer_abs, sc, s);
         if (rc == MDC_OK && cudaMemcpyAsync(vs, sc.stats, sizeof vs, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
         if (rc == MDC_OK && cudaStreamSynchronize(s) != cudaSuccess) { mdc_set_error("mdc_vignette_calib: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
         if (rc != MDC_OK) break;

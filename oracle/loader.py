@@ -223,9 +223,12 @@ class PortOracle:
         L.oport_rescale.argtypes = [C.c_int, _f64p, _f64p]
         L.oport_rescale.restype = C.c_double
         L.oport_leak_padding.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int]
-        L.oport_vc_plane_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_double, _f32p, _f32p, _f64p]
-        L.oport_vc_vignette_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_double, _f32p, _f32p, _f64p]
+        L.oport_vc_plane_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _f64p]
+        L.oport_vc_vignette_step.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _f64p]
         L.oport_vc_smooth.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p]
+        L.oport_vc_plane_maps.argtypes = [_f64p, C.c_int, C.c_int, C.c_float, C.c_float, _f32p, _f32p]
+        L.oport_vc_mask_maps.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.oport_vc_prepare_image.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _f32p]
         L.oport_time_frames.restype = C.c_double
         L.oport_time_frames.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _u8p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -371,23 +374,37 @@ class PortOracle:
         return img
 
     # ---- vignetteCalib optimiser (main_vignetteCalib.cpp:395-585)
-    def vc_plane_step(self, images, p2x, p2y, wI, hI, vignette, plane_color, oth2):
+    def vc_plane_step(self, images, p2x, p2y, wI, hI, vignette, plane_color, oth2, int_abs=True):
         """Returns (new plane colour, FF, FC, (E, R)); images [n, wI*hI], p2x/p2y [n, gw*gh] float32."""
         n, gwgh = p2x.shape
         pc = np.ascontiguousarray(plane_color, np.float32).copy()
         ff, fc, st = np.zeros(gwgh, np.float32), np.zeros(gwgh, np.float32), np.zeros(2, np.float64)
         self.lib.oport_vc_plane_step(_p(images, _f32p), _p(p2x, _f32p), _p(p2y, _f32p), n, gwgh, wI, hI, _p(vignette, _f32p), _p(pc, _f32p),
-                                     float(oth2), _p(ff, _f32p), _p(fc, _f32p), _p(st, _f64p))
+                                     int(oth2), int(int_abs), _p(ff, _f32p), _p(fc, _f32p), _p(st, _f64p))
         return pc, ff, fc, st
 
-    def vc_vignette_step(self, images, p2x, p2y, wI, hI, plane_color, vignette, oth2):
+    def vc_vignette_step(self, images, p2x, p2y, wI, hI, plane_color, vignette, oth2, int_abs=True):
         """Returns (new normalised vignette, TT, CT, (E, R))."""
         n, gwgh = p2x.shape
         v = np.ascontiguousarray(vignette, np.float32).copy()
         tt, ct, st = np.zeros(wI * hI, np.float32), np.zeros(wI * hI, np.float32), np.zeros(2, np.float64)
         self.lib.oport_vc_vignette_step(_p(images, _f32p), _p(p2x, _f32p), _p(p2y, _f32p), n, gwgh, wI, hI, _p(plane_color, _f32p), _p(v, _f32p),
-                                        float(oth2), _p(tt, _f32p), _p(ct, _f32p), _p(st, _f64p))
+                                        int(oth2), int(int_abs), _p(tt, _f32p), _p(ct, _f32p), _p(st, _f64p))
         return v, tt, ct, st
+
+    def vc_plane_maps(self, H, gw, gh, facw=5.0, fach=5.0):
+        X, Y = np.zeros(gw * gh, np.float32), np.zeros(gw * gh, np.float32)
+        self.lib.oport_vc_plane_maps(_p(np.ascontiguousarray(H, np.float64).ravel(), _f64p), gw, gh, facw, fach, _p(X, _f32p), _p(Y, _f32p))
+        return X, Y
+
+    def vc_mask_maps(self, X, Y, wI, hI):
+        self.lib.oport_vc_mask_maps(_p(X, _f32p), _p(Y, _f32p), X.size, wI, hI)
+
+    def vc_prepare_image(self, raw, wI, hI, mean_exposure, exposure, max_abs_grad=255):
+        out = np.zeros(wI * hI, np.float32)
+        self.lib.oport_vc_prepare_image(_p(np.ascontiguousarray(raw, np.float32), _f32p), wI, hI, float(mean_exposure), float(exposure), max_abs_grad,
+                                        _p(out, _f32p))
+        return out
 
     def vc_smooth(self, vignette, wI, hI, iters=4):
         out, tmp = np.zeros(wI * hI, np.float32), np.zeros(wI * hI, np.float32)

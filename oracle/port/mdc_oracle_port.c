@@ -368,7 +368,16 @@ void oport_leak_padding(unsigned char* img, unsigned char* tmp, int w, int h, in
  *   reference guarantees 1 < x+0.5 < wI-2 for finite entries, :352-356, so all four bilinear taps are in bounds),
  *   plane_color [gw*gh], vignette [wI*hI].
  * One deviation: the reference reads plane_color UNINITIALISED in its first plane step (new float[] at :381, first use :425);
- * here the caller supplies the starting values. */
+ * here the caller supplies the starting values.
+ * Toolchain-dependent detail: the outlier test is `abs(residual) > oth2` on a double (:423, :481).  Where only `int abs(int)` is
+ * visible to unqualified lookup (libstdc++ before GCC 6; also this repo's stand-in headers) the residual is TRUNCATED TO INT
+ * first; with <cmath>'s overloads in the global namespace it is fabs.  int_abs selects the former (the author-era behaviour). */
+static int oport_vc_outlier(double residual, int oth2, int int_abs) {
+    if (!int_abs) return fabs(residual) > oth2;
+    /* abs((int)residual) > oth2: residual is a square (>= 0) or NaN; out-of-range / NaN conversions give INT_MIN on x86 */
+    if (!(residual < 2147483648.0)) return 0;
+    return (int)residual > oth2;
+}
 
 /* getInterpolatedElement, main_vignetteCalib.cpp:52-70 */
 static float oport_vc_interp(const float* mat, float x, float y, int width) {
@@ -380,7 +389,7 @@ static float oport_vc_interp(const float* mat, float x, float y, int width) {
 
 /* "optimize planeColor", :400-446.  stats[0] = E, stats[1] = R.  ff/fc: gw*gh floats scratch (planeColorFF/FC). */
 void oport_vc_plane_step(const float* images, const float* p2x, const float* p2y, int n, int gwgh, int wI, int hI,
-                         const float* vignette, float* plane_color, double oth2, float* ff, float* fc, double stats[2]) {
+                         const float* vignette, float* plane_color, int oth2, int int_abs, float* ff, float* fc, double stats[2]) {
     double E = 0, R = 0;
     size_t npx = (size_t)wI * hI;
     memset(ff, 0, (size_t)gwgh * sizeof(float));
@@ -396,7 +405,7 @@ void oport_vc_plane_step(const float* images, const float* p2x, const float* p2y
             if (isnan(fac)) continue;
             if (isnan(color)) continue;
             double residual = (double)((color - plane_color[pi] * fac) * (color - plane_color[pi] * fac));
-            if (fabs(residual) > oth2) { E += oth2; R++; continue; }
+            if (oport_vc_outlier(residual, oth2, int_abs)) { E += oth2; R++; continue; }
             ff[pi] += fac * fac;
             fc[pi] += color * fac;
             if (isnan(plane_color[pi])) continue;
@@ -410,7 +419,7 @@ void oport_vc_plane_step(const float* images, const float* p2x, const float* p2y
 
 /* "optimize vignette", :458-533 incl. the normalisation to max factor 1.  tt/ct: wI*hI floats scratch (vignetteFactorTT/CT). */
 void oport_vc_vignette_step(const float* images, const float* p2x, const float* p2y, int n, int gwgh, int wI, int hI,
-                            const float* plane_color, float* vignette, double oth2, float* tt, float* ct, double stats[2]) {
+                            const float* plane_color, float* vignette, int oth2, int int_abs, float* tt, float* ct, double stats[2]) {
     double E = 0, R = 0;
     size_t npx = (size_t)wI * hI;
     memset(tt, 0, npx * sizeof(float));
@@ -428,7 +437,7 @@ void oport_vc_vignette_step(const float* images, const float* p2x, const float* 
             if (isnan(colorPlane)) continue;
             if (isnan(colorImage)) continue;
             double residual = (double)((colorImage - colorPlane * fac) * (colorImage - colorPlane * fac));
-            if (fabs(residual) > oth2) { E += oth2; R++; continue; }
+            if (oport_vc_outlier(residual, oth2, int_abs)) { E += oth2; R++; continue; }
             int ix = (int)x, iy = (int)y;
             float dx = x - ix, dy = y - iy, dxdy = dx * dy;
             size_t b = (size_t)ix + (size_t)iy * wI;
@@ -479,6 +488,63 @@ void oport_vc_smooth(const float* vignette, int wI, int hI, int iters, float* ou
                 if (num > 0) out[idx] = sum / num;
             }
     }
+}
+
+/* ---- vignetteCalib front end between the image reader and the optimiser (main_vignetteCalib.cpp:262-358), restated so that
+ * the reference PROGRAM (oracle/_ref/vignetteCalib_ref, built against stand-in aruco/OpenCV/Eigen) can be replayed: the 3x3
+ * float arithmetic is the stand-in's (oracle/shim/Eigen/Core), not Eigen's. */
+
+/* plane grid -> undistorted image coordinates, :266-282.  H: the homography the program got from cv::findHomography (doubles,
+ * narrowed to float at :253-261).  out: gw*gh floats each; distortCoordinates (:284) is applied by the caller afterwards. */
+void oport_vc_plane_maps(const double H[9], int gw, int gh, float facw, float fach, float* X, float* Y) {
+    float K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ki[9], Hf[9], HK[9];
+    K[0] = gw / facw; K[4] = gh / fach; K[2] = gw / 2; K[5] = gh / 2; K[8] = 1;      /* :196-200 (gw/2 is an int division) */
+    {   /* inverse: adjugate / determinant, as the stand-in does it */
+        const float c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+        const float det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+        Ki[0] = c00 / det; Ki[3] = c01 / det; Ki[6] = c02 / det;
+        Ki[1] = (K[2] * K[7] - K[1] * K[8]) / det;
+        Ki[4] = (K[0] * K[8] - K[2] * K[6]) / det;
+        Ki[7] = (K[1] * K[6] - K[0] * K[7]) / det;
+        Ki[2] = (K[1] * K[5] - K[2] * K[4]) / det;
+        Ki[5] = (K[2] * K[3] - K[0] * K[5]) / det;
+        Ki[8] = (K[0] * K[4] - K[1] * K[3]) / det;
+    }
+    for (int i = 0; i < 9; i++) Hf[i] = (float)H[i];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) HK[r * 3 + c] = Hf[r * 3] * Ki[c] + Hf[r * 3 + 1] * Ki[3 + c] + Hf[r * 3 + 2] * Ki[6 + c];
+    int idx = 0;
+    for (int y = 0; y < gh; y++)
+        for (int x = 0; x < gw; x++) {
+            float v0 = (float)x, v1 = (float)y, v2 = 1.0f, pp[3];
+            for (int r = 0; r < 3; r++) pp[r] = HK[r * 3] * v0 + HK[r * 3 + 1] * v1 + HK[r * 3 + 2] * v2;
+            X[idx] = pp[0] / pp[2];
+            Y[idx] = pp[1] / pp[2];
+            idx++;
+        }
+}
+
+/* points whose rounded position is not strictly inside the image interior become NaN, :345-357 */
+void oport_vc_mask_maps(float* X, float* Y, int n, int wI, int hI) {
+    for (int i = 0; i < n; i++) {
+        int u_d = X[i] + 0.5;
+        int v_d = Y[i] + 0.5;
+        if (!(u_d > 1 && v_d > 1 && u_d < wI - 2 && v_d < hI - 2)) { X[i] = NAN; Y[i] = NAN; }
+    }
+}
+
+/* exposure normalisation and gradient-based invalidation, :288-310 (in place and order-dependent, like the reference) */
+void oport_vc_prepare_image(const float* raw, int wI, int hI, float meanExposure, float exposure, int maxAbsGrad, float* image) {
+    for (int y = 0; y < hI; y++)
+        for (int x = 0; x < wI; x++) image[x + y * wI] = meanExposure * raw[x + y * wI] / exposure;
+    for (int y = 2; y < hI - 2; y++)
+        for (int x = 2; x < wI - 2; x++)
+            for (int deltax = -2; deltax < 3; deltax++)
+                for (int deltay = -2; deltay < 3; deltay++)
+                    if (fabsf(image[x + y * wI] - image[x + deltax + (y + deltay) * wI]) > maxAbsGrad) {
+                        image[x + y * wI] = NAN;
+                        image[x + deltax + (y + deltay) * wI] = NAN;
+                    }
 }
 
 /* ------------------------------------------------- CPU timing loops (bench only) */

@@ -22,6 +22,8 @@
 #define CV_16U 2
 #define CV_32F 5
 #define CV_32FC1 5
+#define CV_64F 6
+#define CV_AA 16
 #define CV_8UC3 16
 #define CV_LOAD_IMAGE_UNCHANGED (-1)
 #define CV_LOAD_IMAGE_GRAYSCALE 0
@@ -31,14 +33,16 @@ typedef unsigned short ushort;
 
 namespace cv {
 
-inline int shim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_8UC3 ? 3 : 4)); }
+inline int shim_elem_size(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : (type == CV_8UC3 ? 3 : (type == CV_64F ? 8 : 4))); }
 
 struct Vec3b {
     unsigned char v[3];
     Vec3b() { v[0] = v[1] = v[2] = 0; }
     Vec3b(unsigned char a, unsigned char b, unsigned char c) { v[0] = a; v[1] = b; v[2] = c; }
 };
-struct Scalar { double v; Scalar(double a = 0) : v(a) {} };
+struct Scalar { double v; Scalar(double a = 0) : v(a) {} Scalar(double a, double, double) : v(a) {} };
+struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b) : x(a), y(b) {} };
+struct Point { int x, y; Point() : x(0), y(0) {} Point(int a, int b) : x(a), y(b) {} };
 
 class Mat {
 public:
@@ -62,6 +66,9 @@ public:
         return *this;
     }
 
+    // convertTo: dst = saturate(round-half-even(src * alpha + beta)); CV_32F source, CV_8U / CV_16U destination only
+    void convertTo(Mat& dst, int type, double alpha = 1, double beta = 0) const;
+
     Mat operator*(double s) const {
         Mat m(rows, cols, type_);
         if (type_ == CV_32F)
@@ -80,6 +87,9 @@ Mat imdecode(const Mat& buf, int flags);
 bool imwrite(const std::string& path, const Mat& m);
 void imshow(const std::string& name, const Mat& m);
 int waitKey(int ms);
+// stand-in: ignores the points and returns the next 3x3 homography (CV_64F) of the file named by $MDC_SHIM_HOMOGRAPHIES
+Mat findHomography(const std::vector<Point2f>& src, const std::vector<Point2f>& dst);
+inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8) {}
 
 }  // namespace cv
 

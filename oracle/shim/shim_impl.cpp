@@ -1,5 +1,6 @@
 // Implementation of the stand-in cv:: free functions (test infrastructure only).
 #include "opencv2/core/core.hpp"
+#include <cmath>
 #include <map>
 #include <fstream>
 
@@ -81,5 +82,30 @@ bool imwrite(const std::string& path, const Mat& m) {
     return true;
 }
 void imshow(const std::string&, const Mat&) {}
+void Mat::convertTo(Mat& dst, int type, double alpha, double beta) const {
+    dst = Mat(rows, cols, type);
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = 0; i < n; i++) {
+        const double v = nearbyint((double)((const float*)data)[i] * alpha + beta);      // NaN / negative -> 0, like saturate_cast
+        if (type == CV_8U) dst.at<uchar>((int)i) = (uchar)(v > 255 ? 255 : (v > 0 ? v : 0));
+        else if (type == CV_16U) dst.at<ushort>((int)i) = (ushort)(v > 65535 ? 65535 : (v > 0 ? v : 0));
+    }
+}
+Mat findHomography(const std::vector<Point2f>&, const std::vector<Point2f>&) {
+    static std::ifstream f;
+    static bool opened = false;
+    if (!opened) {
+        opened = true;
+        const char* path = getenv("MDC_SHIM_HOMOGRAPHIES");
+        if (path) f.open(path);
+    }
+    Mat h(3, 3, CV_64F);
+    for (int i = 0; i < 9; i++) {
+        double v = (i % 4 == 0) ? 1.0 : 0.0;
+        if (f.good()) f >> v;
+        h.at<double>(i) = v;
+    }
+    return h;
+}
 int waitKey(int) { return ' '; }
 }  // namespace cv

@@ -37,8 +37,8 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3 / reps
 
-    plane_ms = timed(lambda: ctx.vc_plane_step(images, p2x, p2y, gw, gh, wI, hI, vig, plane, 1e8))
-    vig_ms = timed(lambda: ctx.vc_vignette_step(images, p2x, p2y, gw, gh, wI, hI, plane, vig, 1e8))
+    plane_ms = timed(lambda: ctx.vc_plane_step(images, p2x, p2y, gw, gh, wI, hI, vig, plane, 10000 * 10000))
+    vig_ms = timed(lambda: ctx.vc_vignette_step(images, p2x, p2y, gw, gh, wI, hI, plane, vig, 10000 * 10000))
     smooth_ms = timed(lambda: ctx.vc_smooth(vig, wI, hI, 4))
     samples = n * gw * gh
     print(json.dumps({"n": n, "plane_points": gw * gh, "visible_fraction": visible, "plane_step_ms": plane_ms, "vignette_step_ms": vig_ms,

@@ -161,10 +161,10 @@ def test_argument_validation_of_the_device_entry_points_needs_no_gpu(dataset_dir
     null = C.c_void_p()
     st = (C.c_double * 2)()
     # no context
-    assert L.mdc_vc_plane_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, st) == 1
-    assert L.mdc_vc_vignette_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, st) == 1
+    assert L.mdc_vc_plane_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, 1, st) == 1
+    assert L.mdc_vc_vignette_step(null, null, null, null, 1, 4, 4, 8, 8, null, null, 1.0, 1, st) == 1
     assert L.mdc_vc_smooth(null, null, 8, 8, 4, null) == 1
-    assert L.mdc_vignette_calib(null, null, null, null, 1, 4, 4, 8, 8, 2, 15, null, null, null, None) == 1
+    assert L.mdc_vignette_calib(null, null, null, null, 1, 4, 4, 8, 8, 2, 15, 1, null, null, null, None) == 1
     assert b"bad argument" in L.mdc_last_error()
     assert L.mdc_estep(null, null, 1, 16, null, null, null, null) == 1
     assert L.mdc_rc_gstep(null, null, 1, 16, null, null, null, null) == 1

@@ -20,12 +20,12 @@ def problem():
     return S.vignette_calib_problem(N, GW, GH, WI, HI, seed=3)
 
 
-def oracle_loop(port, pr, iters, outlier_th, plane0, vig0):
+def oracle_loop(port, pr, iters, outlier_th, plane0, vig0, int_abs=True):
     plane, vig, log = plane0.copy(), vig0.copy(), []
     for it in range(iters):
-        oth2 = float(outlier_th * outlier_th) if it >= iters // 2 else 1e8
-        plane, _, _, ps = port.vc_plane_step(pr["images"], pr["p2x"], pr["p2y"], WI, HI, vig, plane, oth2)
-        vig, _, _, vs = port.vc_vignette_step(pr["images"], pr["p2x"], pr["p2y"], WI, HI, plane, vig, oth2)
+        oth2 = outlier_th * outlier_th if it >= iters // 2 else 10000 * 10000
+        plane, _, _, ps = port.vc_plane_step(pr["images"], pr["p2x"], pr["p2y"], WI, HI, vig, plane, oth2, int_abs)
+        vig, _, _, vs = port.vc_vignette_step(pr["images"], pr["p2x"], pr["p2y"], WI, HI, plane, vig, oth2, int_abs)
         log.append([ps[0], ps[1], vs[0], vs[1]])
     return plane, vig, np.array(log)
 
@@ -72,33 +72,39 @@ def start_state(seed=5):
     return plane, vig
 
 
+# integer_abs: `abs(residual) > oth2` with the residual truncated to int (the reference's era, and the reference program as built
+# for the oracle) or fabs (what the same line means with <cmath>'s overloads in scope) -- include/mdc_b200.h
+MODES = pytest.mark.parametrize("oth2,int_abs", [(10000 * 10000, True), (400, True), (400, False), (9, True), (9, False)],
+                                ids=["no_outliers", "th20_int_abs", "th20_fabs", "th3_int_abs", "th3_fabs"])
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("oth2", [1e8, 400.0], ids=["no_outliers", "outlier_threshold_20"])
-def test_plane_step_is_bit_identical(port, problem, gpu, oth2):
+@MODES
+def test_plane_step_is_bit_identical(port, problem, gpu, oth2, int_abs):
     torch, ctx, d = gpu
     plane0, vig0 = start_state()
-    exp, _, _, st = port.vc_plane_step(problem["images"], problem["p2x"], problem["p2y"], WI, HI, vig0, plane0, oth2)
+    exp, _, _, st = port.vc_plane_step(problem["images"], problem["p2x"], problem["p2y"], WI, HI, vig0, plane0, oth2, int_abs)
     pc = torch.from_numpy(plane0).cuda()
-    E, R = ctx.vc_plane_step(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, torch.from_numpy(vig0).cuda(), pc, oth2)
+    E, R = ctx.vc_plane_step(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, torch.from_numpy(vig0).cuda(), pc, oth2, int_abs)
     assert_bits_equal(pc.cpu().numpy(), exp, "plane colour")
     assert R == st[1] and abs(E - st[0]) <= 1e-9 * abs(st[0])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("oth2", [1e8, 400.0], ids=["no_outliers", "outlier_threshold_20"])
-def test_vignette_step_matches_to_rounding(port, problem, gpu, oth2):
+@MODES
+def test_vignette_step_matches_to_rounding(port, problem, gpu, oth2, int_abs):
     """The reference adds the scattered terms in (image, point) order, the GPU with fp32 atomics in any order."""
     TOL = 2e-5
     torch, ctx, d = gpu
     plane0, vig0 = start_state()
-    exp, tt, _, st = port.vc_vignette_step(problem["images"], problem["p2x"], problem["p2y"], WI, HI, plane0, vig0, oth2)
+    exp, tt, _, st = port.vc_vignette_step(problem["images"], problem["p2x"], problem["p2y"], WI, HI, plane0, vig0, oth2, int_abs)
     v = torch.from_numpy(vig0).cuda()
-    E, R = ctx.vc_vignette_step(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, torch.from_numpy(plane0).cuda(), v, oth2)
+    E, R = ctx.vc_vignette_step(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, torch.from_numpy(plane0).cuda(), v, oth2, int_abs)
     got = v.cpu().numpy()
     firm = np.abs(tt - 1.0) > 1e-3              # pixels whose "TT < 1" test cannot flip with the summation order
     assert np.array_equal(np.isnan(got)[firm], np.isnan(exp)[firm])
     m = np.isfinite(exp) & np.isfinite(got)
-    assert m.sum() > 1000
+    assert m.sum() > 200
     assert np.max(np.abs(got[m] - exp[m]) / np.maximum(np.abs(exp[m]), 1e-6)) < TOL
     assert R == st[1] and abs(E - st[0]) <= 1e-9 * abs(st[0])
 
@@ -117,13 +123,14 @@ def test_smoothing_is_bit_identical(port, gpu):
 
 
 @pytest.mark.gpu
-def test_whole_loop_against_the_oracle_loop(port, problem, gpu, capfd):
+@pytest.mark.parametrize("int_abs", [True, False], ids=["int_abs", "fabs"])
+def test_whole_loop_against_the_oracle_loop(port, problem, gpu, capfd, int_abs):
     torch, ctx, d = gpu
     iters, th = 6, 15
     plane0, vig0 = np.zeros(GW * GH, np.float32), np.ones(WI * HI, np.float32)
-    plane_e, vig_e, log_e = oracle_loop(port, problem, iters, th, plane0, vig0)
+    plane_e, vig_e, log_e = oracle_loop(port, problem, iters, th, plane0, vig0, int_abs)
     pc, v = torch.from_numpy(plane0).cuda(), torch.from_numpy(vig0).cuda()
-    smoothed, log = ctx.vignette_calib(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, iters, th, pc, v)
+    smoothed, log = ctx.vignette_calib(d["images"], d["p2x"], d["p2y"], GW, GH, WI, HI, iters, th, pc, v, int_abs)
     assert "residual terms =>" in capfd.readouterr().out          # the reference's progress lines (:448, :519)
     got_v, got_p = v.cpu().numpy(), pc.cpu().numpy()
     m = np.isfinite(vig_e) & np.isfinite(got_v)
