@@ -33,7 +33,7 @@ fov.distortCoordinatesDevice(x, y)
 pr = S.vignette_calib_problem(5, 48, 40, 64, 56, seed=1)
 d = {k: torch.from_numpy(pr[k]).cuda() for k in ("images", "p2x", "p2y")}
 pc, v = torch.zeros(48 * 40, device="cuda"), torch.ones(64 * 56, device="cuda")
-ctx.vignette_calib(d["images"], d["p2x"], d["p2y"], 48, 40, 64, 56, 2, 15, pc, v)
+ctx.vignette_calib(d["images"], d["p2x"], d["p2y"], 48, 40, 64, 56, 2, 15, pc, v, True)
 torch.cuda.synchronize()
 print("done")
 PY
