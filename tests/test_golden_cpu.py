@@ -63,3 +63,24 @@ def test_product_host_models_match_golden(path, tmp_path):
     defined = g["g"] == g["g"]
     assert_bits_equal(p.getG()[[0, 255]], g["g"][[0, 255]], "G ends")
     assert_bits_equal(p.vignette_maps()[1], g["vinv"], "vignetteMapInv")
+
+
+def test_restated_response_calib_loop_reproduces_the_programs_golden_output(port):
+    """tests/golden/programs/response_calib.npz = output of the reference's responseCalib program (make_golden_programs.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "programs", "response_calib.npz"))
+    w, h, nits, leak = int(g["w"]), int(g["h"]), int(g["nits"]), int(g["leak_padding"])
+    data = np.stack([port.leak_padding(f, w, h, leak) for f in g["frames"]])
+    t = g["exposures"]
+    E = port.einit(data)
+    nums, rmses = [], []
+    for _ in range(nits):
+        G = port.gstep(data, t, E)
+        E = port.estep(data, t, G)
+        port.rescale(E, G)
+        r = port.rmse(data, t, G, E)
+        rmses.append(r[0]); nums.append(r[1])
+    fin = np.isfinite(g["G"])
+    assert np.array_equal(np.isfinite(G), fin)
+    assert np.max(np.abs(G[fin] - g["G"][fin]) / np.maximum(np.abs(g["G"][fin]), 1e-300)) < 5e-14
+    assert np.array_equal(np.array(nums), g["log_num"])
+    assert np.max(np.abs(np.array(rmses) - g["log_rmse"]) / g["log_rmse"]) < 5e-14

@@ -441,6 +441,25 @@ def test_response_calib_loop(api, port):
     assert abs(g[255] - 255.0) < 1e-9
 
 
+def test_response_calib_against_the_reference_programs_own_output(api):
+    """tests/golden/programs/response_calib.npz holds what the reference's responseCalib PROGRAM (main_responseCalib.cpp, unmodified)
+    wrote for a small sequence: the GPU calibrator is compared with it directly, not through the restatement."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "programs", "response_calib.npz"))
+    w, h, nits, leak = int(g["w"]), int(g["h"]), int(g["nits"]), int(g["leak_padding"])
+    ctx = api.Context(None, None, 0)
+    d = torch.from_numpy(g["frames"]).cuda()
+    ctx.rc_leak_padding(d, w, h, leak)
+    E = torch.zeros(w * h, dtype=torch.float64, device="cuda")
+    G = torch.zeros(256, dtype=torch.float64, device="cuda")
+    log = ctx.response_calib(d, torch.from_numpy(g["exposures"]).cuda(), nits, E, G)
+    got, ref = G.cpu().numpy(), g["G"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-300)) < 1e-9      # parallel fp64 sums vs sequential ones
+    assert np.array_equal(log[:, 3], g["log_num"])                                                # sample counts: exact
+    assert np.max(np.abs(log[:, 2] - g["log_rmse"]) / g["log_rmse"]) < 1e-9
+
+
 @pytest.mark.parametrize("cfg", [
     (1280, 1024, 64, 48, "crop", S.TUM_CALIB),          # 20x minification: boxes far too large to stage -> direct global-gather tiles
     (800, 608, 96, 40, "0.9 1.2 0.5 0.5 0", S.TUM_CALIB),   # mixed: some tiles staged, some direct, some black
