@@ -168,6 +168,31 @@ int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_frames, unsigne
 int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_dst, int n_frames, mdc_stream stream);
 
 /* =====================================================================================
+ * Sequence reader + decode-ahead feed — the host side of DatasetReader (BenchmarkDatasetReader.h:83-147, :159-186, :247-345)
+ * without OpenCV / libzip.  Lossless frames only: 8/16-bit grey PNG and binary PGM are decoded by this
+ * library; JPEG frames stay with the caller's decoder (include/compat/BenchmarkDatasetReader.h keeps using cv::imread).
+ * ===================================================================================== */
+typedef struct mdc_seq mdc_seq;
+/* DatasetReader(folder), :85-140: the sorted entries of <folder>/images/, or, if there are none, of <folder>/images.zip (stored /
+ * deflated entries, no zip64); <folder>/times.txt ("id timestamp [exposure]" per line; a count mismatch zeroes all, :322-329).
+ * A missing / unreadable archive returns MDC_ERR_IO (the reference calls exit(1), :117-121). */
+int mdc_seq_open(const char* folder, mdc_seq** out);
+void mdc_seq_close(mdc_seq* s);
+int mdc_seq_num_images(const mdc_seq* s);                 /* getNumImages(), :169 */
+int mdc_seq_is_zipped(const mdc_seq* s);
+const char* mdc_seq_name(const mdc_seq* s, int id);       /* path (folder) or entry name (zip); NULL if out of range */
+double mdc_seq_timestamp(const mdc_seq* s, int id);       /* getTimestamp(), :171-177: 0 if out of range */
+float mdc_seq_exposure(const mdc_seq* s, int id);         /* getExposure(), :179-186 */
+/* getImageRaw_internal(id), :247-276, CV_LOAD_IMAGE_GRAYSCALE semantics: 8-bit grey pixels (a 16-bit source keeps its high byte).
+ * out may be NULL to query the size only.  MDC_ERR_FORMAT if the frame cannot be decoded. */
+int mdc_seq_read_gray8(const mdc_seq* s, int id, uint8_t* out, size_t capacity, int* w, int* h);
+/* getImage(id, flags...) for id in [first, first+count) into HOST level buffers (level l: [count][(w>>l)*(h>>l)] floats, as for
+ * mdc_prepare_batch_host): `threads` host threads (0 = all) decode the next 32 frames into pinned memory while the current 32 go
+ * through H2D -> fused kernel -> D2H.  A frame of the wrong size or an undecodable one stops the call with MDC_ERR_FORMAT
+ * (the reference prints and returns 0 for that frame, :194-205). */
+int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int count, unsigned flags, float* const* h_out_levels, int levels, int threads);
+
+/* =====================================================================================
  * vignetteCalib optimiser, main_vignetteCalib.cpp:395-585.  Everything is device-resident, contiguous:
  *   d_images [n][wI*hI] float (NaN = invalidated pixel, :300-310), d_p2x / d_p2y [n][gw*gh] float plane-to-image maps
  *   (NaN = plane point not visible; finite entries keep the four bilinear taps inside the image, :352-356),

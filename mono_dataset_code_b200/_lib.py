@@ -36,6 +36,15 @@ SIGNATURES = {
     "mdc_fov_distort_coordinates": (C.c_int, [_vp, _f32p, _f32p, C.c_int]),
     "mdc_fov_distort_coordinates_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "mdc_atanf_host": (None, [_f32p, _f32p, C.c_size_t]),
+    "mdc_seq_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "mdc_seq_close": (None, [_vp]),
+    "mdc_seq_num_images": (C.c_int, [_vp]),
+    "mdc_seq_is_zipped": (C.c_int, [_vp]),
+    "mdc_seq_name": (C.c_char_p, [_vp, C.c_int]),
+    "mdc_seq_timestamp": (C.c_double, [_vp, C.c_int]),
+    "mdc_seq_exposure": (C.c_float, [_vp, C.c_int]),
+    "mdc_seq_read_gray8": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mdc_seq_prepare": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint, C.POINTER(_vp), C.c_int, C.c_int]),
     "mdc_vc_plane_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "mdc_vc_vignette_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "mdc_vc_smooth": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

@@ -398,9 +398,60 @@ class ExposureImage:
         self.image = np.empty(w_ * h_, np.float32)
 
 
+class Sequence:
+    """The file side of DatasetReader (BenchmarkDatasetReader.h:83-147, :159-186, :247-345): images/ folder or images.zip, times.txt,
+    raw 8-bit frames (lossless formats: PNG, PGM), and the decode-ahead feed of the GPU path."""
+
+    def __init__(self, folder: str):
+        h = C.c_void_p()
+        self.status = lib.mdc_seq_open(folder.encode(), C.byref(h))
+        self._h = h if self.status == 0 else None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and lib is not None:
+            lib.mdc_seq_close(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def getNumImages(self) -> int:
+        return lib.mdc_seq_num_images(self._h) if self._h else 0
+
+    def isZipped(self) -> bool:
+        return bool(lib.mdc_seq_is_zipped(self._h)) if self._h else False
+
+    def name(self, id_: int):
+        v = lib.mdc_seq_name(self._h, id_) if self._h else None
+        return v.decode() if v else None
+
+    def getTimestamp(self, id_: int) -> float:
+        return lib.mdc_seq_timestamp(self._h, id_) if self._h else 0.0
+
+    def getExposure(self, id_: int) -> float:
+        return lib.mdc_seq_exposure(self._h, id_) if self._h else 0.0
+
+    def getImageRaw_internal(self, id_: int):
+        """Decoded 8-bit grey frame [h, w], or None if it cannot be decoded (cv::imread would return an empty Mat)."""
+        w, h = C.c_int(), C.c_int()
+        if not self._h or lib.mdc_seq_read_gray8(self._h, id_, None, 0, C.byref(w), C.byref(h)) != 0:
+            return None
+        out = np.empty((h.value, w.value), np.uint8)
+        check(lib.mdc_seq_read_gray8(self._h, id_, out.ctypes.data_as(C.c_void_p), out.size, C.byref(w), C.byref(h)), "mdc_seq_read_gray8")
+        return out
+
+    def prepare(self, ctx: "Context", level_shapes, first: int, count: int, rectify, removeGamma, removeVignette, nanOverexposed,
+                threads: int = 0):
+        """getImage for frames [first, first+count) -> list of float32 arrays [count, w_l*h_l] (one per pyramid level)."""
+        outs = [np.empty((count, w * h), np.float32) for (w, h) in level_shapes]
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        check(lib.mdc_seq_prepare(ctx._h, self._h, first, count, _flags(rectify, removeGamma, removeVignette, nanOverexposed), ptrs, len(outs), threads),
+              "mdc_seq_prepare")
+        return outs
+
+
 class FramePreparer:
-    """The getImage composition of DatasetReader (BenchmarkDatasetReader.h:188-243) over frames
-    that are already decoded (decode/zip is out of scope)."""
+    """The getImage composition of DatasetReader (BenchmarkDatasetReader.h:188-243) over frames that are already decoded
+    (use Sequence for the folder / zip / times.txt side)."""
 
     def __init__(self, undistorter: UndistorterFOV, photoUndistorter: PhotometricUndistorter, device: int = 0):
         self.undistorter, self.photoUndistorter = undistorter, photoUndistorter

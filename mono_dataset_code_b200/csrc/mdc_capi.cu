@@ -598,6 +598,7 @@ extern "C" int mdc_atanf_device(const float* d_in, float* d_out, size_t n, int d
 int mdc_ctx_device_ordinal(const mdc_ctx* c) { return c->device; }
 void* mdc_ctx_stream_handle(mdc_ctx* c) { return c->stream; }
 void mdc_ctx_add_launches(mdc_ctx* c, int n) { c->launches += n; }
+void mdc_ctx_geometry(const mdc_ctx* c, int* in_w, int* in_h, int* out_w, int* out_h) { *in_w = c->in_w; *in_h = c->in_h; *out_w = c->out_w; *out_h = c->out_h; }
 
 extern "C" int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, double* d_E, mdc_stream stream) {
     if (!c || !d_data || !d_t || !d_G || !d_E || n < 0 || npix < 0) { mdc_set_error("mdc_estep: bad argument"); return MDC_ERR_INVALID_ARG; }

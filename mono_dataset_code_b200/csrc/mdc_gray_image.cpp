@@ -124,11 +124,15 @@ bool decode_pgm(const std::vector<uint8_t>& file, const std::string& path, mdc_g
 
 }  // namespace
 
+bool mdc_decode_gray_image(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out) {
+    mdc_set_error("%s: not a PNG or PGM image", name.c_str());
+    if (file.size() >= 2 && file[0] == 'P' && file[1] == '5') return decode_pgm(file, name, out);
+    return decode_png(file, name, out);
+}
+
 bool mdc_read_gray_image(const std::string& path, mdc_gray_image* out) {
     std::ifstream f(path.c_str(), std::ios::binary);
     if (!f.good()) { mdc_set_error("cannot open image %s", path.c_str()); return false; }
     std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    mdc_set_error("%s: not a PNG or PGM image", path.c_str());
-    if (file.size() >= 2 && file[0] == 'P' && file[1] == '5') return decode_pgm(file, path, out);
-    return decode_png(file, path, out);
+    return mdc_decode_gray_image(file, path, out);
 }

@@ -38,6 +38,7 @@ struct mdc_gray_image {
     std::vector<uint8_t> px;
 };
 bool mdc_read_gray_image(const std::string& path, mdc_gray_image* out);
+bool mdc_decode_gray_image(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out);      // same, from memory
 
 // Table builders (strict IEEE float; see mdc_host_models.cpp).
 void mdc_fov_build(mdc_fov* f, int mode, const float out_calib_in[5]);
@@ -51,3 +52,4 @@ void mdc_photo_set_vignette(mdc_photo* p, const void* pixels, int depth);
 int mdc_ctx_device_ordinal(const mdc_ctx* c);
 void* mdc_ctx_stream_handle(mdc_ctx* c);          // the context's own cudaStream_t
 void mdc_ctx_add_launches(mdc_ctx* c, int n);
+void mdc_ctx_geometry(const mdc_ctx* c, int* in_w, int* in_h, int* out_w, int* out_h);
