@@ -169,8 +169,8 @@ int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_
 
 /* =====================================================================================
  * Sequence reader + decode-ahead feed — the host side of DatasetReader (BenchmarkDatasetReader.h:83-147, :159-186, :247-345)
- * without OpenCV / libzip.  Lossless frames only: 8/16-bit grey PNG and binary PGM are decoded by this
- * library; JPEG frames stay with the caller's decoder (include/compat/BenchmarkDatasetReader.h keeps using cv::imread).
+ * without OpenCV / libzip.  Frames: 8/16-bit grey PNG, binary PGM and baseline JPEG (grey or colour, read as
+ * grey), decoded by this library to the same bytes as cv::imread(..., CV_LOAD_IMAGE_GRAYSCALE).
  * ===================================================================================== */
 typedef struct mdc_seq mdc_seq;
 /* DatasetReader(folder), :85-140: the sorted entries of <folder>/images/, or, if there are none, of <folder>/images.zip (stored /
@@ -183,7 +183,8 @@ int mdc_seq_is_zipped(const mdc_seq* s);
 const char* mdc_seq_name(const mdc_seq* s, int id);       /* path (folder) or entry name (zip); NULL if out of range */
 double mdc_seq_timestamp(const mdc_seq* s, int id);       /* getTimestamp(), :171-177: 0 if out of range */
 float mdc_seq_exposure(const mdc_seq* s, int id);         /* getExposure(), :179-186 */
-/* getImageRaw_internal(id), :247-276, CV_LOAD_IMAGE_GRAYSCALE semantics: 8-bit grey pixels (a 16-bit source keeps its high byte).
+/* getImageRaw_internal(id), :247-276, CV_LOAD_IMAGE_GRAYSCALE semantics: 8-bit grey pixels (a 16-bit PNG keeps its high byte, a
+ * colour JPEG gives its luminance component).
  * out may be NULL to query the size only.  MDC_ERR_FORMAT if the frame cannot be decoded. */
 int mdc_seq_read_gray8(const mdc_seq* s, int id, uint8_t* out, size_t capacity, int* w, int* h);
 /* getImage(id, flags...) for id in [first, first+count) into HOST level buffers (level l: [count][(w>>l)*(h>>l)] floats, as for

@@ -432,11 +432,20 @@ class Sequence:
 
     def getImageRaw_internal(self, id_: int):
         """Decoded 8-bit grey frame [h, w], or None if it cannot be decoded (cv::imread would return an empty Mat)."""
+        if not self._h:
+            return None
         w, h = C.c_int(), C.c_int()
-        if not self._h or lib.mdc_seq_read_gray8(self._h, id_, None, 0, C.byref(w), C.byref(h)) != 0:
+        guess = getattr(self, "_last_shape", None)
+        if guess is not None:                       # frames of a sequence share one size: try a buffer of that size first
+            out = np.empty(guess, np.uint8)
+            rc = lib.mdc_seq_read_gray8(self._h, id_, out.ctypes.data_as(C.c_void_p), out.size, C.byref(w), C.byref(h))
+            if rc == 0 and (h.value, w.value) == guess:
+                return out
+        if lib.mdc_seq_read_gray8(self._h, id_, None, 0, C.byref(w), C.byref(h)) != 0:
             return None
         out = np.empty((h.value, w.value), np.uint8)
         check(lib.mdc_seq_read_gray8(self._h, id_, out.ctypes.data_as(C.c_void_p), out.size, C.byref(w), C.byref(h)), "mdc_seq_read_gray8")
+        self._last_shape = (h.value, w.value)
         return out
 
     def prepare(self, ctx: "Context", level_shapes, first: int, count: int, rectify, removeGamma, removeVignette, nanOverexposed,

@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     objs, log, rebuilt = [], [], False
-    for src in ("mdc_host_models.cpp", "mdc_gray_image.cpp", "mdc_sequence.cpp"):
+    for src in ("mdc_host_models.cpp", "mdc_gray_image.cpp", "mdc_jpeg.cpp", "mdc_sequence.cpp"):
         o = os.path.join(obj_dir, src + ".o")
         s = os.path.join(CSRC, src)
         if force or _newer(o, [s] + headers):

@@ -125,8 +125,9 @@ bool decode_pgm(const std::vector<uint8_t>& file, const std::string& path, mdc_g
 }  // namespace
 
 bool mdc_decode_gray_image(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out) {
-    mdc_set_error("%s: not a PNG or PGM image", name.c_str());
+    mdc_set_error("%s: not a PNG, PGM or JPEG image", name.c_str());
     if (file.size() >= 2 && file[0] == 'P' && file[1] == '5') return decode_pgm(file, name, out);
+    if (file.size() >= 2 && file[0] == 0xff && file[1] == 0xd8) return mdc_decode_jpeg_gray(file, name, out);
     return decode_png(file, name, out);
 }
 

@@ -39,6 +39,7 @@ struct mdc_gray_image {
 };
 bool mdc_read_gray_image(const std::string& path, mdc_gray_image* out);
 bool mdc_decode_gray_image(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out);      // same, from memory
+bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out);       // baseline JPEG -> luminance (mdc_jpeg.cpp)
 
 // Table builders (strict IEEE float; see mdc_host_models.cpp).
 void mdc_fov_build(mdc_fov* f, int mode, const float out_calib_in[5]);

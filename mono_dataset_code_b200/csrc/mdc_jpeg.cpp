@@ -1,0 +1,332 @@
+// Baseline JPEG -> 8-bit grey, for the frames of the published sequences (images.zip holds JPEGs; the reference reads them with
+// cv::imread(..., CV_LOAD_IMAGE_GRAYSCALE), BenchmarkDatasetReader.h:252, :274).
+//
+// The image has no libjpeg to link, so this is a small decoder of its own, written to give the SAME BYTES as the decoder behind
+// cv::imread (libjpeg / libjpeg-turbo with its default settings) for the files it accepts:
+//   * baseline sequential DCT, Huffman coding, 8-bit samples (SOF0; SOF1 with 8-bit tables works the same), 1 or 3 components,
+//     any sampling factors, restart intervals.  Progressive / arithmetic / 12-bit / lossless files are rejected (MDC_ERR_FORMAT).
+//   * grey output = the luminance component only — what libjpeg does for out_color_space = JCS_GRAYSCALE: chroma blocks are
+//     entropy-decoded (they share the bit stream) and dropped, so no upsampling or colour conversion is involved.
+//   * inverse DCT = the "accurate integer" method (JDCT_ISLOW, libjpeg's default): the Loeffler-Ligtenberg-Moschytz
+//     factorisation in 13-bit fixed point with 2 extra bits kept between the column and the row pass, as published in the
+//     Independent JPEG Group's jidctint.c; libjpeg-turbo's SIMD versions are bit-exact with it.  Restated here from that
+//     description (ITU-T T.81 for the entropy coding); tests/test_jpeg_decoder.py compares the result with cv2's decoder on
+//     grey and colour files of several qualities, sampling modes and restart intervals, byte for byte.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mdc_internal.h"
+
+namespace {
+
+constexpr int kLookBits = 9;      // Huffman codes up to this length are resolved by one table look-up
+
+struct HuffTable {
+    bool defined = false;
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    // canonical decoding tables (T.81 Annex F.2.2.3) + a prefix table for the short codes
+    int mincode[17], maxcode[18], valptr[17];
+    uint16_t look[1 << kLookBits];      // (code length << 8) | symbol, 0 = longer than kLookBits
+    void build() {
+        int code = 0, k = 0;
+        memset(look, 0, sizeof look);
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k;
+            mincode[l] = code;
+            for (int i = 0; i < bits[l]; ++i, ++code, ++k)
+                if (l <= kLookBits) {
+                    const int first = code << (kLookBits - l), span = 1 << (kLookBits - l);
+                    for (int j = 0; j < span; ++j) look[first + j] = static_cast<uint16_t>((l << 8) | vals[k]);
+                }
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+    }
+};
+
+struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; };
+
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc = 0;      // the next bits of the stream, left-aligned
+    int n = 0;             // how many of them are valid
+    bool hit_marker = false;
+    // entropy-coded bytes: 0xFF 0x00 is a stuffed 0xFF, 0xFF followed by anything else is a marker (zero bits from then on)
+    void fill() {
+        while (n <= 56) {
+            uint64_t b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xff) {
+                    if (p + 1 < end && p[1] == 0x00) p += 2;
+                    else { hit_marker = true; b = 0; }
+                } else {
+                    ++p;
+                }
+            }
+            acc |= b << (56 - n);
+            n += 8;
+        }
+    }
+    inline int peek(int count) {                       // count in 1..25
+        if (n < count) fill();
+        return static_cast<int>(acc >> (64 - count));
+    }
+    inline void skip(int count) { acc <<= count; n -= count; }
+    inline int bits(int count) {
+        if (count == 0) return 0;
+        const int v = peek(count);
+        skip(count);
+        return v;
+    }
+    void reset() { acc = 0; n = 0; hit_marker = false; }
+};
+
+inline int decode_symbol(BitReader& br, const HuffTable& t) {
+    const int look = t.look[br.peek(kLookBits)];
+    if (look) { br.skip(look >> 8); return look & 0xff; }
+    // longer code: canonical search from kLookBits + 1 bits on
+    int l = kLookBits + 1;
+    int code = br.peek(l);
+    while (l <= 16 && code > t.maxcode[l]) { ++l; code = br.peek(l); }
+    if (l > 16) return -1;
+    br.skip(l);
+    return t.vals[t.valptr[l] + code - t.mincode[l]];
+}
+// T.81 F.2.2.1 EXTEND
+inline int extend(int v, int t) { return (t && v < (1 << (t - 1))) ? v - (1 << t) + 1 : v; }
+
+const uint8_t kZigZag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                             35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ---- inverse DCT, accurate integer method (13-bit constants, 2 guard bits between the passes)
+constexpr int kConstBits = 13, kPass1Bits = 2;
+constexpr int32_t F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373,
+                  F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819,
+                  F_2_562915447 = 20995, F_3_072711026 = 25172;
+inline int32_t descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
+inline uint8_t clamp_sample(int32_t v) { v += 128; return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+struct Butterfly { int32_t e0, e1, e2, e3, o0, o1, o2, o3; };      // out[k] = e_k + o_(3-k), out[7-k] = e_k - o_(3-k)
+inline Butterfly idct_1d(int32_t c0, int32_t c1, int32_t c2, int32_t c3, int32_t c4, int32_t c5, int32_t c6, int32_t c7) {
+    Butterfly r;
+    // even part
+    int32_t z1 = (c2 + c6) * F_0_541196100;
+    const int32_t t2 = z1 + c6 * (-F_1_847759065), t3 = z1 + c2 * F_0_765366865;
+    const int32_t t0 = (c0 + c4) << kConstBits, t1 = (c0 - c4) << kConstBits;
+    r.e0 = t0 + t3; r.e3 = t0 - t3; r.e1 = t1 + t2; r.e2 = t1 - t2;
+    // odd part
+    int32_t a0 = c7, a1 = c5, a2 = c3, a3 = c1;
+    z1 = a0 + a3;
+    int32_t z2 = a1 + a2, z3 = a0 + a2, z4 = a1 + a3;
+    const int32_t z5 = (z3 + z4) * F_1_175875602;
+    a0 *= F_0_298631336; a1 *= F_2_053119869; a2 *= F_3_072711026; a3 *= F_1_501321110;
+    z1 *= -F_0_899976223; z2 *= -F_2_562915447; z3 *= -F_1_961570560; z4 *= -F_0_390180644;
+    z3 += z5; z4 += z5;
+    r.o0 = a0 + z1 + z3; r.o1 = a1 + z2 + z4; r.o2 = a2 + z2 + z3; r.o3 = a3 + z1 + z4;
+    return r;
+}
+
+// coef: dequantised coefficients in natural order; out: 8 rows of 8 samples, `stride` apart.  Columns / rows whose AC terms are all
+// zero take a shortcut that gives exactly what the full butterfly gives for them (dc << 2, resp. (ws0 + 16) >> 5).
+void idct_block(const int32_t coef[64], uint8_t* out, size_t stride) {
+    int32_t ws[64];
+    for (int c = 0; c < 8; ++c) {
+        if ((coef[8 + c] | coef[16 + c] | coef[24 + c] | coef[32 + c] | coef[40 + c] | coef[48 + c] | coef[56 + c]) == 0) {
+            const int32_t v = coef[c] * (1 << kPass1Bits);
+            ws[c] = ws[8 + c] = ws[16 + c] = ws[24 + c] = ws[32 + c] = ws[40 + c] = ws[48 + c] = ws[56 + c] = v;
+            continue;
+        }
+        const Butterfly b = idct_1d(coef[c], coef[8 + c], coef[16 + c], coef[24 + c], coef[32 + c], coef[40 + c], coef[48 + c], coef[56 + c]);
+        const int s = kConstBits - kPass1Bits;
+        ws[c] = descale(b.e0 + b.o3, s);       ws[56 + c] = descale(b.e0 - b.o3, s);
+        ws[8 + c] = descale(b.e1 + b.o2, s);   ws[48 + c] = descale(b.e1 - b.o2, s);
+        ws[16 + c] = descale(b.e2 + b.o1, s);  ws[40 + c] = descale(b.e2 - b.o1, s);
+        ws[24 + c] = descale(b.e3 + b.o0, s);  ws[32 + c] = descale(b.e3 - b.o0, s);
+    }
+    for (int r = 0; r < 8; ++r) {
+        const int32_t* w = ws + 8 * r;
+        uint8_t* o = out + r * stride;
+        if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
+            memset(o, clamp_sample(descale(w[0], kPass1Bits + 3)), 8);
+            continue;
+        }
+        const Butterfly b = idct_1d(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        const int s = kConstBits + kPass1Bits + 3;
+        o[0] = clamp_sample(descale(b.e0 + b.o3, s));  o[7] = clamp_sample(descale(b.e0 - b.o3, s));
+        o[1] = clamp_sample(descale(b.e1 + b.o2, s));  o[6] = clamp_sample(descale(b.e1 - b.o2, s));
+        o[2] = clamp_sample(descale(b.e2 + b.o1, s));  o[5] = clamp_sample(descale(b.e2 - b.o1, s));
+        o[3] = clamp_sample(descale(b.e3 + b.o0, s));  o[4] = clamp_sample(descale(b.e3 - b.o0, s));
+    }
+}
+
+inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+}  // namespace
+
+bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out) {
+    const uint8_t* d = file.data();
+    const size_t n = file.size();
+    if (n < 4 || d[0] != 0xff || d[1] != 0xd8) { mdc_set_error("%s: not a JPEG file", name.c_str()); return false; }
+    uint16_t quant[4][64];
+    bool quant_defined[4] = {false, false, false, false};
+    HuffTable dc[4], ac[4];
+    std::vector<Component> comps;
+    int width = 0, height = 0, restart_interval = 0;
+    bool have_frame = false;
+    size_t pos = 2;
+    auto fail = [&](const char* what) { mdc_set_error("%s: %s", name.c_str(), what); return false; };
+    while (pos + 4 <= n) {
+        if (d[pos] != 0xff) return fail("corrupt JPEG (marker expected)");
+        while (pos < n && d[pos] == 0xff) ++pos;             // fill bytes
+        if (pos >= n) break;
+        const int marker = d[pos++];
+        if (marker == 0xd8 || (marker >= 0xd0 && marker <= 0xd7) || marker == 0x01) continue;
+        if (marker == 0xd9) break;
+        if (pos + 2 > n) return fail("truncated JPEG");
+        const int len = be16(d + pos);
+        if (len < 2 || pos + len > n) return fail("truncated JPEG segment");
+        const uint8_t* seg = d + pos + 2;
+        const int seg_len = len - 2;
+        if (marker == 0xdb) {                                  // DQT
+            int i = 0;
+            while (i < seg_len) {
+                const int pq = seg[i] >> 4, tq = seg[i] & 15;
+                ++i;
+                if (tq > 3 || i + (pq ? 128 : 64) > seg_len) return fail("bad quantisation table");
+                for (int k = 0; k < 64; ++k) {
+                    quant[tq][kZigZag[k]] = static_cast<uint16_t>(pq ? be16(seg + i + 2 * k) : seg[i + k]);
+                }
+                i += pq ? 128 : 64;
+                quant_defined[tq] = true;
+            }
+        } else if (marker == 0xc4) {                           // DHT
+            int i = 0;
+            while (i + 17 <= seg_len) {
+                const int tc = seg[i] >> 4, th = seg[i] & 15;
+                if (tc > 1 || th > 3) return fail("bad Huffman table id");
+                HuffTable& t = tc ? ac[th] : dc[th];
+                int total = 0;
+                t.bits[0] = 0;
+                for (int l = 1; l <= 16; ++l) { t.bits[l] = seg[i + l]; total += t.bits[l]; }
+                i += 17;
+                if (total > 256 || i + total > seg_len) return fail("bad Huffman table");
+                memcpy(t.vals, seg + i, static_cast<size_t>(total));
+                i += total;
+                t.defined = true;
+                t.build();
+            }
+        } else if (marker == 0xc0 || marker == 0xc1) {         // SOF0 / SOF1 (Huffman, sequential)
+            if (seg_len < 6) return fail("bad frame header");
+            if (seg[0] != 8) return fail("only 8-bit JPEG samples are supported");
+            height = be16(seg + 1);
+            width = be16(seg + 3);
+            const int nc = seg[5];
+            if ((nc != 1 && nc != 3) || seg_len < 6 + 3 * nc || width < 1 || height < 1) return fail("unsupported JPEG frame (components / size)");
+            comps.resize(static_cast<size_t>(nc));
+            for (int c = 0; c < nc; ++c) {
+                comps[c].id = seg[6 + 3 * c];
+                comps[c].h = seg[7 + 3 * c] >> 4;
+                comps[c].v = seg[7 + 3 * c] & 15;
+                comps[c].tq = seg[8 + 3 * c];
+                if (comps[c].h < 1 || comps[c].h > 4 || comps[c].v < 1 || comps[c].v > 4 || comps[c].tq > 3) return fail("bad component description");
+            }
+            have_frame = true;
+        } else if (marker == 0xc2 || (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc)) {
+            return fail("progressive / lossless / arithmetic-coded JPEG is not supported (baseline only)");
+        } else if (marker == 0xdd) {                           // DRI
+            if (seg_len < 2) return fail("bad restart interval");
+            restart_interval = be16(seg);
+        } else if (marker == 0xda) {                           // SOS: the one scan of a baseline file
+            if (!have_frame) return fail("scan before frame header");
+            const int ns = seg[0];
+            if (ns != static_cast<int>(comps.size()) || seg_len < 1 + 2 * ns + 3) return fail("non-interleaved multi-scan JPEG is not supported");
+            for (int k = 0; k < ns; ++k) {
+                const int cid = seg[1 + 2 * k];
+                bool found = false;
+                for (size_t c = 0; c < comps.size(); ++c)
+                    if (comps[c].id == cid) { comps[c].td = seg[2 + 2 * k] >> 4; comps[c].ta = seg[2 + 2 * k] & 15; found = true; }
+                if (!found) return fail("scan names an unknown component");
+            }
+            pos += static_cast<size_t>(len);
+            // ---- decode the scan
+            int hmax = 1, vmax = 1;
+            for (size_t c = 0; c < comps.size(); ++c) { hmax = std::max(hmax, comps[c].h); vmax = std::max(vmax, comps[c].v); comps[c].pred = 0; }
+            const Component& Y = comps[0];
+            if (!quant_defined[Y.tq]) return fail("missing quantisation table");
+            for (size_t c = 0; c < comps.size(); ++c)
+                if (comps[c].td > 3 || comps[c].ta > 3 || !dc[comps[c].td].defined || !ac[comps[c].ta].defined) return fail("missing Huffman table");
+            const bool single = comps.size() == 1;
+            // a single-component scan is not interleaved: its MCU is one block whatever the sampling factors say (T.81 A.2.2)
+            const int mcu_w = single ? 8 : 8 * hmax, mcu_h = single ? 8 : 8 * vmax;
+            const int mcus_x = (width + mcu_w - 1) / mcu_w, mcus_y = (height + mcu_h - 1) / mcu_h;
+            const int yh = single ? 1 : Y.h, yv = single ? 1 : Y.v;
+            // luminance plane padded to whole blocks; for subsampled colour files Y has h x v blocks per MCU at full resolution
+            // only if Y carries the maximum factors (always the case for files written by libjpeg/OpenCV); otherwise Y itself
+            // is subsampled and a grey read would need upsampling, which is not supported
+            if (!single && (Y.h != hmax || Y.v != vmax)) return fail("JPEG with a subsampled luminance component is not supported");
+            const size_t pw = static_cast<size_t>(mcus_x) * yh * 8, ph = static_cast<size_t>(mcus_y) * yv * 8;
+            std::vector<uint8_t> plane(pw * ph);
+            BitReader br{d + pos, d + n};
+            int32_t coef[64];
+            int until_restart = restart_interval;
+            for (int my = 0; my < mcus_y; ++my)
+                for (int mx = 0; mx < mcus_x; ++mx) {
+                    if (restart_interval && until_restart == 0) {
+                        // byte-align, expect RSTn, reset predictors
+                        const uint8_t* q = br.p;
+                        while (q + 1 < br.end && !(q[0] == 0xff && q[1] >= 0xd0 && q[1] <= 0xd7)) ++q;
+                        if (q + 1 >= br.end) return fail("missing restart marker");
+                        br.p = q + 2;
+                        br.reset();
+                        for (size_t c = 0; c < comps.size(); ++c) comps[c].pred = 0;
+                        until_restart = restart_interval;
+                    }
+                    for (size_t c = 0; c < comps.size(); ++c) {
+                        Component& comp = comps[c];
+                        const int bh = single ? 1 : comp.h, bv = single ? 1 : comp.v;
+                        for (int by = 0; by < bv; ++by)
+                            for (int bx = 0; bx < bh; ++bx) {
+                                // DC
+                                const int t = decode_symbol(br, dc[comp.td]);
+                                if (t < 0 || t > 15) return fail("corrupt JPEG data (DC)");
+                                comp.pred += extend(br.bits(t), t);
+                                if (c == 0) { memset(coef, 0, sizeof coef); coef[0] = comp.pred * quant[Y.tq][0]; }
+                                // AC
+                                for (int k = 1; k < 64;) {
+                                    const int rs = decode_symbol(br, ac[comp.ta]);
+                                    if (rs < 0) return fail("corrupt JPEG data (AC)");
+                                    const int r = rs >> 4, s = rs & 15;
+                                    if (s == 0) {
+                                        if (r != 15) break;      // EOB
+                                        k += 16;
+                                        continue;
+                                    }
+                                    k += r;
+                                    if (k > 63) return fail("corrupt JPEG data (run past the block)");
+                                    const int v = extend(br.bits(s), s);
+                                    if (c == 0) coef[kZigZag[k]] = v * quant[Y.tq][kZigZag[k]];
+                                    ++k;
+                                }
+                                if (c == 0) {
+                                    const size_t x0 = (static_cast<size_t>(mx) * yh + bx) * 8, y0 = (static_cast<size_t>(my) * yv + by) * 8;
+                                    idct_block(coef, plane.data() + y0 * pw + x0, pw);
+                                }
+                            }
+                    }
+                    if (restart_interval) --until_restart;
+                }
+            out->rows = height; out->cols = width; out->depth = 8;
+            out->px.resize(static_cast<size_t>(width) * height);
+            for (int y = 0; y < height; ++y) memcpy(out->px.data() + static_cast<size_t>(y) * width, plane.data() + static_cast<size_t>(y) * pw, static_cast<size_t>(width));
+            return true;
+        }
+        pos += static_cast<size_t>(len);
+    }
+    return fail("JPEG without image data");
+}

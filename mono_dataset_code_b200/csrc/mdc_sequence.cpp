@@ -2,10 +2,8 @@
 // decode-ahead feed of the GPU path.
 //
 //   mdc_seq_open      images/ folder (sorted) or, if that is empty, images.zip (central directory, sorted names); times.txt
-//   mdc_seq_read_gray8 getImageRaw_internal with CV_LOAD_IMAGE_GRAYSCALE for the lossless formats this library decodes itself:
-//                     8/16-bit grey PNG (16 -> 8 bit by dropping the low byte, as OpenCV's reader does) and binary PGM.
-//                     JPEG frames stay with the caller's decoder (no libjpeg in the build image; decode parity of lossy frames is
-//                     unpinned by the reference anyway).
+//   mdc_seq_read_gray8 getImageRaw_internal with CV_LOAD_IMAGE_GRAYSCALE: 8/16-bit grey PNG (16 -> 8 bit by dropping the low byte, as
+//                     OpenCV's reader does), binary PGM, baseline JPEG (mdc_jpeg.cpp) - the same bytes as cv::imread returns.
 //   mdc_seq_prepare   getImage for a range of frames: worker threads decode chunk k+1 into pinned memory while chunk k goes
 //                     through mdc_prepare_batch_host (H2D, fused kernel, D2H on three streams).
 //

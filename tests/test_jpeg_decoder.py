@@ -1,0 +1,93 @@
+"""csrc/mdc_jpeg.cpp: baseline JPEG -> 8-bit grey, compared byte for byte with the decoder behind cv::imread (the reference reads
+its frames with cv::imread(..., CV_LOAD_IMAGE_GRAYSCALE), BenchmarkDatasetReader.h:252, :274)."""
+import os
+
+import numpy as np
+import pytest
+
+from mono_dataset_code_b200 import api
+
+cv2 = pytest.importorskip("cv2")
+
+
+def scene(rng, h, w, kind):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    if kind == "smooth":
+        img = 128 + 90 * np.sin(xx * 0.07) * np.cos(yy * 0.05)
+    elif kind == "noise":
+        img = rng.integers(0, 256, (h, w)).astype(np.float64)
+    elif kind == "edges":
+        img = ((xx // 13 + yy // 9) % 2) * 255.0
+    else:
+        img = 40 + 0.6 * xx + rng.normal(0, 12, (h, w))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def sequence_of(tmp_path, blobs):
+    os.makedirs(tmp_path / "images", exist_ok=True)
+    with open(tmp_path / "times.txt", "w") as t:
+        for i, b in enumerate(blobs):
+            (tmp_path / "images" / f"{i:05d}.jpg").write_bytes(b)
+            t.write(f"{i} {i * 0.05:.3f} 1.0\n")
+    return api.Sequence(str(tmp_path))
+
+
+CASES = []
+for kind in ("smooth", "noise", "edges", "ramp"):
+    for quality in (35, 90, 100):
+        CASES.append((kind, quality))
+
+
+@pytest.mark.parametrize("size", [(64, 48), (83, 61), (8, 8), (1, 1), (17, 129), (640, 480)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_grey_jpeg_matches_opencv(tmp_path, size):
+    w, h = size
+    rng = np.random.default_rng(w * 1000 + h)
+    blobs, expect = [], []
+    for kind, quality in CASES:
+        img = scene(rng, h, w, kind)
+        for extra in ([], [cv2.IMWRITE_JPEG_OPTIMIZE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 3]):
+            ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality] + extra)
+            assert ok
+            blobs.append(enc.tobytes())
+            expect.append(cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+    seq = sequence_of(tmp_path, blobs)
+    assert seq.getNumImages() == len(blobs)
+    for i, exp in enumerate(expect):
+        got = seq.getImageRaw_internal(i)
+        assert got is not None, f"file {i} rejected"
+        assert got.shape == exp.shape and np.array_equal(got, exp), f"file {i}: {np.count_nonzero(got != exp)} pixels differ"
+
+
+@pytest.mark.parametrize("sampling", ["444", "422", "420", "411", "440"])
+def test_colour_jpeg_read_as_grey_matches_opencv(tmp_path, sampling):
+    """Grey read of a colour file = its luminance component (libjpeg out_color_space = JCS_GRAYSCALE)."""
+    factor = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling, None)
+    if factor is None or not hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        pytest.skip("this OpenCV cannot choose JPEG sampling factors")
+    rng = np.random.default_rng(5)
+    blobs, expect = [], []
+    for (w, h) in ((96, 64), (75, 53), (33, 17)):
+        bgr = np.stack([scene(rng, h, w, k) for k in ("smooth", "noise", "ramp")], axis=-1)
+        for quality in (50, 95):
+            for extra in ([], [cv2.IMWRITE_JPEG_RST_INTERVAL, 2]):
+                ok, enc = cv2.imencode(".jpg", bgr, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, factor] + extra)
+                assert ok
+                blobs.append(enc.tobytes())
+                expect.append(cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+    seq = sequence_of(tmp_path, blobs)
+    for i, exp in enumerate(expect):
+        got = seq.getImageRaw_internal(i)
+        assert got is not None and np.array_equal(got, exp), f"file {i}"
+
+
+def test_unsupported_and_corrupt_files_are_rejected(tmp_path):
+    from mono_dataset_code_b200 import _lib
+    img = scene(np.random.default_rng(1), 40, 56, "smooth")
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    ok2, base = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 80])
+    blob = base.tobytes()
+    seq = sequence_of(tmp_path, [prog.tobytes(), blob[:len(blob) // 3], blob[:2] + b"\x00\x11" + blob[4:]])
+    assert seq.getImageRaw_internal(0) is None and b"baseline only" in _lib.lib.mdc_last_error()
+    assert seq.getImageRaw_internal(2) is None
+    trunc = seq.getImageRaw_internal(1)                     # a truncated scan decodes to something (like libjpeg, with a warning) or fails
+    assert trunc is None or trunc.shape == img.shape
