@@ -105,26 +105,28 @@ const uint8_t kZigZag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4
                              35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 // ---- inverse DCT, accurate integer method (13-bit constants, 2 guard bits between the passes)
+// Temporaries are 64-bit like libjpeg's (its JLONG is `long`), so no input — not even a corrupt one — can overflow.
+typedef int64_t wide;
 constexpr int kConstBits = 13, kPass1Bits = 2;
-constexpr int32_t F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373,
-                  F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819,
-                  F_2_562915447 = 20995, F_3_072711026 = 25172;
-inline int32_t descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
-inline uint8_t clamp_sample(int32_t v) { v += 128; return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+constexpr wide F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373,
+               F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819,
+               F_2_562915447 = 20995, F_3_072711026 = 25172;
+inline wide descale(wide x, int n) { return (x + (wide(1) << (n - 1))) >> n; }      // arithmetic shift (floor), as in libjpeg
+inline uint8_t clamp_sample(wide v) { v += 128; return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
-struct Butterfly { int32_t e0, e1, e2, e3, o0, o1, o2, o3; };      // out[k] = e_k + o_(3-k), out[7-k] = e_k - o_(3-k)
-inline Butterfly idct_1d(int32_t c0, int32_t c1, int32_t c2, int32_t c3, int32_t c4, int32_t c5, int32_t c6, int32_t c7) {
+struct Butterfly { wide e0, e1, e2, e3, o0, o1, o2, o3; };      // out[k] = e_k + o_(3-k), out[7-k] = e_k - o_(3-k)
+inline Butterfly idct_1d(wide c0, wide c1, wide c2, wide c3, wide c4, wide c5, wide c6, wide c7) {
     Butterfly r;
     // even part
-    int32_t z1 = (c2 + c6) * F_0_541196100;
-    const int32_t t2 = z1 + c6 * (-F_1_847759065), t3 = z1 + c2 * F_0_765366865;
-    const int32_t t0 = (c0 + c4) << kConstBits, t1 = (c0 - c4) << kConstBits;
+    wide z1 = (c2 + c6) * F_0_541196100;
+    const wide t2 = z1 + c6 * (-F_1_847759065), t3 = z1 + c2 * F_0_765366865;
+    const wide t0 = (c0 + c4) * (wide(1) << kConstBits), t1 = (c0 - c4) * (wide(1) << kConstBits);
     r.e0 = t0 + t3; r.e3 = t0 - t3; r.e1 = t1 + t2; r.e2 = t1 - t2;
     // odd part
-    int32_t a0 = c7, a1 = c5, a2 = c3, a3 = c1;
+    wide a0 = c7, a1 = c5, a2 = c3, a3 = c1;
     z1 = a0 + a3;
-    int32_t z2 = a1 + a2, z3 = a0 + a2, z4 = a1 + a3;
-    const int32_t z5 = (z3 + z4) * F_1_175875602;
+    wide z2 = a1 + a2, z3 = a0 + a2, z4 = a1 + a3;
+    const wide z5 = (z3 + z4) * F_1_175875602;
     a0 *= F_0_298631336; a1 *= F_2_053119869; a2 *= F_3_072711026; a3 *= F_1_501321110;
     z1 *= -F_0_899976223; z2 *= -F_2_562915447; z3 *= -F_1_961570560; z4 *= -F_0_390180644;
     z3 += z5; z4 += z5;
@@ -135,10 +137,10 @@ inline Butterfly idct_1d(int32_t c0, int32_t c1, int32_t c2, int32_t c3, int32_t
 // coef: dequantised coefficients in natural order; out: 8 rows of 8 samples, `stride` apart.  Columns / rows whose AC terms are all
 // zero take a shortcut that gives exactly what the full butterfly gives for them (dc << 2, resp. (ws0 + 16) >> 5).
 void idct_block(const int32_t coef[64], uint8_t* out, size_t stride) {
-    int32_t ws[64];
+    wide ws[64];
     for (int c = 0; c < 8; ++c) {
         if ((coef[8 + c] | coef[16 + c] | coef[24 + c] | coef[32 + c] | coef[40 + c] | coef[48 + c] | coef[56 + c]) == 0) {
-            const int32_t v = coef[c] * (1 << kPass1Bits);
+            const wide v = wide(coef[c]) * (1 << kPass1Bits);
             ws[c] = ws[8 + c] = ws[16 + c] = ws[24 + c] = ws[32 + c] = ws[40 + c] = ws[48 + c] = ws[56 + c] = v;
             continue;
         }
@@ -150,7 +152,7 @@ void idct_block(const int32_t coef[64], uint8_t* out, size_t stride) {
         ws[24 + c] = descale(b.e3 + b.o0, s);  ws[32 + c] = descale(b.e3 - b.o0, s);
     }
     for (int r = 0; r < 8; ++r) {
-        const int32_t* w = ws + 8 * r;
+        const wide* w = ws + 8 * r;
         uint8_t* o = out + r * stride;
         if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {
             memset(o, clamp_sample(descale(w[0], kPass1Bits + 3)), 8);
@@ -228,6 +230,7 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
             width = be16(seg + 3);
             const int nc = seg[5];
             if ((nc != 1 && nc != 3) || seg_len < 6 + 3 * nc || width < 1 || height < 1) return fail("unsupported JPEG frame (components / size)");
+            if (static_cast<long long>(width) * height > (1LL << 28)) return fail("JPEG frame larger than 2^28 pixels");
             comps.resize(static_cast<size_t>(nc));
             for (int c = 0; c < nc; ++c) {
                 comps[c].id = seg[6 + 3 * c];
@@ -244,6 +247,7 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
             restart_interval = be16(seg);
         } else if (marker == 0xda) {                           // SOS: the one scan of a baseline file
             if (!have_frame) return fail("scan before frame header");
+            if (seg_len < 1) return fail("bad scan header");
             const int ns = seg[0];
             if (ns != static_cast<int>(comps.size()) || seg_len < 1 + 2 * ns + 3) return fail("non-interleaved multi-scan JPEG is not supported");
             for (int k = 0; k < ns; ++k) {
@@ -295,8 +299,9 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                                 // DC
                                 const int t = decode_symbol(br, dc[comp.td]);
                                 if (t < 0 || t > 15) return fail("corrupt JPEG data (DC)");
-                                comp.pred += extend(br.bits(t), t);
-                                if (c == 0) { memset(coef, 0, sizeof coef); coef[0] = comp.pred * quant[Y.tq][0]; }
+                                // libjpeg stores coefficients as 16-bit JCOEF: the running DC value wraps there (only corrupt data gets that far)
+                                comp.pred = static_cast<int16_t>(static_cast<uint32_t>(comp.pred) + static_cast<uint32_t>(extend(br.bits(t), t)));
+                                if (c == 0) { memset(coef, 0, sizeof coef); coef[0] = comp.pred * static_cast<int32_t>(quant[Y.tq][0]); }
                                 // AC
                                 for (int k = 1; k < 64;) {
                                     const int rs = decode_symbol(br, ac[comp.ta]);
@@ -310,7 +315,7 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                                     k += r;
                                     if (k > 63) return fail("corrupt JPEG data (run past the block)");
                                     const int v = extend(br.bits(s), s);
-                                    if (c == 0) coef[kZigZag[k]] = v * quant[Y.tq][kZigZag[k]];
+                                    if (c == 0) coef[kZigZag[k]] = v * static_cast<int32_t>(quant[Y.tq][kZigZag[k]]);
                                     ++k;
                                 }
                                 if (c == 0) {

@@ -50,6 +50,7 @@ struct mdc_seq {
     std::string path;                  // with trailing '/'
     bool zipped = false;
     int zip_fd = -1;
+    uint64_t zip_bytes = 0;            // size of the archive: no entry can be larger (compressed)
     std::vector<std::string> files;    // full paths (folder) or entry names (zip), sorted
     std::vector<ZipEntry> entries;     // parallel to files when zipped
     std::vector<double> timestamps;
@@ -78,6 +79,7 @@ bool read_zip_directory(mdc_seq* s, const std::string& archive) {
     if (s->zip_fd < 0) { mdc_set_error("cannot open archive %s", archive.c_str()); return false; }
     struct stat st;
     if (fstat(s->zip_fd, &st) != 0 || st.st_size < 22) { mdc_set_error("%s: not a zip archive", archive.c_str()); return false; }
+    s->zip_bytes = static_cast<uint64_t>(st.st_size);
     // end-of-central-directory record: last 22 .. 22+65535 bytes
     const size_t tail = static_cast<size_t>(std::min<off_t>(st.st_size, 22 + 65535));
     std::vector<uint8_t> buf(tail);
@@ -121,6 +123,8 @@ bool read_zip_entry(const mdc_seq* s, const ZipEntry& e, std::vector<uint8_t>* o
     uint8_t lh[30];
     if (!pread_all(s->zip_fd, lh, 30, e.local_offset) || le32(lh) != 0x04034b50u) { mdc_set_error("%s: bad local header", e.name.c_str()); return false; }
     const off_t data = static_cast<off_t>(e.local_offset) + 30 + le16(lh + 26) + le16(lh + 28);
+    // a corrupt directory must not make us allocate gigabytes: entries cannot be larger than the archive (deflate expands < 1100x)
+    if (e.comp_size > s->zip_bytes || (e.size >> 10) > e.comp_size + 1024u) { mdc_set_error("%s: implausible entry size", e.name.c_str()); return false; }
     out->resize(e.size);
     if (e.method == 0) {
         if (e.comp_size != e.size || (e.size && !pread_all(s->zip_fd, out->data(), e.size, data))) { mdc_set_error("%s: truncated stored entry", e.name.c_str()); return false; }

@@ -91,3 +91,26 @@ def test_unsupported_and_corrupt_files_are_rejected(tmp_path):
     assert seq.getImageRaw_internal(2) is None
     trunc = seq.getImageRaw_internal(1)                     # a truncated scan decodes to something (like libjpeg, with a warning) or fails
     assert trunc is None or trunc.shape == img.shape
+
+
+def test_random_corruption_never_crashes(tmp_path):
+    """Bit flips and truncations anywhere in the file: the decoder either returns an image of the declared size or an error."""
+    rng = np.random.default_rng(11)
+    img = scene(rng, 48, 64, "ramp")
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 75, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    base = bytearray(enc.tobytes())
+    blobs = []
+    for k in range(300):
+        b = bytearray(base)
+        for _ in range(rng.integers(1, 4)):
+            b[rng.integers(2, len(b))] ^= 1 << rng.integers(0, 8)
+        if k % 5 == 0:
+            b = b[: rng.integers(4, len(b))]
+        blobs.append(bytes(b))
+    seq = sequence_of(tmp_path, blobs)
+    shapes = set()
+    for i in range(len(blobs)):
+        got = seq.getImageRaw_internal(i)
+        if got is not None:
+            shapes.add(got.shape)
+    assert (48, 64) in shapes            # most single-bit flips in the entropy data still decode
