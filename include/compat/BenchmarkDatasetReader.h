@@ -9,6 +9,10 @@
 // undistort<float> on the CPU (:222-223).  Here the raw 8-bit frame goes to the GPU once and the whole mode
 // switch of :210-241 is ONE fused sm_100a kernel launch (mdc_prepare_batch_host) whose result is bit-identical
 // to the reference's; all four calibration tables live in one device context owned by the reader.
+//
+// Define MDC_NATIVE_SEQUENCE_READER before including this header to drop the libzip and cv::imread/imdecode dependencies as
+// well: folder listing, images.zip, times.txt and frame decode (baseline JPEG, grey PNG, PGM -> the bytes cv::imread would
+// return) then come from libmdc_b200's own sequence reader (mdc_seq_*); cv::Mat is still the frame type.
 #pragma once
 #include <algorithm>
 #include <cassert>
@@ -24,7 +28,9 @@
 #include "FOVUndistorter.h"
 #include "PhotometricUndistorter.h"
 
+#ifndef MDC_NATIVE_SEQUENCE_READER
 #include "zip.h"
+#endif
 
 // Sorted list of the entries of `dir` (full paths appended to `files`); -1 if it cannot be opened.
 inline int getdir(std::string dir, std::vector<std::string> &files)
@@ -52,17 +58,33 @@ public:
 		: width(0), height(0), widthOrg(0), heightOrg(0), path(folder), isZipped(false),
 		  undistorter(0), photoUndistorter(0), ziparchive(0), deviceContext(0)
 	{
+#ifdef MDC_NATIVE_SEQUENCE_READER
+		if(mdc_seq_open(path.c_str(), &ziparchive) != MDC_OK) exit(1);      // the reference exits when images.zip cannot be read
+		isZipped = mdc_seq_is_zipped(ziparchive) != 0;
+		for(int i = 0; i < mdc_seq_num_images(ziparchive); i++)
+		{
+			files.push_back(mdc_seq_name(ziparchive, i));
+			timestamps.push_back(mdc_seq_timestamp(ziparchive, i));
+			exposures.push_back(mdc_seq_exposure(ziparchive, i));
+		}
+		loadCalibration();
+#else
 		locateImages();
 		loadTimestamps(path + "times.txt");
 		loadCalibration();
 		printf("Dataset %s: Got %d files!\n", path.c_str(), getNumImages());
+#endif
 	}
 	~DatasetReader()
 	{
 		if(deviceContext != 0) mdc_ctx_destroy(deviceContext);
 		delete undistorter;
 		delete photoUndistorter;
+#ifdef MDC_NATIVE_SEQUENCE_READER
+		mdc_seq_close(ziparchive);
+#else
 		if(ziparchive != 0) zip_close(ziparchive);
+#endif
 	}
 
 	UndistorterFOV* getUndistorter() { return undistorter; }
@@ -106,13 +128,26 @@ public:
 
 	cv::Mat getImageRaw_internal(int id)
 	{
+#ifdef MDC_NATIVE_SEQUENCE_READER
+		// frames normally have the calibrated size: decode straight into a Mat of that size, re-decode only if it differs
+		int w = 0, h = 0;
+		cv::Mat frame(heightOrg, widthOrg, CV_8U);
+		int status = mdc_seq_read_gray8(ziparchive, id, frame.data, (size_t)widthOrg * heightOrg, &w, &h);
+		if(status == MDC_OK && w == widthOrg && h == heightOrg) return frame;
+		if(w < 1 || h < 1) return cv::Mat();                 // undecodable: empty, like cv::imread
+		cv::Mat other(h, w, CV_8U);
+		status = mdc_seq_read_gray8(ziparchive, id, other.data, (size_t)w * h, &w, &h);
+		return status == MDC_OK ? other : cv::Mat();
+#else
 		if(!isZipped) return cv::imread(files[id], CV_LOAD_IMAGE_GRAYSCALE);
 		long bytes = readArchiveEntry(id);
 		return cv::imdecode(cv::Mat((int)bytes, 1, CV_8U, &databuffer[0]), CV_LOAD_IMAGE_GRAYSCALE);
+#endif
 	}
 
 private:
 	static bool inRange(int id, size_t n) { return id >= 0 && id < (int)n; }
+#ifndef MDC_NATIVE_SEQUENCE_READER
 
 	// images/ folder if it has entries, else images.zip (exit(1) if that cannot be opened, like the reference)
 	void locateImages()
@@ -142,23 +177,6 @@ private:
 		}
 		printf("got %d entries and %d files from zipfile!\n", numEntries, (int)files.size());
 		std::sort(files.begin(), files.end());
-	}
-
-	// calibration models on the host + one device context holding all four tables for the fused kernel
-	void loadCalibration()
-	{
-		undistorter = new UndistorterFOV((path + "camera.txt").c_str());
-		widthOrg = undistorter->getInputDims()[0];
-		heightOrg = undistorter->getInputDims()[1];
-		width = undistorter->getOutputDims()[0];
-		height = undistorter->getOutputDims()[1];
-		photoUndistorter = new PhotometricUndistorter(path + "pcalib.txt", path + "vignette.png", widthOrg, heightOrg);
-		if(mdc_ctx_create(UndistorterFOV::b200Device(), undistorter->b200Model(), photoUndistorter->b200Model(),
-				&deviceContext) != MDC_OK)
-		{
-			printf("DatasetReader: cannot create the B200 device context: %s\n", mdc_last_error());
-			deviceContext = 0;
-		}
 	}
 
 	// inflate entry `id` into databuffer; first guess 6 bytes/pixel, one retry at 60 bytes/pixel, then give up
@@ -203,6 +221,25 @@ private:
 		}
 	}
 
+#endif
+
+	// calibration models on the host + one device context holding all four tables for the fused kernel
+	void loadCalibration()
+	{
+		undistorter = new UndistorterFOV((path + "camera.txt").c_str());
+		widthOrg = undistorter->getInputDims()[0];
+		heightOrg = undistorter->getInputDims()[1];
+		width = undistorter->getOutputDims()[0];
+		height = undistorter->getOutputDims()[1];
+		photoUndistorter = new PhotometricUndistorter(path + "pcalib.txt", path + "vignette.png", widthOrg, heightOrg);
+		if(mdc_ctx_create(UndistorterFOV::b200Device(), undistorter->b200Model(), photoUndistorter->b200Model(),
+				&deviceContext) != MDC_OK)
+		{
+			printf("DatasetReader: cannot create the B200 device context: %s\n", mdc_last_error());
+			deviceContext = 0;
+		}
+	}
+
 	std::vector<std::string> files;
 	std::vector<double> timestamps;
 	std::vector<float> exposures;
@@ -213,7 +250,11 @@ private:
 
 	UndistorterFOV* undistorter;
 	PhotometricUndistorter* photoUndistorter;
+#ifdef MDC_NATIVE_SEQUENCE_READER
+	mdc_seq* ziparchive;
+#else
 	zip_t* ziparchive;
+#endif
 	std::vector<char> databuffer;
 	mdc_ctx* deviceContext;
 };

@@ -113,3 +113,51 @@ def test_compat_classes_match_oracle_on_gpu(compat_exe, port, tmp_path):
     ex_, ey_ = f.distort(np.array([0.0, 10.5, ow], np.float32), np.array([0.0, 20.25, oh], np.float32))
     assert_bits_equal(xs, ex_, "distortCoordinates x")
     assert_bits_equal(ys, ey_, "distortCoordinates y")
+
+
+@pytest.mark.parametrize("zipped", [False, True], ids=["folder", "zip"])
+def test_native_sequence_reader_mode_of_the_compat_header(tmp_path, zipped):
+    """MDC_NATIVE_SEQUENCE_READER: DatasetReader without libzip / cv::imread — file order, times.txt, JPEG / PNG / PGM frames."""
+    import zipfile
+    cv2 = pytest.importorskip("cv2")
+    exe = compile_cpp(os.path.join(ROOT, "tests", "cpp", "native_reader_check.cpp"), str(tmp_path / "native_reader_check"))
+    iw, ih, n = 96, 64, 7
+    d = tmp_path / "seq"
+    S.write_dataset_dir(str(d), iw, ih, iw, ih, "crop")
+    stage = d / ("stage" if zipped else "images")
+    os.makedirs(stage)
+    expect = []
+    for i in range(n):
+        fr = S.frame(i, iw, ih, ["uniform", "speckle", "gradient"][i % 3]).reshape(ih, iw)
+        if i % 3 == 0:
+            ok, enc = cv2.imencode(".jpg", fr, [cv2.IMWRITE_JPEG_QUALITY, 85])
+            (stage / f"{i:05d}.jpg").write_bytes(enc.tobytes())
+            expect.append(cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+        elif i % 3 == 1:
+            S.write_png_gray(str(stage / f"{i:05d}.png"), fr)
+            expect.append(fr)
+        else:
+            S.write_pgm(str(stage / f"{i:05d}.pgm"), fr)
+            expect.append(fr)
+    if zipped:
+        with zipfile.ZipFile(d / "images.zip", "w", zipfile.ZIP_DEFLATED) as z:
+            for nm in sorted(os.listdir(stage), reverse=True):
+                z.write(stage / nm, nm)
+    with open(d / "times.txt", "w") as t:
+        for i in range(n):
+            t.write(f"{i} {5.25 + i:.6f} {0.75 * (i + 1):.4f}\n")
+    out = tmp_path / "dump.bin"
+    r = subprocess.run([exe, str(d) + "/", str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    blob = out.read_bytes()
+    (count,) = struct.unpack_from("i", blob, 0)
+    assert count == n
+    pos = 4
+    for i in range(n):
+        stamp, exposure, rows, cols = struct.unpack_from("=dfii", blob, pos)
+        pos += struct.calcsize("=dfii")
+        assert stamp == float(f"{5.25 + i:.6f}") and exposure == np.float32(f"{0.75 * (i + 1):.4f}")
+        assert (rows, cols) == (ih, iw)
+        px = np.frombuffer(blob, np.uint8, rows * cols, pos).reshape(rows, cols)
+        pos += rows * cols
+        assert np.array_equal(px, expect[i]), f"frame {i}"
