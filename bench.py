@@ -161,6 +161,24 @@ def cpu_baseline(files):
             "single_thread": {"value": n1 / s1, "frames": n1, "unmap_ms": 1e3 * stages[0] / n1, "undistort_ms": 1e3 * stages[1] / n1}}
 
 
+def cpu_calibrator_sample():
+    """The oracle's plain-C restatement of the responseCalib passes (main_responseCalib.cpp:283-346, one thread, like the reference)
+    on a bounded sample: n = 1000 exposures x 20 000 pixels, scaled to the 1 MP of BASELINE configs[4]."""
+    from oracle import loader
+    port = loader.PortOracle()
+    rng = np.random.default_rng(7)
+    n, npix, full = 1000, 20000, 1000 * 1000
+    data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+    t = np.linspace(0.05, 20.0, n)
+    G = np.linspace(0.0, 255.0, 256)
+    t0 = time.perf_counter(); E = port.estep(data, t, G); t1 = time.perf_counter()
+    port.gstep(data, t, E); t2 = time.perf_counter()
+    port.rmse(data, t, G, E); t3 = time.perf_counter()
+    k = full / npix
+    return {"kind": "port", "cores": 1, "sample": f"n={n} x {npix} pixels, scaled x{k:.0f} to 1 MP",
+            "estep_ms_per_pass": 1e3 * (t1 - t0) * k, "gstep_ms_per_pass": 1e3 * (t2 - t1) * k, "rmse_ms_per_pass": 1e3 * (t3 - t2) * k}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -367,6 +385,11 @@ def run_gpu_arm(args):
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c5_estep": estep}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(files)
+            if estep is not None:
+                try:
+                    estep["cpu_baseline"] = cpu_calibrator_sample()
+                except Exception as exc:      # the headline line must not depend on this extra
+                    estep["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
