@@ -180,3 +180,18 @@ def test_argument_validation_of_the_device_entry_points_needs_no_gpu(dataset_dir
     assert "ERROR: invalid UndistorterFOV!" in capfd.readouterr().out
     L.mdc_fov_destroy(bad)
     assert L.mdc_atanf_device(null, null, 3, 0, null) == 1
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/mdc_b200.h is the FFI boundary: it must compile as C99 (no C++ types, no torch types) and link from a C program."""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "mdc_b200.h"\n#include <stdio.h>\nint main(void) { mdc_fov* f = 0; printf("%s %d\\n", mdc_version(), mdc_fov_is_valid(f)); return 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "mono_dataset_code_b200", "lib")
+    exe = tmp_path / "c_abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"), str(src), "-o", str(exe),
+                        "-L" + libdir, "-lmdc_b200", "-Wl,-rpath," + libdir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("mdc_b200")
