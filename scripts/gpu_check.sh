@@ -17,7 +17,6 @@ echo "== sweep"; : > gpurun_out/sweep.jsonl
 for cf in 4 8 16 32 64 256; do for cps in 2 3; do
   MDC_CHUNK_FRAMES=$cf MDC_CTAS_PER_SM=$cps timeout 300 python bench.py --steps 20 --warmup 3 --only-kernel 2>/dev/null | tail -1 >> gpurun_out/sweep.jsonl
 done; done
-for co in 4 16; do MDC_COST_IN=1 MDC_COST_OUT=$co timeout 300 python bench.py --steps 20 --warmup 3 --only-kernel 2>/dev/null | tail -1 >> gpurun_out/sweep.jsonl; done
 cat gpurun_out/sweep.jsonl | cut -c1-300
 fi
 if has ncu; then
