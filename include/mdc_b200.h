@@ -188,8 +188,8 @@ float mdc_seq_exposure(const mdc_seq* s, int id);         /* getExposure(), :179
  * out may be NULL to query the size only.  MDC_ERR_FORMAT if the frame cannot be decoded. */
 int mdc_seq_read_gray8(const mdc_seq* s, int id, uint8_t* out, size_t capacity, int* w, int* h);
 /* getImage(id, flags...) for id in [first, first+count) into HOST level buffers (level l: [count][(w>>l)*(h>>l)] floats, as for
- * mdc_prepare_batch_host): `threads` host threads (0 = all) decode the next 32 frames into pinned memory while the current 32 go
- * through H2D -> fused kernel -> D2H.  A frame of the wrong size or an undecodable one stops the call with MDC_ERR_FORMAT
+ * mdc_prepare_batch_host): `threads` host threads (0 = all) decode the next chunk (one frame per thread, 32..256 frames) into pinned
+ * memory while the current chunk goes through H2D -> fused kernel -> D2H.  A frame of the wrong size or an undecodable one stops the call with MDC_ERR_FORMAT
  * (the reference prints and returns 0 for that frame, :194-205). */
 int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int count, unsigned flags, float* const* h_out_levels, int levels, int threads);
 

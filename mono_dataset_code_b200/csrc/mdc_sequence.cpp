@@ -4,8 +4,8 @@
 //   mdc_seq_open      images/ folder (sorted) or, if that is empty, images.zip (central directory, sorted names); times.txt
 //   mdc_seq_read_gray8 getImageRaw_internal with CV_LOAD_IMAGE_GRAYSCALE: 8/16-bit grey PNG (16 -> 8 bit by dropping the low byte, as
 //                     OpenCV's reader does), binary PGM, baseline JPEG (mdc_jpeg.cpp) - the same bytes as cv::imread returns.
-//   mdc_seq_prepare   getImage for a range of frames: worker threads decode chunk k+1 into pinned memory while chunk k goes
-//                     through mdc_prepare_batch_host (H2D, fused kernel, D2H on three streams).
+//   mdc_seq_prepare   getImage for a range of frames: worker threads decode chunk k+1 (32..256 frames, one per thread) into
+//                     pinned memory while chunk k goes through mdc_prepare_batch_host (H2D, fused kernel, D2H on three streams).
 //
 // The zip reader handles what `zip` / Python's zipfile / the TUM archives produce: stored and deflated entries, no encryption,
 // no zip64 (archives < 4 GB, < 65535 entries), CRC-32 verified.
@@ -258,7 +258,8 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     for (int l = 0; l < levels; ++l)      // level l of getImage's result: (w >> l) x (h >> l), mdc_prepare_batch
         level_px[static_cast<size_t>(l)] = static_cast<size_t>((rectify ? out_w : in_w) >> l) * static_cast<size_t>((rectify ? out_h : in_h) >> l);
     if (threads < 1) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
-    const int chunk = 32;
+    // one frame per decode thread and chunk, so that a JPEG sequence keeps all of them busy; 32..256 frames per chunk
+    const int chunk = std::min(256, std::max(32, threads));
     void* stage[2] = {nullptr, nullptr};
     for (int b = 0; b < 2; ++b)
         if (mdc_host_alloc(&stage[b], static_cast<size_t>(chunk) * n_in) != MDC_OK) { if (stage[0]) mdc_host_free(stage[0]); return MDC_ERR_CUDA; }
