@@ -376,7 +376,8 @@ def run_gpu_arm(args):
                            "frames_per_step_per_gpu": B, "flags": "rectify|removeGamma|removeVignette", "pyramid_levels": 1,
                            "parallelism": f"frame-sharded dp{world}, tables NCCL-broadcast at init, no steady-state collective",
                            "l2_policy": f"inputs larger than L2 ({B * n_in >> 20} MiB in, {B * n_out * 4 >> 20} MiB out per step)",
-                           "loader": {None: "auto(tma)", 1: "tma", 0: "ldg"}[args.tma]},
+                           "loader": ({0: "ldg", 1: "tma", 2: "tex"}[args.tma] if args.tma is not None else
+                                      "auto(" + ("tex" if ctx.loader_usable("tex") else "tma" if ctx.loader_usable("tma") else "ldg") + ")")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (TRAFFIC["dram_bytes_per_frame"] * B / 1e9 if TRAFFIC else None),
                              "traffic_note": (TRAFFIC["note"] if TRAFFIC else "no ncu capture committed"),
@@ -403,7 +404,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU (device-resident)")
     ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
-    ap.add_argument("--tma", type=int, default=None, help="force the input loader: 1 = TMA, 0 = LDG")
+    ap.add_argument("--tma", "--loader", type=int, default=None, dest="tma",
+                    help="force K1's input loader: 2 = texture gather, 1 = TMA, 0 = LDG (default: auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--levels", type=int, default=1, help="pyramid levels for --only-kernel sweeps")
     ap.add_argument("--no-estep", action="store_true", help="skip the configs[4] E-step leg")

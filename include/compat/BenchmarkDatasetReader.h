@@ -122,7 +122,12 @@ public:
 				? mdc_prepare_batch_host(deviceContext, imageRaw.data, 1, mode, level0, 1) : MDC_ERR_CUDA;
 		// an invalid rectifier leaves the image unwritten, like the reference (undistort is then a no-op)
 		if(status != MDC_OK && status != MDC_ERR_INVALID_OBJECT)
+		{
+			// no device / CUDA failure: the reference has no such state; never hand out an image that was not computed
 			printf("DatasetReader::getImage: %s\n", deviceContext != 0 ? mdc_last_error() : "no device context");
+			delete result;
+			return 0;
+		}
 		return result;
 	}
 

@@ -136,8 +136,17 @@ int mdc_ctx_device_tables(const mdc_ctx* c, const float** d_remap_x, const float
 int mdc_ctx_level_dims(const mdc_ctx* c, int level, int* w, int* h);
 /* Number of kernel launches issued through this context so far (bench bookkeeping). */
 long long mdc_ctx_launch_count(const mdc_ctx* c);
-/* Tuning knobs (0 keeps the default): use_tma = -1 auto / 0 off / 1 on. */
+/* Tuning knobs.  use_tma selects how the fused kernel K1 fetches the input taps: -1 = auto (the fastest loader usable for this
+ * geometry), or one of MDC_LOADER_*; a loader that cannot describe the geometry / pointer makes the per-frame calls fail with
+ * MDC_ERR_UNSUPPORTED (LDG always works).  ctas_per_sm: 0 keeps the default. */
+#define MDC_LOADER_LDG 0   /* register-staged global loads into shared memory (any row pitch) */
+#define MDC_LOADER_TMA 1   /* cp.async.bulk.tensor boxes into a shared-memory ring (row pitch multiple of 16 bytes) */
+#define MDC_LOADER_TEX 2   /* texture gather (tld4) straight from the frames: taps on the TEX pipe, look-ups + stores on the LSU pipe
+                              (row pitch multiple of the device's texture pitch alignment; enabled by a bit-exactness self-check
+                              against the other loaders when the context is created) */
 int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm);
+/* 1 if `loader` (MDC_LOADER_*) can be used with this context's geometry on this device, else 0. */
+int mdc_ctx_loader_usable(const mdc_ctx* c, int loader);
 
 /* -------------------------------------------------------------------------------------
  * Device-resident per-frame operators (all pointers are DEVICE pointers; `stream` is a

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mdc_ctx_level_dims": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mdc_ctx_launch_count": (C.c_longlong, [_vp]),
     "mdc_ctx_configure": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "mdc_ctx_loader_usable": (C.c_int, [_vp, C.c_int]),
     "mdc_unmap_u8": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_uint, _vp]),
     "mdc_undistort_u8": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "mdc_undistort_f32": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

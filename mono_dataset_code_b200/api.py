@@ -242,8 +242,18 @@ class Context:
     def __del__(self):
         self.close()
 
+    LOADERS = {"auto": -1, "ldg": 0, "tma": 1, "tex": 2}
+
     def configure(self, use_tma: int = -1, ctas_per_sm: int = 0):
+        """use_tma: the K1 input loader, -1 auto / 0 LDG / 1 TMA / 2 texture gather (MDC_LOADER_*), or its name."""
+        if isinstance(use_tma, str):
+            use_tma = self.LOADERS[use_tma]
         check(lib.mdc_ctx_configure(self._h, use_tma, ctas_per_sm), "mdc_ctx_configure")
+
+    def loader_usable(self, loader) -> bool:
+        if isinstance(loader, str):
+            loader = self.LOADERS[loader]
+        return bool(lib.mdc_ctx_loader_usable(self._h, loader))
 
     @property
     def launch_count(self) -> int:

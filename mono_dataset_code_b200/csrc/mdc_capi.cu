@@ -50,6 +50,7 @@ constexpr int kMapSlots = 8;        // host-side cache of encoded descriptor set
 constexpr int kHostPipeDepth = 3;   // host-buffer pipeline: chunks in flight
 constexpr int kCounterRing = 64;
 constexpr int kMaxStagedPx = 8192;  // largest staged box (pixels, height rounded to 8): 32 KB float tile
+constexpr int kTexSlots = 32;       // host-side cache of texture-object sets, keyed by (frames ptr, n_frames, chunk)
 
 }  // namespace
 
@@ -73,8 +74,15 @@ struct mdc_ctx {
     const void* map_key_ptr[kMapSlots] = {};
     int map_key_frames[kMapSlots] = {};
     int map_next = 0;
-    // knobs
+    // texture-gather loader: device limits, self-check verdict, cache of texture-object sets (one object per chunk of frames)
+    int tex_max_rows = 0, tex_max_width = 0, tex_pitch_align = 32, tex_base_align = 512;
+    bool tex_ok = false;                 // the context-creation self-check found the texture path bit-identical to the staged path
+    struct TexEntry { const void* ptr = nullptr; int n_frames = 0, chunk = 0; std::vector<cudaTextureObject_t> objs; };
+    TexEntry tex_cache[kTexSlots];
+    int tex_next = 0;
+    // knobs (loader: -1 auto, 0 LDG, 1 TMA, 2 texture gather)
     int use_tma = -1, ctas_per_sm = 0, chunk_frames = 0, tma_stages = 0;
+    int tex_tiles_per_cta = 2, tex_prefetch = 0, k1_study = kStudyAll;
     // streams + host pipeline scratch
     cudaStream_t stream = nullptr;
     cudaStream_t pipe_stream[kHostPipeDepth] = {nullptr, nullptr, nullptr};
@@ -236,6 +244,83 @@ int ctx_common_init(mdc_ctx* c, int device) {
     if (e) c->chunk_frames = atoi(e);
     e = getenv("MDC_TMA_STAGES");
     if (e) c->tma_stages = atoi(e);
+    e = getenv("MDC_TEX_TILES");
+    if (e) c->tex_tiles_per_cta = std::max(1, atoi(e));
+    e = getenv("MDC_TEX_PREFETCH");
+    if (e) c->tex_prefetch = atoi(e) != 0;
+    e = getenv("MDC_K1_STUDY");
+    if (e) c->k1_study = atoi(e) & kStudyAll;
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    // texture gather has its own (smaller) size limit; pitch-2D linear textures have one too
+    c->tex_max_width = std::min(prop.maxTexture2DGather[0], prop.maxTexture2DLinear[0]);
+    c->tex_max_rows = std::min(prop.maxTexture2DGather[1], prop.maxTexture2DLinear[1]);
+    e = getenv("MDC_TEX_MAX_ROWS");
+    if (e) c->tex_max_rows = atoi(e);
+    c->tex_pitch_align = static_cast<int>(prop.texturePitchAlignment);
+    c->tex_base_align = static_cast<int>(prop.textureAlignment);
+    return MDC_OK;
+}
+
+// ---- texture-gather loader plumbing -------------------------------------------------------------------------------
+// Frames per chunk (= per texture object) for `frames`: as many as the gather height limit allows (at most `want`), such that
+// every chunk starts on a texture-aligned address.  0 = this geometry / pointer cannot use the texture path.
+int tex_chunk_frames(const mdc_ctx* c, const uint8_t* frames, int want) {
+    if (c->in_w % c->tex_pitch_align != 0 || c->in_w > c->tex_max_width || c->in_h < 2) return 0;
+    if (reinterpret_cast<uintptr_t>(frames) % static_cast<uintptr_t>(c->tex_base_align) != 0) return 0;
+    const long long frame_bytes = static_cast<long long>(c->in_w) * c->in_h;
+    for (int n = std::min(want, c->tex_max_rows / c->in_h); n >= 1; --n)
+        if ((frame_bytes * n) % c->tex_base_align == 0) return n;
+    return 0;
+}
+
+void tex_entry_release(mdc_ctx::TexEntry& e) {
+    for (cudaTextureObject_t t : e.objs) cudaDestroyTextureObject(t);
+    e.objs.clear();
+    e.ptr = nullptr;
+}
+
+// texture objects for `frames` ([n_frames][H][W] u8) cut into chunks of `chunk` frames; cached on the host
+int get_textures(mdc_ctx* c, const uint8_t* frames, int n_frames, int chunk, const std::vector<cudaTextureObject_t>** out) {
+    for (int s = 0; s < kTexSlots; ++s) {
+        mdc_ctx::TexEntry& e = c->tex_cache[s];
+        if (e.ptr == frames && e.n_frames == n_frames && e.chunk == chunk) { *out = &e.objs; return MDC_OK; }
+    }
+    mdc_ctx::TexEntry& e = c->tex_cache[c->tex_next];
+    c->tex_next = (c->tex_next + 1) % kTexSlots;
+    if (e.ptr) {                       // evicting: a launch that still reads these objects may be in flight on any stream
+        CU_CHECK(cudaDeviceSynchronize());
+        tex_entry_release(e);
+    }
+    const int n_chunks = (n_frames + chunk - 1) / chunk;
+    const size_t frame_bytes = static_cast<size_t>(c->in_w) * c->in_h;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int nf = std::min(chunk, n_frames - k * chunk);
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = const_cast<uint8_t*>(frames) + static_cast<size_t>(k) * chunk * frame_bytes;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        rd.res.pitch2D.width = static_cast<size_t>(c->in_w);
+        rd.res.pitch2D.height = static_cast<size_t>(c->in_h) * nf;
+        rd.res.pitch2D.pitchInBytes = static_cast<size_t>(c->in_w);
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t t = 0;
+        cudaError_t err = cudaCreateTextureObject(&t, &rd, &td, nullptr);
+        if (err != cudaSuccess) {
+            mdc_set_error("cudaCreateTextureObject failed: %s (chunk %d, %d x %d rows)", cudaGetErrorString(err), k, c->in_w, c->in_h * nf);
+            tex_entry_release(e);
+            return MDC_ERR_CUDA;
+        }
+        e.objs.push_back(t);
+    }
+    e.ptr = frames; e.n_frames = n_frames; e.chunk = chunk;
+    *out = &e.objs;
     return MDC_OK;
 }
 
@@ -290,8 +375,67 @@ UnmapFlags sanitise(const mdc_ctx* c, unsigned flags) {
     return u;
 }
 
+// levels beyond the fused epilogue: stand-alone K2 chain, two levels per launch where possible
+int run_deep_levels(mdc_ctx* c, int n_frames, float* const* d_out_levels, int in_kernel, int levels, cudaStream_t stream) {
+    for (int l = in_kernel; l < levels;) {
+        const int sw = c->out_w >> (l - 1), sh = c->out_h >> (l - 1);
+        if (l + 1 < levels) {
+            CU_CHECK(launch_pyr_down2(d_out_levels[l - 1], sw, sh, d_out_levels[l], d_out_levels[l + 1], n_frames, stream));
+            l += 2;
+        } else {
+            CU_CHECK(launch_pyr_down(d_out_levels[l - 1], sw, sh, d_out_levels[l], n_frames, stream));
+            l += 1;
+        }
+        c->launches++;
+    }
+    return MDC_OK;
+}
+
+// K1 through the texture-gather loader.  One launch covers up to kMaxTex chunks (= texture objects).
+int run_fused_tex(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chunk, UnmapFlags u, float* const* d_out_levels, int levels,
+                  cudaStream_t stream) {
+    const std::vector<cudaTextureObject_t>* objs = nullptr;
+    int rc = get_textures(c, d_frames, n_frames, chunk, &objs);
+    if (rc != MDC_OK) return rc;
+    const int in_kernel = std::min(levels, kInKernelLevels);
+    const int n_chunks = static_cast<int>(objs->size());
+    const int min_ctas = c->ctas_per_sm > 0 ? std::min(std::max(c->ctas_per_sm, 2), 4) : 3;
+    for (int c0 = 0; c0 < n_chunks; c0 += kMaxTex) {
+        const int nc = std::min(kMaxTex, n_chunks - c0);
+        const int f0 = c0 * chunk, nf = std::min(n_frames - f0, nc * chunk);
+        FusedParams p;
+        memset(&p, 0, sizeof p);
+        p.frames = d_frames + static_cast<size_t>(f0) * c->in_w * c->in_h; p.n_frames = nf;
+        p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h;
+        p.remap_x = c->d_rx; p.remap_y = c->d_ry; p.vinv = c->d_vinv; p.ginv = c->d_ginv;
+        p.tiles = c->d_tiles; p.work_counter = nullptr;
+        p.tiles_x = c->tiles_x; p.n_tiles = static_cast<int>(c->tiles.size());
+        p.levels = in_kernel;
+        for (int l = 0; l < in_kernel; ++l) {
+            p.lw[l] = c->out_w >> l; p.lh[l] = c->out_h >> l;
+            p.out[l] = d_out_levels[l] ? d_out_levels[l] + static_cast<size_t>(f0) * p.lw[l] * p.lh[l] : nullptr;
+        }
+        p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
+        p.chunk_frames = chunk;
+        p.tiles_per_cta = c->tex_tiles_per_cta;
+        TexSet texs;
+        memset(&texs, 0, sizeof texs);
+        for (int k = 0; k < nc; ++k) texs.tex[k] = (*objs)[c0 + k];
+        CU_CHECK(launch_fused_tex(p, texs, nc, min_ctas, c->tex_prefetch != 0, c->k1_study, stream));
+        c->launches++;
+    }
+    return run_deep_levels(c, n_frames, d_out_levels, in_kernel, levels, stream);
+}
+
+// loader: -1 = the context's setting (auto: texture gather if its self-check passed, else TMA, else LDG)
 int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, float* const* d_out_levels, int levels,
-              cudaStream_t stream) {
+              cudaStream_t stream, int loader = -1) {
+    if (loader < 0) loader = c->use_tma;
+    if (loader == 2 || (loader < 0 && c->tex_ok)) {
+        const int chunk = tex_chunk_frames(c, d_frames, c->chunk_frames > 0 ? c->chunk_frames : 48);
+        if (chunk > 0) return run_fused_tex(c, d_frames, n_frames, chunk, u, d_out_levels, levels, stream);
+        if (loader == 2) { mdc_set_error("texture-gather loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
+    }
     FusedParams p;
     memset(&p, 0, sizeof p);
     p.frames = d_frames; p.n_frames = n_frames;
@@ -308,8 +452,8 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     p.lut_gamma = u.gamma; p.use_vig = u.vig; p.kill = u.kill;
     p.box_px_max = c->box_px_max;
     p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 48;
-    bool tma = c->plan_tma_ok && c->use_tma != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
-    if (c->use_tma == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
+    bool tma = c->plan_tma_ok && loader != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
+    if (loader == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
     const TmaMaps* maps = nullptr;
     if (tma) {
         int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
@@ -324,21 +468,56 @@ int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, f
     if (c->ctas_per_sm > 0) per_sm = std::min(per_sm, c->ctas_per_sm);
     const long long items = static_cast<long long>(p.n_tiles) * ((n_frames + p.chunk_frames - 1) / p.chunk_frames);
     int grid = static_cast<int>(std::min<long long>(static_cast<long long>(per_sm) * c->sm_count, std::max<long long>(items, 1)));
-    CU_CHECK(launch_fused(p, maps, grid, min_ctas, stream));
+    if (c->k1_study != kStudyAll && tma && u.vig && in_kernel == 1 && min_ctas == 3) CU_CHECK(launch_fused_study(p, maps, grid, c->k1_study, stream));
+    else CU_CHECK(launch_fused(p, maps, grid, min_ctas, stream));
     c->launches++;
-    // levels beyond the fused epilogue: stand-alone K2 chain, two levels per launch where possible
-    for (int l = in_kernel; l < levels;) {
-        const int sw = c->out_w >> (l - 1), sh = c->out_h >> (l - 1);
-        if (l + 1 < levels) {
-            CU_CHECK(launch_pyr_down2(d_out_levels[l - 1], sw, sh, d_out_levels[l], d_out_levels[l + 1], n_frames, stream));
-            l += 2;
-        } else {
-            CU_CHECK(launch_pyr_down(d_out_levels[l - 1], sw, sh, d_out_levels[l], n_frames, stream));
-            l += 1;
-        }
-        c->launches++;
-    }
-    return MDC_OK;
+    return run_deep_levels(c, n_frames, d_out_levels, in_kernel, levels, stream);
+}
+
+// Self-check of the texture-gather loader, run once per context: K1 over three synthetic frames (all byte values, saturated
+// pixels, NaN flag on) through the texture path and through the staged (TMA) or LDG path; the texture path is used by default
+// only if the two outputs are bit-identical.  This pins the two things the CUDA documentation does not promise for this use —
+// texture gather on pitch-linear memory and the order of the four returned texels — on the device the context lives on.
+void tex_selfcheck(mdc_ctx* c) {
+    c->tex_ok = false;
+    const char* e = getenv("MDC_USE_TEX");
+    const bool verbose = getenv("MDC_VERBOSE") != nullptr;
+    if (e && atoi(e) == 0) return;
+    if (!c->have_fov || c->tiles.empty()) return;
+    const int nf = 3;
+    const size_t n_in = static_cast<size_t>(c->in_w) * c->in_h, n_out = static_cast<size_t>(c->out_w) * c->out_h;
+    uint8_t* raw = nullptr;
+    float *out_a = nullptr, *out_b = nullptr;
+    unsigned long long* d_bad = nullptr;
+    auto cleanup = [&]() { cudaFree(raw); cudaFree(out_a); cudaFree(out_b); cudaFree(d_bad); cudaGetLastError(); };
+    if (cudaMalloc(&raw, nf * n_in + 1024) != cudaSuccess || cudaMalloc(&out_a, nf * n_out * 4) != cudaSuccess ||
+        cudaMalloc(&out_b, nf * n_out * 4) != cudaSuccess || cudaMalloc(&d_bad, 8) != cudaSuccess) { cleanup(); return; }
+    uint8_t* frames = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 511) & ~static_cast<uintptr_t>(511));
+    const int chunk = tex_chunk_frames(c, frames, c->chunk_frames > 0 ? c->chunk_frames : 48);
+    if (chunk < 1) { if (verbose) fprintf(stderr, "[mdc] texture-gather loader: geometry not describable (pitch %d, limit %d rows)\n", c->in_w, c->tex_max_rows); cleanup(); return; }
+    std::vector<uint8_t> h(nf * n_in);
+    uint32_t lcg = 12345u;
+    for (size_t i = 0; i < h.size(); ++i) { lcg = lcg * 1664525u + 1013904223u; h[i] = static_cast<uint8_t>(lcg >> 24); }
+    for (size_t i = 0; i < h.size(); i += 97) h[i] = 255;
+    bool ok = cudaMemcpy(frames, h.data(), h.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemset(out_a, 0xff, nf * n_out * 4) == cudaSuccess && cudaMemset(out_b, 0, nf * n_out * 4) == cudaSuccess &&
+              cudaMemset(d_bad, 0, 8) == cudaSuccess;
+    const UnmapFlags u{c->have_gamma, c->have_gamma && c->have_vig, true};
+    float* la[1] = {out_a};
+    float* lb[1] = {out_b};
+    const long long launches0 = c->launches;
+    ok = ok && run_fused(c, frames, nf, u, la, 1, c->stream, 2) == MDC_OK;
+    ok = ok && run_fused(c, frames, nf, u, lb, 1, c->stream, c->plan_tma_ok ? 1 : 0) == MDC_OK;
+    ok = ok && launch_count_mismatch(out_a, out_b, nf * n_out, d_bad, c->stream) == cudaSuccess;
+    unsigned long long bad = ~0ull;
+    ok = ok && cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    c->launches = launches0;             // bookkeeping counts the caller's launches only
+    for (auto& t : c->tex_cache) if (t.ptr == frames) tex_entry_release(t);
+    c->tex_ok = ok && bad == 0;
+    if (verbose || (ok && bad != 0))
+        fprintf(stderr, "[mdc] texture-gather loader self-check: %s (%llu of %zu output words differ from the %s loader; chunk = %d frames)\n",
+                c->tex_ok ? "bit-identical, enabled" : "DISABLED", ok ? bad : 0ull, nf * n_out, c->plan_tma_ok ? "TMA" : "LDG", chunk);
+    cleanup();
 }
 
 int finish(mdc_ctx* c, mdc_stream user_stream, cudaStream_t s) {
@@ -390,6 +569,7 @@ extern "C" int mdc_ctx_create(int device, const mdc_fov* fov, const mdc_photo* p
         CTX_CHECK(cudaMemcpy(c->d_vinv, photo->vinv.data(), nb, cudaMemcpyHostToDevice));
     }
 #undef CTX_CHECK
+    tex_selfcheck(c);
     *out = c;
     return MDC_OK;
 }
@@ -422,6 +602,7 @@ extern "C" int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h,
         build_plan(c, hx.data(), hy.data());
         if ((rc = upload_plan(c)) != MDC_OK) { mdc_ctx_destroy(c); return rc; }
     }
+    tex_selfcheck(c);
     *out = c;
     return MDC_OK;
 }
@@ -439,6 +620,8 @@ extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     if (c->owns_tables) { cudaFree(c->d_rx); cudaFree(c->d_ry); cudaFree(c->d_ginv); cudaFree(c->d_vinv); }
     cudaFree(c->d_tiles); cudaFree(c->d_counters); cudaFree(c->d_rc);
     for (int s = 0; s < kMapSlots; ++s) free(c->maps[s]);
+    cudaDeviceSynchronize();
+    for (auto& t : c->tex_cache) tex_entry_release(t);
     for (int s = 0; s < kHostPipeDepth; ++s) {
         if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }
         cudaFree(c->pipe_in[s]); cudaFree(c->pipe_out[s]);
@@ -467,10 +650,20 @@ extern "C" int mdc_ctx_level_dims(const mdc_ctx* c, int level, int* w, int* h) {
 extern "C" long long mdc_ctx_launch_count(const mdc_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm) {
-    if (!c) return MDC_ERR_INVALID_ARG;
+    if (!c || use_tma < -1 || use_tma > 2) return MDC_ERR_INVALID_ARG;
     c->use_tma = use_tma;
     c->ctas_per_sm = ctas_per_sm;
     return MDC_OK;
+}
+
+extern "C" int mdc_ctx_loader_usable(const mdc_ctx* c, int loader) {
+    if (!c || !c->have_fov) return 0;
+    switch (loader) {
+        case MDC_LOADER_LDG: return 1;
+        case MDC_LOADER_TMA: return c->plan_tma_ok ? 1 : 0;
+        case MDC_LOADER_TEX: return c->tex_ok ? 1 : 0;
+        default: return 0;
+    }
 }
 
 // --------------------------------------------------------------- device-resident operators
@@ -778,21 +971,29 @@ extern "C" int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_f
         }
         c->pipe_in_bytes = in_bytes; c->pipe_out_bytes = out_bytes;
     }
-    int k = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
+    // On any failure the copies of earlier chunks into the caller's buffers may still be in flight on the other pipe streams:
+    // drain all of them before returning, so the caller can free or reuse its buffers.
+    auto drain = [&]() {
+        cudaError_t first = cudaSuccess;
+        for (int s = 0; s < kHostPipeDepth; ++s)
+            if (c->pipe_stream[s]) { const cudaError_t e = cudaStreamSynchronize(c->pipe_stream[s]); if (first == cudaSuccess) first = e; }
+        return first;
+    };
+    int k = 0, rc = MDC_OK;
+    for (int f0 = 0; f0 < n_frames && rc == MDC_OK; f0 += chunk, ++k) {
         const int nf = std::min(chunk, n_frames - f0);
         const int s = k % kHostPipeDepth;
         cudaStream_t st = c->pipe_stream[s];
-        CU_CHECK(cudaMemcpyAsync(c->pipe_in[s], frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(nf) * n_in, cudaMemcpyHostToDevice, st));
+        cudaError_t ce = cudaMemcpyAsync(c->pipe_in[s], frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(nf) * n_in, cudaMemcpyHostToDevice, st);
         float* lv[MDC_MAX_PYR_LEVELS];
         size_t off = 0;
         for (int l = 0; l < levels; ++l) { lv[l] = c->pipe_out[s] + off; off += static_cast<size_t>(nf) * lvl_px[l]; }
-        int rc = mdc_prepare_batch(c, c->pipe_in[s], nf, flags, lv, levels, st);
-        if (rc != MDC_OK) return rc;
-        for (int l = 0; l < levels; ++l)
-            CU_CHECK(cudaMemcpyAsync(out_levels[l] + static_cast<size_t>(f0) * lvl_px[l], lv[l], static_cast<size_t>(nf) * lvl_px[l] * 4, cudaMemcpyDeviceToHost, st));
+        if (ce == cudaSuccess) rc = mdc_prepare_batch(c, c->pipe_in[s], nf, flags, lv, levels, st);
+        for (int l = 0; l < levels && rc == MDC_OK && ce == cudaSuccess; ++l)
+            ce = cudaMemcpyAsync(out_levels[l] + static_cast<size_t>(f0) * lvl_px[l], lv[l], static_cast<size_t>(nf) * lvl_px[l] * 4, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) { mdc_set_error("mdc_prepare_batch_host: copy failed: %s", cudaGetErrorString(ce)); rc = MDC_ERR_CUDA; }
     }
-    for (int s = 0; s < kHostPipeDepth; ++s)
-        if (c->pipe_stream[s]) CU_CHECK(cudaStreamSynchronize(c->pipe_stream[s]));
-    return MDC_OK;
+    const cudaError_t drained = drain();
+    if (rc == MDC_OK && drained != cudaSuccess) { mdc_set_error("mdc_prepare_batch_host: %s", cudaGetErrorString(drained)); rc = MDC_ERR_CUDA; }
+    return rc;
 }

@@ -10,11 +10,14 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <exception>
 #include <iterator>
 
 #include "mdc_internal.h"
 
 namespace {
+
+constexpr uint64_t kMaxImagePixels = 1ull << 28;
 
 uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
 
@@ -52,6 +55,12 @@ bool decode_png(const std::vector<uint8_t>& file, const std::string& path, mdc_g
                       path.c_str(), color, depth, interlace);
         return false;
     }
+    // untrusted dimensions: bound them before anything is sized from them (same 2^28-pixel cap as the JPEG path)
+    if (width > 0x7fffffffu || height > 0x7fffffffu || static_cast<uint64_t>(width) * height > kMaxImagePixels) {
+        mdc_set_error("%s: implausible PNG dimensions %u x %u", path.c_str(), width, height);
+        return false;
+    }
+    if (idat.empty()) { mdc_set_error("%s: PNG without image data", path.c_str()); return false; }
     const size_t bpp = depth / 8, stride = static_cast<size_t>(width) * bpp;
     std::vector<uint8_t> raw((stride + 1) * height);
     uLongf raw_len = static_cast<uLongf>(raw.size());
@@ -102,16 +111,19 @@ bool decode_pgm(const std::vector<uint8_t>& file, const std::string& path, mdc_g
     while (got < 3 && pos < file.size()) {
         if (file[pos] == '#') { while (pos < file.size() && file[pos] != '\n') ++pos; continue; }
         if (isspace(file[pos])) { ++pos; continue; }
-        int v = 0; bool any = false;
-        while (pos < file.size() && isdigit(file[pos])) { v = v * 10 + (file[pos] - '0'); ++pos; any = true; }
+        long long v = 0; bool any = false;
+        while (pos < file.size() && isdigit(file[pos])) {
+            v = v * 10 + (file[pos] - '0'); ++pos; any = true;
+            if (v > 0x7fffffffLL) { mdc_set_error("%s: malformed PGM header (number too large)", path.c_str()); return false; }
+        }
         if (!any) { mdc_set_error("%s: malformed PGM header", path.c_str()); return false; }
-        vals[got++] = v;
+        vals[got++] = static_cast<int>(v);
     }
     if (got != 3) { mdc_set_error("%s: malformed PGM header", path.c_str()); return false; }
     ++pos;  // the single whitespace after maxval
     const int w = vals[0], h = vals[1], maxv = vals[2];
     const size_t n = static_cast<size_t>(w) * h, bpp = maxv < 256 ? 1 : 2;
-    if (w <= 0 || h <= 0 || pos + n * bpp > file.size()) { mdc_set_error("%s: truncated PGM", path.c_str()); return false; }
+    if (w <= 0 || h <= 0 || maxv <= 0 || maxv > 65535 || n > kMaxImagePixels || pos + n * bpp > file.size()) { mdc_set_error("%s: truncated PGM", path.c_str()); return false; }
     out->rows = h; out->cols = w; out->depth = bpp == 1 ? 8 : 16;
     out->px.resize(n * bpp);
     if (bpp == 1) memcpy(out->px.data(), &file[pos], n);
@@ -124,16 +136,28 @@ bool decode_pgm(const std::vector<uint8_t>& file, const std::string& path, mdc_g
 
 }  // namespace
 
+// No exception leaves the decoders: allocation failures on hostile input become an ordinary "unreadable image" (the callers sit
+// behind extern "C" entry points and std::async workers).
 bool mdc_decode_gray_image(const std::vector<uint8_t>& file, const std::string& name, mdc_gray_image* out) {
     mdc_set_error("%s: not a PNG, PGM or JPEG image", name.c_str());
-    if (file.size() >= 2 && file[0] == 'P' && file[1] == '5') return decode_pgm(file, name, out);
-    if (file.size() >= 2 && file[0] == 0xff && file[1] == 0xd8) return mdc_decode_jpeg_gray(file, name, out);
-    return decode_png(file, name, out);
+    try {
+        if (file.size() >= 2 && file[0] == 'P' && file[1] == '5') return decode_pgm(file, name, out);
+        if (file.size() >= 2 && file[0] == 0xff && file[1] == 0xd8) return mdc_decode_jpeg_gray(file, name, out);
+        return decode_png(file, name, out);
+    } catch (const std::exception& e) {
+        mdc_set_error("%s: cannot decode (%s)", name.c_str(), e.what());
+        return false;
+    }
 }
 
 bool mdc_read_gray_image(const std::string& path, mdc_gray_image* out) {
-    std::ifstream f(path.c_str(), std::ios::binary);
-    if (!f.good()) { mdc_set_error("cannot open image %s", path.c_str()); return false; }
-    std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    return mdc_decode_gray_image(file, path, out);
+    try {
+        std::ifstream f(path.c_str(), std::ios::binary);
+        if (!f.good()) { mdc_set_error("cannot open image %s", path.c_str()); return false; }
+        std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        return mdc_decode_gray_image(file, path, out);
+    } catch (const std::exception& e) {
+        mdc_set_error("%s: cannot read (%s)", path.c_str(), e.what());
+        return false;
+    }
 }

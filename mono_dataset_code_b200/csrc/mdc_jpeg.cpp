@@ -30,10 +30,13 @@ struct HuffTable {
     // canonical decoding tables (T.81 Annex F.2.2.3) + a prefix table for the short codes
     int mincode[17], maxcode[18], valptr[17];
     uint16_t look[1 << kLookBits];      // (code length << 8) | symbol, 0 = longer than kLookBits
-    void build() {
+    // false = over-subscribed table (more codes of some length than the prefix code space has left; libjpeg's
+    // JERR_BAD_HUFF_TABLE).  Must be checked before look[] is filled: such a table would index past its end.
+    bool build() {
         int code = 0, k = 0;
         memset(look, 0, sizeof look);
         for (int l = 1; l <= 16; ++l) {
+            if (code + bits[l] > (1 << l)) return false;
             valptr[l] = k;
             mincode[l] = code;
             for (int i = 0; i < bits[l]; ++i, ++code, ++k)
@@ -45,6 +48,7 @@ struct HuffTable {
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
+        return true;
     }
 };
 
@@ -220,8 +224,8 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                 if (total > 256 || i + total > seg_len) return fail("bad Huffman table");
                 memcpy(t.vals, seg + i, static_cast<size_t>(total));
                 i += total;
-                t.defined = true;
-                t.build();
+                t.defined = t.build();
+                if (!t.defined) return fail("bad Huffman table (over-subscribed code lengths)");
             }
         } else if (marker == 0xc0 || marker == 0xc1) {         // SOF0 / SOF1 (Huffman, sequential)
             if (seg_len < 6) return fail("bad frame header");

@@ -150,7 +150,7 @@ __device__ __forceinline__ float lut_value(const FusedParams& p, int v) {
     return r;
 }
 
-template <bool kTma, bool kVig, bool kPyr, int kMinCtas>
+template <bool kTma, bool kVig, bool kPyr, int kMinCtas, int kStudy = kStudyAll>
 __global__ void __launch_bounds__(kTma ? kConsumers + 32 : kConsumers, kMinCtas)
 fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TmaMaps maps) {
     const int kNs = kTma ? p.tma_stages : kLdgStages;   // ring depth (runtime: as many stages as fit next to 3 CTAs/SM)
@@ -347,6 +347,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             }
         }
 
+        uint32_t study_acc = 0;
         // ------------------------------------------------------------ frame loop, specialised on how the taps are fetched
         auto run_frames = [&](auto staged_c, auto black_c) {
         constexpr bool kStaged = decltype(staged_c)::value;
@@ -369,7 +370,10 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int q = 2 * h + j;
-                    if (kStaged) {
+                    if (!(kStudy & kStudyTaps)) {      // floor study: tap bytes from the ALU instead of the staged box
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) b[j][k] = (off[q] + static_cast<uint32_t>(f + 37 * k)) & 0xffu;
+                    } else if (kStaged) {
                         const uint32_t a0 = base + off[q], a1 = a0 + static_cast<uint32_t>(pitch);
                         b[j][0] = lds_u8(a0); b[j][1] = lds_u8_1(a0);
                         b[j][2] = lds_u8(a1); b[j][3] = lds_u8_1(a1);
@@ -383,7 +387,8 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) g[j][k] = lds_f32(lut_lane + (b[j][k] << 7));
+                    for (int k = 0; k < 4; ++k)
+                        g[j][k] = (kStudy & kStudyLut) ? lds_f32(lut_lane + (b[j][k] << 7)) : __uint_as_float(0x3f800000u | b[j][k]);
                 if (kStaged && h == 1) {
                     if (kTma) {          // all tap bytes of this warp are in registers: hand the stage back to the producer
                         __syncwarp();
@@ -411,7 +416,10 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
             }
 
             // ---- level 0: one full 128-byte row segment per warp store
-            if (full_tile) {
+            if (!(kStudy & kStudyStores)) {      // floor study: fold the pixels into a register instead of storing them
+                study_acc ^= __float_as_uint(px[0]) ^ __float_as_uint(px[1]);
+                study_acc ^= __float_as_uint(px[2]) ^ __float_as_uint(px[3]);
+            } else if (full_tile) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) stg_cs(o0 + static_cast<size_t>(q) * p.out_w, px[q]);
             } else if (x_ok) {
@@ -452,6 +460,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         };
         if (staged) { if (has_black) run_frames(std::true_type{}, std::true_type{}); else run_frames(std::true_type{}, std::false_type{}); }
         else run_frames(std::false_type{}, std::true_type{});
+        if (!(kStudy & kStudyStores) && study_acc == 0x9e3779b9u && x_ok) stg_cs(p.out[0], 0.0f);   // keeps the folded pixels alive
         if (!kTma) {         // LDG loader: thread 0 pulls the next item for the whole CTA
             consumer_barrier();
             if (tid == 0) s_item[0] = static_cast<int>(gridDim.x) + atomicAdd(p.work_counter, 1);
@@ -509,6 +518,295 @@ cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, in
     if (e != cudaSuccess) return e;
     static const TmaMaps none = {};
     fn<<<grid, tma ? kConsumers + 32 : kConsumers, smem, stream>>>(p, tma ? *maps : none);
+    return cudaGetLastError();
+}
+
+// Floor-study launches of the shipped TMA variant <tma, vignette, no pyramid, 3 CTAs/SM> with parts of the frame loop disabled.
+cudaError_t launch_fused_study(const FusedParams& p, const TmaMaps* maps, int grid, int study, cudaStream_t stream) {
+    if (!maps || p.levels > 1) return cudaErrorInvalidValue;
+    FusedKernelFn fn = nullptr;
+    switch (study & kStudyAll) {
+        case 0: fn = fused_prepare_kernel<true, true, false, 3, 0>; break;
+        case 1: fn = fused_prepare_kernel<true, true, false, 3, 1>; break;
+        case 2: fn = fused_prepare_kernel<true, true, false, 3, 2>; break;
+        case 3: fn = fused_prepare_kernel<true, true, false, 3, 3>; break;
+        case 4: fn = fused_prepare_kernel<true, true, false, 3, 4>; break;
+        case 5: fn = fused_prepare_kernel<true, true, false, 3, 5>; break;
+        case 6: fn = fused_prepare_kernel<true, true, false, 3, 6>; break;
+        default: fn = fused_prepare_kernel<true, true, false, 3, 7>; break;
+    }
+    const size_t smem = fused_smem_bytes(p.box_px_max, p.tma_stages);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    fn<<<grid, kConsumers + 32, smem, stream>>>(p, *maps);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// K1, texture-gather loader.  Same arithmetic, different plumbing: the four tap bytes of an output pixel are exactly the
+// 2x2 footprint a texture unit fetches for bilinear filtering, so ONE `tld4` (texture gather, point-addressed at the integer
+// source position) returns them — through the TEX pipe, straight from the u8 frames in global memory (L2 -> L1), with no
+// shared-memory staging at all.  That takes the tap traffic (21 of the 45 shared-memory wavefronts per warp and frame of
+// the TMA-staged kernel) off the LSU data pipe, which is left with the response-LUT look-ups and the stores;
+// the two pipes then run side by side:
+//     TEX  4 tld4 per warp-frame (4 lanes/clock/SM)          LSU  16 LUT + ~7 store wavefronts per warp-frame
+// There is no producer warp, no mbarrier and no CTA-wide barrier in the frame loop: a warp owns a STRIP (4 output rows x
+// 32 columns) of its CTA's tile over the frames of one chunk and never talks to another warp.
+//
+// Frames are addressed as u8 pitch-2D texture objects over the caller's frame stack (no copy): the frames of a chunk are
+// stacked vertically in one object (row = frame_in_chunk*in_h + y; texture gather limits the height, so the chunk length
+// follows from it, see run_fused), point sampling, unnormalised coordinates.  tld4 at (xi+1, yi+1) selects texels floor(u-0.5) = xi, xi+1 / yi, yi+1 — both
+// half-integers are exact in the TEX unit's fixed-point coordinates — and returns them as
+//     .x = (xi, yi+1)   .y = (xi+1, yi+1)   .z = (xi+1, yi)   .w = (xi, yi)          (checked at context creation).
+// =====================================================================================
+__device__ __forceinline__ void tld4_u8(unsigned long long tex, float u, float v, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+    asm volatile("tld4.r.2d.v4.u32.f32 {%0, %1, %2, %3}, [%4, {%5, %6}];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(tex), "f"(u), "f"(v));
+}
+
+template <bool kVig, bool kPyr, int kMinCtas, bool kPrefetch, int kStudy>
+__global__ void __launch_bounds__(kTexThreads, kMinCtas)
+fused_tex_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ TexSet texs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* lut = reinterpret_cast<float*>(smem_raw);                    // [256][32] lane-replicated response LUT
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256 * 32; i += blockDim.x) lut[i] = lut_value(p, i >> 5);
+    __syncthreads();
+
+    const uint32_t lut_lane = smem_u32(lut) + 4u * lane;
+    const float frame_rows = static_cast<float>(p.in_h);               // texture rows per frame (exact: < 2^24)
+
+    // grid = (tile groups, chunks).  Everything that selects the texture object and bounds the loops below depends on
+    // blockIdx and kernel parameters only, i.e. is CTA-uniform by construction, so ptxas keeps the handle in a uniform
+    // register (with a dynamically scheduled work loop it wraps every TLD4 in a 7-instruction divergence loop instead).
+    // Load balance is left to the hardware CTA scheduler: CTAs are short (tiles_per_cta tiles x one chunk of frames) and
+    // are issued chunk-major, so chip-wide everybody is inside the same chunk or the next.
+    const int chunk = blockIdx.y;
+    const int f_begin = chunk * p.chunk_frames, f_end = min(f_begin + p.chunk_frames, p.n_frames);
+    const unsigned long long tex = texs.tex[chunk];                     // one texture object per chunk (frames stacked vertically)
+    const int wrow = warp;                                              // strip of the tile: output rows 4*warp .. 4*warp+3
+    for (int t = 0; t < p.tiles_per_cta; ++t) {
+        const int tile = static_cast<int>(blockIdx.x) * p.tiles_per_cta + t;
+        if (tile >= p.n_tiles) break;
+        {
+        const int tx0 = (tile % p.tiles_x) * kTile, ty0 = (tile / p.tiles_x) * kTile;
+        const int ox = tx0 + lane, oy0 = ty0 + 4 * wrow;
+
+        // ------------------------------------------------------------ per-(strip, chunk) prologue: weights, vignette taps, coordinates
+        float w[4][4], vi[4][4], tu[4], tv[4];
+        unsigned valid = 0, inside = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int oy = oy0 + q;
+            float sx = -1.0f, sy = -1.0f;
+            if (ox < p.out_w && oy < p.out_h) {
+                inside |= 1u << q;
+                const size_t o = static_cast<size_t>(oy) * p.out_w + ox;
+                sx = __ldg(p.remap_x + o);
+                sy = __ldg(p.remap_y + o);
+            }
+            tu[q] = 1.0f; tv[q] = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { w[q][k] = 0.0f; vi[q][k] = 1.0f; }
+            if (!(sx < 0)) {  // the reference tests only remapX (FOVUndistorter.cpp:347)
+                valid |= 1u << q;
+                const int xi = static_cast<int>(sx), yi = static_cast<int>(sy);   // truncation, :352-353
+                const float fx = __fsub_rn(sx, static_cast<float>(xi));
+                const float fy = __fsub_rn(sy, static_cast<float>(yi));
+                const float fxy = __fmul_rn(fx, fy);
+                w[q][3] = fxy;
+                w[q][2] = __fsub_rn(fy, fxy);
+                w[q][1] = __fsub_rn(fx, fxy);
+                w[q][0] = __fadd_rn(__fsub_rn(__fsub_rn(1.0f, fx), fy), fxy);
+                tu[q] = static_cast<float>(xi + 1);
+                tv[q] = static_cast<float>(yi + 1);
+                if (kVig) {
+                    const int g = yi * p.in_w + xi;
+                    vi[q][0] = __ldg(p.vinv + g);
+                    vi[q][1] = __ldg(p.vinv + g + 1);
+                    vi[q][2] = __ldg(p.vinv + g + p.in_w);
+                    vi[q][3] = __ldg(p.vinv + g + p.in_w + 1);
+                }
+            }
+        }
+        const bool any_black = valid != inside;                         // some in-image pixel of this thread has no source
+        uint64_t w2[2][4], vi2[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w2[h][k] = pack2(w[2 * h][k], w[2 * h + 1][k]);
+                vi2[h][k] = pack2(vi[2 * h][k], vi[2 * h + 1][k]);
+            }
+
+        float* o0 = p.out[0] + static_cast<size_t>(f_begin) * p.lw[0] * p.lh[0] + static_cast<size_t>(oy0) * p.out_w + ox;
+        const size_t o0_step = static_cast<size_t>(p.lw[0]) * p.lh[0];
+        const bool full_strip = inside == 0xfu;
+        float *o1 = nullptr, *o2 = nullptr;
+        uint32_t o1_step = 0, o2_step = 0;
+        bool st1 = false, st2 = false;
+        if (kPyr) {
+            const int X1 = (tx0 >> 1) + (lane >> 1), Y1 = (ty0 >> 1) + 2 * wrow + (lane & 1);   // even lane: upper block, odd lane: lower block
+            st1 = X1 < p.lw[1] && Y1 < p.lh[1];
+            o1_step = static_cast<uint32_t>(p.lw[1]) * static_cast<uint32_t>(p.lh[1]);
+            o1 = p.out[1] + static_cast<size_t>(f_begin) * o1_step + static_cast<size_t>(Y1) * p.lw[1] + X1;
+            if (p.levels > 2) {
+                const int X2 = (tx0 >> 2) + (lane >> 2), Y2 = (ty0 >> 2) + wrow;
+                st2 = (lane & 3) == 0 && X2 < p.lw[2] && Y2 < p.lh[2];
+                o2_step = static_cast<uint32_t>(p.lw[2]) * static_cast<uint32_t>(p.lh[2]);
+                o2 = p.out[2] + static_cast<size_t>(f_begin) * o2_step + static_cast<size_t>(Y2) * p.lw[2] + X2;
+            }
+        }
+        uint32_t study_acc = 0;
+
+        // taps of one frame: b[q] = {(xi,yi), (xi+1,yi), (xi,yi+1), (xi+1,yi+1)} = reference order src[0], src[1], src[in_w], src[1+in_w]
+        auto fetch = [&](uint32_t (&b)[4][4], int f) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (kStudy & kStudyTaps) tld4_u8(tex, tu[q], tv[q], b[q][2], b[q][3], b[q][1], b[q][0]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) b[q][k] = (__float_as_uint(tu[q]) + static_cast<uint32_t>(f + 37 * k)) & 0xffu;
+                }
+            }
+            // advance the coordinates to the next frame of the stack
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tv[q] = __fadd_rn(tv[q], frame_rows);
+        };
+
+        uint32_t bn[4][4];
+        if (kPrefetch) fetch(bn, f_begin);
+        for (int f = f_begin; f < f_end; ++f) {
+            uint32_t b[4][4];
+            if (kPrefetch) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) b[q][k] = bn[q][k];
+                if (f + 1 < f_end) fetch(bn, f + 1);        // next frame's taps are in flight during this frame's arithmetic
+            } else {
+                fetch(b, f);
+            }
+            float px[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float g[2][4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        g[j][k] = (kStudy & kStudyLut) ? lds_f32(lut_lane + (b[2 * h + j][k] << 7)) : __uint_as_float(0x3f800000u | b[2 * h + j][k]);
+                // unMapImage multiply + bilinear blend, reference order (PhotometricUndistorter.cpp:205, FOVUndistorter.cpp:362-365)
+                float t_lo[4], t_hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t v = pack2(g[0][k], g[1][k]);
+                    if (kVig) v = mul2(v, vi2[h][k]);
+                    v = mul2(w2[h][k], v);
+                    unpack2(v, t_lo[k], t_hi[k]);
+                }
+                px[2 * h] = __fadd_rn(__fadd_rn(__fadd_rn(t_lo[3], t_lo[2]), t_lo[1]), t_lo[0]);
+                px[2 * h + 1] = __fadd_rn(__fadd_rn(__fadd_rn(t_hi[3], t_hi[2]), t_hi[1]), t_hi[0]);
+            }
+            if (any_black) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) px[q] = ((valid >> q) & 1u) ? px[q] : 0.0f;
+            }
+            // ---- level 0: one full 128-byte row segment per warp store
+            if (!(kStudy & kStudyStores)) {
+                study_acc ^= __float_as_uint(px[0]) ^ __float_as_uint(px[1]);
+                study_acc ^= __float_as_uint(px[2]) ^ __float_as_uint(px[3]);
+            } else if (full_strip) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stg_cs(o0 + static_cast<size_t>(q) * p.out_w, px[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((inside >> q) & 1u) stg_cs(o0 + static_cast<size_t>(q) * p.out_w, px[q]);
+            }
+            o0 += o0_step;
+            // ---- pyramid epilogue (same lane roles as the staged kernel): dst = 0.25f*(((a+b)+c)+d)
+            if (kPyr) {
+                const bool odd = (lane & 1) != 0;
+                const float r1 = __shfl_xor_sync(0xffffffffu, odd ? px[0] : px[2], 1);
+                const float r2 = __shfl_xor_sync(0xffffffffu, odd ? px[1] : px[3], 1);
+                const float pa = odd ? r1 : px[0], pb = odd ? px[2] : r1, pc = odd ? r2 : px[1], pd = odd ? px[3] : r2;
+                const float l1 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(pa, pb), pc), pd));
+                if (st1) stg_cs(o1, l1);
+                o1 += o1_step;
+                if (p.levels > 2) {
+                    const float c2 = __shfl_down_sync(0xffffffffu, l1, 1);
+                    const float b2 = __shfl_down_sync(0xffffffffu, l1, 2);
+                    const float d2 = __shfl_down_sync(0xffffffffu, l1, 3);
+                    const float l2 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(l1, b2), c2), d2));   // lanes = 0 mod 4
+                    if (st2) stg_cs(o2, l2);
+                    o2 += o2_step;
+                }
+            }
+        }
+        if (!(kStudy & kStudyStores) && study_acc == 0x9e3779b9u && (inside & 1u)) stg_cs(p.out[0], 0.0f);   // keeps the folded pixels alive
+        }
+    }
+}
+
+typedef void (*FusedTexFn)(const FusedParams, const TexSet);
+template <int kMinCtas, bool kPrefetch>
+static FusedTexFn fused_tex_variant_t(bool vig, bool pyr) {
+    if (vig) return pyr ? fused_tex_kernel<true, true, kMinCtas, kPrefetch, kStudyAll> : fused_tex_kernel<true, false, kMinCtas, kPrefetch, kStudyAll>;
+    return pyr ? fused_tex_kernel<false, true, kMinCtas, kPrefetch, kStudyAll> : fused_tex_kernel<false, false, kMinCtas, kPrefetch, kStudyAll>;
+}
+static FusedTexFn fused_tex_variant(bool vig, bool pyr, int min_ctas, bool prefetch, int study) {
+    if (study != kStudyAll && vig && !pyr) {      // floor study: <vignette, no pyramid, 3 CTAs/SM, no prefetch> with parts disabled
+        switch (study & kStudyAll) {
+            case 0: return fused_tex_kernel<true, false, 3, false, 0>;
+            case 1: return fused_tex_kernel<true, false, 3, false, 1>;
+            case 2: return fused_tex_kernel<true, false, 3, false, 2>;
+            case 3: return fused_tex_kernel<true, false, 3, false, 3>;
+            case 4: return fused_tex_kernel<true, false, 3, false, 4>;
+            case 5: return fused_tex_kernel<true, false, 3, false, 5>;
+            case 6: return fused_tex_kernel<true, false, 3, false, 6>;
+            default: break;
+        }
+    }
+    if (prefetch) {
+        if (min_ctas <= 2) return fused_tex_variant_t<2, true>(vig, pyr);
+        return min_ctas == 3 ? fused_tex_variant_t<3, true>(vig, pyr) : fused_tex_variant_t<4, true>(vig, pyr);
+    }
+    if (min_ctas <= 2) return fused_tex_variant_t<2, false>(vig, pyr);
+    return min_ctas == 3 ? fused_tex_variant_t<3, false>(vig, pyr) : fused_tex_variant_t<4, false>(vig, pyr);
+}
+constexpr int kTexSmemBytes = 256 * 32 * 4;
+
+int fused_tex_max_ctas_per_sm(bool vig, bool pyr, int min_ctas, bool prefetch) {
+    int n = 0;
+    FusedTexFn fn = fused_tex_variant(vig, pyr, min_ctas, prefetch, kStudyAll);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTexSmemBytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kTexThreads, kTexSmemBytes) != cudaSuccess) return 0;
+    return n;
+}
+
+cudaError_t launch_fused_tex(const FusedParams& p, const TexSet& texs, int n_chunks, int min_ctas, bool prefetch, int study, cudaStream_t stream) {
+    if (n_chunks < 1 || n_chunks > kMaxTex || p.tiles_per_cta < 1) return cudaErrorInvalidValue;
+    FusedTexFn fn = fused_tex_variant(p.use_vig != 0, p.levels > 1, min_ctas, prefetch, study);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTexSmemBytes);
+    if (e != cudaSuccess) return e;
+    const dim3 grid(static_cast<unsigned>((p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta), static_cast<unsigned>(n_chunks));
+    fn<<<grid, kTexThreads, kTexSmemBytes, stream>>>(p, texs);
+    return cudaGetLastError();
+}
+
+// bit-wise comparison of two device buffers (self-check of the texture-gather loader at context creation)
+__global__ void __launch_bounds__(256) count_mismatch_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t n,
+                                                             unsigned long long* __restrict__ out) {
+    unsigned long long bad = 0;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) bad += a[i] != b[i];
+    if (bad) atomicAdd(out, bad);
+}
+cudaError_t launch_count_mismatch(const void* a, const void* b, size_t n_words, unsigned long long* out, cudaStream_t stream) {
+    if (n_words == 0) return cudaSuccess;
+    size_t blocks = (n_words + 255) / 256;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    count_mismatch_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint32_t*>(a), static_cast<const uint32_t*>(b), n_words, out);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,8 @@ constexpr int kMaxStages = 8;
 constexpr int kItemSlots = 4;          // work items in flight between the producer warp and the consumers
 constexpr int kSmemHeaderBytes = 33024;   // lut 32768 + item ring 32 + 24 mbarriers 192, rounded up to 128
 constexpr int kMaxClasses = 64;      // distinct TMA box shapes per plan (descriptors travel as kernel parameters)
+constexpr int kMaxTex = 128;         // texture-gather loader: u8 pitch-2D texture objects per launch (one per chunk of frames)
+constexpr int kTexThreads = 256;     // texture-gather loader: 8 independent warps per CTA, no producer warp
 
 // How a tile's input pixels are fetched.
 enum TileMode : int { TILE_EMPTY = 0, TILE_STAGED = 1, TILE_DIRECT = 2, TILE_HAS_BLACK = 0x10 /* flag */ };
@@ -34,6 +36,12 @@ struct alignas(16) TileDesc {
 // __grid_constant__ kernel parameter (no device-memory copy, no lifetime to manage).
 struct TmaMaps {
     alignas(64) CUtensorMap m[kMaxClasses];
+};
+
+// Texture-gather loader: one u8 pitch-2D texture object per chunk of `chunk_frames` consecutive frames (stacked vertically:
+// texture row = frame_in_chunk * in_h + y), passed by value like the TMA descriptors.
+struct TexSet {
+    unsigned long long tex[kMaxTex];
 };
 
 struct FusedParams {
@@ -54,12 +62,22 @@ struct FusedParams {
     int box_px_max;              // largest staged box (pixels) -> smem carve-up
     int chunk_frames;            // frames per schedule chunk (L2 residency of the inputs)
     int tma_stages;              // depth of the TMA stage ring (2..kMaxStages)
+    int tiles_per_cta;           // texture-gather loader: consecutive tiles one CTA works through (grid.x = ceil(n_tiles / tiles_per_cta))
 };
+
+// Floor-study switches (profiles/r02_k1_floor_study.md): which of the three shared-memory/LSU consumers of the frame loop run.
+// kStudyAll is the product; the others replace the disabled part by one or two ALU instructions so that the rest can be timed alone.
+enum StudyBits : int { kStudyTaps = 1, kStudyLut = 2, kStudyStores = 4, kStudyAll = 7 };
 
 size_t fused_smem_bytes(int box_px_max, int stages);
 int fused_tma_stages(int box_px_max, int ctas_per_sm);
 cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, int min_ctas, cudaStream_t stream);  // maps == nullptr: LDG loader
 int fused_max_ctas_per_sm(int box_px_max, int stages, bool tma, bool vig, bool pyr, int min_ctas);
+cudaError_t launch_fused_study(const FusedParams& p, const TmaMaps* maps, int grid, int study, cudaStream_t stream);   // <tma, vig, no pyramid, 3 CTAs/SM> only
+// texture-gather loader (taps through the TEX pipe, LUT + stores through the LSU pipe)
+cudaError_t launch_fused_tex(const FusedParams& p, const TexSet& texs, int n_chunks, int min_ctas, bool prefetch, int study, cudaStream_t stream);
+int fused_tex_max_ctas_per_sm(bool vig, bool pyr, int min_ctas, bool prefetch);
+cudaError_t launch_count_mismatch(const void* a, const void* b, size_t n_words, unsigned long long* out, cudaStream_t stream);
 
 cudaError_t launch_unmap(const uint8_t* in, float* out, size_t n, int n_frames, const float* ginv, const float* vinv,
                          unsigned kill, cudaStream_t stream);

@@ -10,6 +10,7 @@
 // The zip reader handles what `zip` / Python's zipfile / the TUM archives produce: stored and deflated entries, no encryption,
 // no zip64 (archives < 4 GB, < 65535 entries), CRC-32 verified.
 #include <algorithm>
+#include <exception>
 #include <cstdio>
 #include <cstring>
 #include <dirent.h>
@@ -91,6 +92,11 @@ bool read_zip_directory(mdc_seq* s, const std::string& archive) {
     const uint16_t n_entries = le16(&buf[eocd + 10]);
     const uint32_t cd_size = le32(&buf[eocd + 12]), cd_off = le32(&buf[eocd + 16]);
     if (n_entries == 0xffff || cd_off == 0xffffffffu) { mdc_set_error("%s: zip64 archives are not supported", archive.c_str()); return false; }
+    // plausibility before anything is sized from the (untrusted) record: the directory lies inside the archive and holds its entries
+    if (static_cast<uint64_t>(cd_off) + cd_size > s->zip_bytes || static_cast<uint64_t>(n_entries) * 46u > cd_size) {
+        mdc_set_error("%s: corrupt central directory", archive.c_str());
+        return false;
+    }
     std::vector<uint8_t> cd(cd_size);
     if (cd_size && !pread_all(s->zip_fd, cd.data(), cd_size, cd_off)) { mdc_set_error("%s: truncated central directory", archive.c_str()); return false; }
     size_t pos = 0;
@@ -124,7 +130,7 @@ bool read_zip_entry(const mdc_seq* s, const ZipEntry& e, std::vector<uint8_t>* o
     if (!pread_all(s->zip_fd, lh, 30, e.local_offset) || le32(lh) != 0x04034b50u) { mdc_set_error("%s: bad local header", e.name.c_str()); return false; }
     const off_t data = static_cast<off_t>(e.local_offset) + 30 + le16(lh + 26) + le16(lh + 28);
     // a corrupt directory must not make us allocate gigabytes: entries cannot be larger than the archive (deflate expands < 1100x)
-    if (e.comp_size > s->zip_bytes || (e.size >> 10) > e.comp_size + 1024u) { mdc_set_error("%s: implausible entry size", e.name.c_str()); return false; }
+    if (e.comp_size > s->zip_bytes || static_cast<uint64_t>(data) + e.comp_size > s->zip_bytes || (e.size >> 10) > e.comp_size + 1024u) { mdc_set_error("%s: implausible entry size", e.name.c_str()); return false; }
     out->resize(e.size);
     if (e.method == 0) {
         if (e.comp_size != e.size || (e.size && !pread_all(s->zip_fd, out->data(), e.size, data))) { mdc_set_error("%s: truncated stored entry", e.name.c_str()); return false; }
@@ -166,7 +172,7 @@ void load_times(mdc_seq* s) {
 }
 
 // 8-bit grey pixels of frame `id` (decoded); 16-bit sources keep the high byte
-bool read_gray8(const mdc_seq* s, int id, std::vector<uint8_t>* px, int* w, int* h) {
+bool read_gray8_unguarded(const mdc_seq* s, int id, std::vector<uint8_t>* px, int* w, int* h) {
     mdc_gray_image img;
     if (s->zipped) {
         std::vector<uint8_t> file;
@@ -183,13 +189,24 @@ bool read_gray8(const mdc_seq* s, int id, std::vector<uint8_t>* px, int* w, int*
     for (size_t i = 0; i < n; ++i) (*px)[i] = static_cast<uint8_t>(src[i] >> 8);
     return true;
 }
+// no exception (bad_alloc / length_error on a hostile file) may cross the C ABI or a std::async worker
+bool read_gray8(const mdc_seq* s, int id, std::vector<uint8_t>* px, int* w, int* h) {
+    try {
+        return read_gray8_unguarded(s, id, px, w, h);
+    } catch (const std::exception& e) {
+        mdc_set_error("%s: cannot read (%s)", s->files[static_cast<size_t>(id)].c_str(), e.what());
+        return false;
+    }
+}
 
 }  // namespace
 
 extern "C" int mdc_seq_open(const char* folder, mdc_seq** out) {
     if (!folder || !out) { mdc_set_error("mdc_seq_open: bad argument"); return MDC_ERR_INVALID_ARG; }
     *out = nullptr;
-    mdc_seq* s = new mdc_seq();
+    mdc_seq* s = nullptr;
+    try {
+    s = new mdc_seq();
     s->path = folder;
     if (!s->path.empty() && s->path[s->path.size() - 1] != '/') s->path += "/";
     list_dir(s->path + "images/", &s->files);
@@ -207,6 +224,11 @@ extern "C" int mdc_seq_open(const char* folder, mdc_seq** out) {
     }
     load_times(s);
     printf("Dataset %s: Got %d files!\n", s->path.c_str(), static_cast<int>(s->files.size()));
+    } catch (const std::exception& e) {
+        mdc_set_error("mdc_seq_open(%s): %s", folder, e.what());
+        if (s) { if (s->zip_fd >= 0) close(s->zip_fd); delete s; }
+        return MDC_ERR_IO;
+    }
     *out = s;
     return MDC_OK;
 }

@@ -46,16 +46,28 @@ def mixed_frames(n, w, h):
     return np.stack([S.frame(i, w, h, kinds[i % len(kinds)]) for i in range(n)])
 
 
+LOADER_ID = {"ldg": 0, "tma": 1, "tex": 2}
+
+
+def select_loader(prep, loader):
+    """Force one of K1's three input loaders (include/mdc_b200.h MDC_LOADER_*); skip where it cannot describe the geometry."""
+    if not prep.ctx.loader_usable(loader):
+        pytest.skip(f"the {loader} loader is not usable for this geometry on this device (the other loaders cover it)")
+    prep.ctx.configure(use_tma=LOADER_ID[loader])
+
+
+def usable_loaders(prep):
+    return [i for n, i in LOADER_ID.items() if prep.ctx.loader_usable(n)]
+
+
 @pytest.mark.parametrize("name", list(CALIBS))
-@pytest.mark.parametrize("loader", ["tma", "ldg"])
+@pytest.mark.parametrize("loader", ["tex", "tma", "ldg"])
 def test_get_image_all_flag_combinations(name, loader, api, port, dataset_dir):
     iw, ih, ow, oh, mode, calib = CALIBS[name]
     files = dataset_dir(name, vignette_zeros=(name in ("odd_sizes", "c1_crop_640")))
     u, p = make_models(api, files, iw, ih)
     prep = api.FramePreparer(u, p)
-    if loader == "tma" and iw % 16 != 0:
-        pytest.skip("TMA needs a 16-byte row pitch; the LDG loader covers this width")
-    prep.ctx.configure(use_tma=1 if loader == "tma" else 0)
+    select_loader(prep, loader)
     rx, ry, ginv, vinv = oracle_tables(port, files)
     frames = mixed_frames(7, iw, ih)
     d_frames = torch.from_numpy(frames).cuda()
@@ -68,15 +80,13 @@ def test_get_image_all_flag_combinations(name, loader, api, port, dataset_dir):
 
 
 @pytest.mark.parametrize("name", ["c1_crop_640", "odd_sizes", "upscale", "full_blackpx"])
-@pytest.mark.parametrize("loader", ["tma", "ldg"])
+@pytest.mark.parametrize("loader", ["tex", "tma", "ldg"])
 def test_pyramid_levels(name, loader, api, port, dataset_dir):
     iw, ih, ow, oh, mode, calib = CALIBS[name]
-    if loader == "tma" and iw % 16 != 0:
-        pytest.skip("LDG loader covers this width")
     files = dataset_dir(name)
     u, p = make_models(api, files, iw, ih)
     prep = api.FramePreparer(u, p)
-    prep.ctx.configure(use_tma=1 if loader == "tma" else 0)
+    select_loader(prep, loader)
     rx, ry, ginv, vinv = oracle_tables(port, files)
     frames = mixed_frames(5, iw, ih)
     d_frames = torch.from_numpy(frames).cuda()
@@ -107,7 +117,7 @@ def test_against_reference_golden_vectors(path, api, tmp_path):
     p = api.PhotometricUndistorter(str(pc), str(vig), iw, ih)
     prep = api.FramePreparer(u, p)
     d_frames = torch.from_numpy(g["frames"]).cuda()
-    for use_tma in (0, -1):
+    for use_tma in usable_loaders(prep) + [-1]:
         prep.ctx.configure(use_tma=use_tma)
         for flags in range(16):
             rectify, gm, v, k = flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, (flags >> 3) & 1
@@ -186,7 +196,7 @@ def test_full_size_configs(name, api, port, dataset_dir):
     frames = mixed_frames(4, iw, ih)
     n_big = 64
     big = torch.from_numpy(np.concatenate([frames] * (n_big // 4))).cuda()
-    for use_tma in (-1, 0):
+    for use_tma in usable_loaders(prep) + [-1]:
         prep.ctx.configure(use_tma=use_tma)
         outs = prep.prepare_device(big, 1, 1, 1, 1, levels=5)
         lv = [o.cpu().numpy() for o in outs]
@@ -214,7 +224,7 @@ def test_batch_beyond_4gb_and_2g_elements(api, port, dataset_dir):
     n = 1700
     big = torch.from_numpy(frames).cuda().repeat(n // 4, 1)
     assert big.shape == (n, iw * ih)
-    for use_tma in (-1, 0):
+    for use_tma in usable_loaders(prep) + [-1]:
         prep.ctx.configure(use_tma=use_tma)
         outs = prep.prepare_device(big, 1, 1, 1, 1, levels=3)
         for i in range(4):
@@ -332,7 +342,7 @@ def test_many_frames_cross_chunk_boundaries(api, port, dataset_dir):
     n = 131
     frames = mixed_frames(n, iw, ih)
     d = torch.from_numpy(frames).cuda()
-    for use_tma in (-1, 0):
+    for use_tma in usable_loaders(prep) + [-1]:
         prep.ctx.configure(use_tma=use_tma)
         out = prep.prepare_device(d, 1, 1, 1, 0, levels=3)
         lv = [o.cpu().numpy() for o in out]
@@ -474,7 +484,7 @@ def test_unusual_geometries(cfg, api, port, dataset_dir):
     rx, ry, ginv, vinv = oracle_tables(port, files)
     frames = mixed_frames(5, iw, ih)
     d = torch.from_numpy(frames).cuda()
-    for use_tma in (-1, 0):
+    for use_tma in usable_loaders(prep) + [-1]:
         prep.ctx.configure(use_tma=use_tma)
         for flags in ((1, 1, 1, 1), (1, 0, 0, 0), (1, 1, 0, 1)):
             levels = 4

@@ -114,3 +114,26 @@ def test_random_corruption_never_crashes(tmp_path):
         if got is not None:
             shapes.add(got.shape)
     assert (48, 64) in shapes            # most single-bit flips in the entropy data still decode
+
+
+def test_oversubscribed_huffman_table_is_rejected(tmp_path):
+    """A DHT segment whose code lengths over-subscribe the prefix code (255 codes of length 1) passes the `total <= 256` check but
+    must be refused before the 9-bit prefix table is filled (libjpeg: JERR_BAD_HUFF_TABLE); it used to write past the table."""
+    from mono_dataset_code_b200 import _lib
+    img = scene(np.random.default_rng(2), 24, 32, "smooth")
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 80])
+    blob = enc.tobytes()
+    at = blob.find(b"\xff\xc4")
+    assert at > 0
+    seg_len = (blob[at + 2] << 8) | blob[at + 3]
+    bad_counts = bytes([255] + [0] * 15)
+    for counts in (bad_counts, bytes([1, 3] + [0] * 14), bytes([0] * 8 + [255] + [0] * 7 )):
+        total = sum(counts)
+        dht = b"\xff\xc4" + (2 + 1 + 16 + total).to_bytes(2, "big") + b"\x00" + counts + bytes([i & 0xff for i in range(total)])
+        evil = blob[:at] + dht + blob[at + 2 + seg_len:]
+        seq = sequence_of(tmp_path / f"c{counts[0]}_{counts[1]}_{counts[8]}", [evil])
+        got = seq.getImageRaw_internal(0)
+        if counts[0] == 255 or counts[:2] == bytes([1, 3]):
+            assert got is None and b"Huffman" in _lib.lib.mdc_last_error()
+        else:       # 255 codes of length 9 fit the code space: a legal (if useless) table, decoded or rejected later without a crash
+            assert got is None or got.shape == img.shape

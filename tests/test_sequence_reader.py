@@ -186,3 +186,46 @@ def test_decode_ahead_feed_matches_the_oracle(tmp_path, zipped):
     if not zipped:
         with pytest.raises(api.MdcError):
             api.Sequence(str(tmp_path)).prepare(prep.ctx, prep.level_shapes(True, 1), 0, 20, True, True, True, False, threads=2)
+
+
+def test_hostile_headers_are_errors_not_crashes(tmp_path):
+    """Untrusted dimensions and directory records are bounded before anything is sized from them; nothing throws across the C ABI."""
+    import struct
+    import zlib
+    from mono_dataset_code_b200 import _lib
+    os.makedirs(tmp_path / "images")
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body))
+    sig = b"\x89PNG\r\n\x1a\n"
+    huge = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 0xFFFFFFFF, 0xFFFFFFFF, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0")) + chunk(b"IEND", b"")
+    big = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 70000, 70000, 16, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0")) + chunk(b"IEND", b"")
+    noidat = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 4, 4, 8, 0, 0, 0, 0)) + chunk(b"IEND", b"")
+    (tmp_path / "images" / "00000.png").write_bytes(huge)
+    (tmp_path / "images" / "00001.png").write_bytes(big)
+    (tmp_path / "images" / "00002.png").write_bytes(noidat)
+    (tmp_path / "images" / "00003.pgm").write_bytes(b"P5\n99999999999999999999 2\n255\n" + bytes(8))
+    (tmp_path / "images" / "00004.pgm").write_bytes(b"P5\n2000000000 2000000000\n255\n" + bytes(8))
+    write_times(tmp_path / "times.txt", 5)
+    seq = api.Sequence(str(tmp_path))
+    assert seq.getNumImages() == 5
+    for i in range(5):
+        assert seq.getImageRaw_internal(i) is None, i
+    assert seq.getImageRaw_internal(0) is None and b"implausible PNG dimensions" in _lib.lib.mdc_last_error()
+    # zip: central directory pointing outside the archive / claiming more entries than it can hold
+    z = tmp_path / "z"
+    os.makedirs(z)
+    with zipfile.ZipFile(z / "images.zip", "w", zipfile.ZIP_STORED) as f:
+        f.writestr("00000.pgm", b"P5\n4 2\n255\n" + bytes(range(8)))
+    good = bytearray((z / "images.zip").read_bytes())
+    eocd = good.rfind(b"PK\x05\x06")
+    for field, value in ((12, 0xFFFFFFF0), (16, 0x7FFFFFFF), (10, 5000)):      # cd_size, cd_off, n_entries
+        bad = bytearray(good)
+        if field == 10:
+            bad[eocd + field:eocd + field + 2] = struct.pack("<H", value)
+        else:
+            bad[eocd + field:eocd + field + 4] = struct.pack("<I", value)
+        (z / "images.zip").write_bytes(bytes(bad))
+        s2 = api.Sequence(str(z))
+        assert s2.status == 2 and s2.getNumImages() == 0, (field, value)
+        assert b"central directory" in _lib.lib.mdc_last_error()
