@@ -122,43 +122,110 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arms
-def cpu_reference_setup(files):
-    """(kind, run(n_frames, threads) -> seconds, cores).  Prefers the reference's own compiled code."""
-    from oracle import loader
-    from mono_dataset_code_b200 import synthetic as S
-    cores = os.cpu_count() or 1
-    frames = S.frames(16, IN_W, IN_H)
-    if loader.ref_available():
-        R = loader.RefOracle()
-        R.register_image(files["vignette"], files["vignette_pixels"])
-        fov = R.fov(files["camera"])
-        photo = R.photo(files["pcalib"], files["vignette"], IN_W, IN_H)
-        assert fov.valid and photo.valid_vignette
+def workload_name():
+    """One string for both arms (the driver compares the two `config` objects)."""
+    return (f"{IN_W}x{IN_H} mono8 -> {OUT_W}x{OUT_H} f32: GInv[I]*vignetteInv + FOV crop remap per frame "
+            "(unMapImage + undistort<float>, BASELINE configs[1])")
 
-        def run(n_frames, threads):
-            return R.time_frames(fov, photo, frames, n_frames, threads, (1, 1, 0))
-        return "reference", run, cores
-    P = loader.PortOracle()
-    f = P.fov_from_file(files["camera"])
-    rx, ry = f.tables()
-    ginv, _ = P.photo_tables(np.loadtxt(files["pcalib"], dtype=np.float32))
-    _, vinv = P.vignette_maps(files["vignette_pixels"])
 
-    def run(n_frames, threads):
-        return P.time_frames(rx, ry, IN_W, IN_H, OUT_W, OUT_H, ginv, vinv.reshape(-1), frames, n_frames, threads, 3, 1), np.zeros(2)
-    return "port", run, cores
+def config_dict(batch=256):
+    """`config` of the JSON line — the same object on both arms (what differs between them is in `run_config`)."""
+    return {"workload": workload_name(), "flags": "rectify|removeGamma|removeVignette", "pyramid_levels": 1,
+            "frames": "uniform random mono8, 16 distinct (CPU arm) / one resident batch per GPU (GPU arm)",
+            "l2_policy": f"GPU arm: inputs larger than L2 ({batch * IN_W * IN_H >> 20} MiB in, {batch * OUT_W * OUT_H * 4 >> 20} MiB out per step of {batch} frames); "
+                         "CPU arm: per-thread outputs + shared inputs exceed the last-level cache"}
+
+
+class CpuReference:
+    """The reference's own per-frame code on the host cores (oracle/_ref = /root/reference/src/*.cpp compiled unmodified), or the
+    plain-C restatement when that build is absent.  Two figures:
+      single_thread  the reference as shipped: one thread, unMapImage -> undistort<float> per frame (BenchmarkDatasetReader.h:222-223)
+      all_cores      the same loop on every hardware thread: persistent pinned workers, private first-touched buffers, one replica
+                     of the tables per NUMA node; timed inside the library between a start barrier and the last worker's finish."""
+
+    def __init__(self, files, threads=0):
+        from oracle import loader
+        from mono_dataset_code_b200 import synthetic as S
+        self.frames = S.frames(16, IN_W, IN_H)
+        self.cores = os.cpu_count() or 1
+        self.pool = None
+        if loader.ref_available():
+            self.kind = "reference"
+            self.R = R = loader.RefOracle()
+            R.register_image(files["vignette"], files["vignette_pixels"])
+            self.fov = R.fov(files["camera"])
+            self.photo = R.photo(files["pcalib"], files["vignette"], IN_W, IN_H)
+            assert self.fov.valid and self.photo.valid_vignette
+            # The reference's loop does not scale to every hardware thread: beyond a few dozen workers the private
+            # float images (2 x 5 MB per thread) evict each other and throughput FALLS (profiles/r02_cpu_ref_scaling.jsonl).
+            # The CPU arm therefore runs at the best worker count / placement of a short sweep — its fastest configuration.
+            self.sweep = []
+            cands = [(threads, "0")] if threads else [(t, sp) for t in sorted({8, 16, 32, 64, self.cores}) if t <= self.cores for sp in ("0", "1")]
+            best = None
+            for t, spread in cands:
+                os.environ["MDC_REF_SPREAD"] = spread
+                pool = loader.RefPool(R, files["camera"], files["pcalib"], files["vignette"], IN_W, IN_H, self.frames, t, (1, 1, 0))
+                pool.run(2)
+                s = min(pool.run(6)[0], pool.run(6)[0])
+                fps = t * 6 / s
+                self.sweep.append({"threads": t, "spread_over_numa_nodes": spread == "1", "frames_per_s": round(fps, 1)})
+                if best is None or fps > best[0]:
+                    if best is not None:
+                        best[1].close()
+                    best = (fps, pool, spread)
+                else:
+                    pool.close()
+            self.pool = best[1]
+            self.placement = "spread over NUMA nodes" if best[2] == "1" else "compact"
+            self.threads, self.numa_nodes = self.pool.threads, self.pool.numa_nodes
+        else:
+            self.kind = "port"
+            self.P = P = loader.PortOracle()
+            f = P.fov_from_file(files["camera"])
+            self.rx, self.ry = f.tables()
+            self.ginv, _ = P.photo_tables(np.loadtxt(files["pcalib"], dtype=np.float32))
+            _, vinv = P.vignette_maps(files["vignette_pixels"])
+            self.vinv = vinv.reshape(-1)
+            self.threads, self.numa_nodes = (threads or self.cores), None
+
+    def single_thread(self, n=150):
+        if self.kind == "reference":
+            self.R.time_frames(self.fov, self.photo, self.frames, 8, 1, (1, 1, 0))
+            s, st = self.R.time_frames(self.fov, self.photo, self.frames, n, 1, (1, 1, 0))
+            return {"value": n / s, "frames": n, "unmap_ms": 1e3 * st[0] / n, "undistort_ms": 1e3 * st[1] / n}
+        self.P.time_frames(self.rx, self.ry, IN_W, IN_H, OUT_W, OUT_H, self.ginv, self.vinv, self.frames, 8, 1, 3, 1)
+        s = self.P.time_frames(self.rx, self.ry, IN_W, IN_H, OUT_W, OUT_H, self.ginv, self.vinv, self.frames, n, 1, 3, 1)
+        return {"value": n / s, "frames": n}
+
+    def all_cores(self, frames_per_thread):
+        """(frames, seconds) of one all-core pass."""
+        if self.pool is not None:
+            s, _ = self.pool.run(frames_per_thread)
+            return self.threads * frames_per_thread, s
+        n = self.threads * frames_per_thread
+        return n, self.P.time_frames(self.rx, self.ry, IN_W, IN_H, OUT_W, OUT_H, self.ginv, self.vinv, self.frames, n, self.threads, 3, 1)
+
+    def describe(self):
+        return (f"{self.threads} pinned threads" + (f" ({self.placement}) on {self.numa_nodes} NUMA node(s), tables + inputs replicated per node" if self.numa_nodes else "")
+                + f" = the fastest of a sweep over worker counts on this {self.cores}-thread host; private buffers first-touched by their thread; "
+                "timed inside the library; decode/alloc excluded")
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
 
 
 def cpu_baseline(files):
-    kind, run, cores = cpu_reference_setup(files)
-    run(8, 1)                                   # warm caches / page in
-    n1 = 150
-    s1, stages = run(n1, 1)
-    nP = max(cores * 48, 256)
-    sP, _ = run(nP, cores)
-    return {"value": nP / sP, "unit": "frames/s", "cores": cores, "kind": kind,
-            "sample": f"{nP} frames of 1280x1024 (16 distinct, cycled) over {cores} threads; unMapImage+undistort<float>, decode/alloc excluded",
-            "single_thread": {"value": n1 / s1, "frames": n1, "unmap_ms": 1e3 * stages[0] / n1, "undistort_ms": 1e3 * stages[1] / n1}}
+    ref = CpuReference(files)
+    one = ref.single_thread()
+    ref.all_cores(2)                                   # warm-up: page in, spin up
+    fpt = 24
+    n, s = ref.all_cores(fpt)
+    out = {"value": n / s, "unit": "frames/s", "cores": ref.threads, "kind": ref.kind,
+           "sample": f"{n} frames of {IN_W}x{IN_H} (16 distinct, cycled), {fpt} per thread; " + ref.describe(),
+           "single_thread": one, "thread_sweep": getattr(ref, "sweep", None)}
+    ref.close()
+    return out
 
 
 def cpu_calibrator_sample():
@@ -185,28 +252,267 @@ def run_reference_arm(args):
         return
     tmp = tempfile.mkdtemp(prefix="mdc_bench_")
     files = write_calibration(tmp)
-    kind, run, cores = cpu_reference_setup(files)
-    per_step = max(cores * 8, 64)
-    for _ in range(args.warmup):
-        run(max(cores, 16), cores)
-    t0 = time.perf_counter()
+    ref = CpuReference(files)
+    one = ref.single_thread()
+    fpt = 16                                           # frames per thread and step: ~1-2 s of work per step on all cores
+    for _ in range(max(args.warmup, 1)):
+        ref.all_cores(2)
+    frames = secs = 0.0
     for _ in range(args.steps):
-        run(per_step, cores)
-    dt = time.perf_counter() - t0
-    fps = per_step * args.steps / dt
+        n, s = ref.all_cores(fpt)
+        frames += n
+        secs += s
+    fps = frames / secs
+    per_step = ref.threads * fpt
     line = {"impl": "reference", "metric": "frames_per_s_1280x1024_photometric_fov_undistort", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "1280x1024 mono8 -> 1280x1024 f32, GInv LUT * vignette + FOV crop remap (BASELINE configs[1])",
-                       "frames_per_step": per_step, "threads": cores},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                             "sample": f"{per_step} frames/step x {args.steps} steps over {cores} threads"},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (uniform random mono8 frames, synthetic TUM-style calibration; SURVEY.md §8d)",
+            "config": config_dict(),
+            "run_config": {"frames_per_step": per_step, "threads": ref.threads, "numa_nodes": ref.numa_nodes},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.threads, "kind": ref.kind,
+                             "sample": f"{per_step} frames/step x {args.steps} steps ({fpt} per thread and step); " + ref.describe(),
+                             "single_thread": one},
+            "as_shipped_single_thread": one, "thread_sweep": getattr(ref, "sweep", None),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    ref.close()
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(local):
+    """Run this rank (and every thread it starts later) on the CPUs of the NUMA node its GPU hangs off, so that pinned staging
+    buffers, decode threads and the copy engine's host side are local to the GPU's PCIe root (8-GPU e2e 0.55)."""
+    from mono_dataset_code_b200 import _lib
+    info = {"gpu": local, "node": None, "cpus_bound": None}
+    if os.environ.get("MDC_NUMA_BIND", "1") == "0":
+        info["disabled"] = True
+        return info
+    node = int(_lib.lib.mdc_device_numa_node(local))
+    if node < 0:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(node=node, cpus_bound=len(cpus))
+    except OSError:
+        pass
+    return info
+
+
+def pcie_ceiling(dev, n_bytes=256 << 20, reps=5):
+    """Plain pinned-memory copies of the e2e leg's size class: GB/s host->device and device->host (CUDA events)."""
+    import torch
+    host = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    devb = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in {"h2d_gbs": (devb, host), "d2h_gbs": (host, devb)}.items():
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = reps * n_bytes / (a.elapsed_time(b) * 1e-3) / 1e9
+    return out
+
+
+def max_over_ranks(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sharded_estep_leg(args, ctx, comm, dev, rank, world, peak, barrier):
+    """BASELINE configs[4] at N > 1: responseCalib over n = 1000 exposures x 1 MP with the image stack split by PIXEL RANGE over the
+    ranks: E-step, G-step accumulation and rmse run on the local slice; per loop iteration one 256-double
+    all-reduce (G-step) and three 2-double all-reduces (rmse).  Strong scaling: the 1 MP problem is fixed, each rank holds 1/N of it."""
+    import torch
+    import torch.distributed as dist
+    from mono_dataset_code_b200 import sharding
+    n_img, npix = 1000, 1000 * 1000
+    lo, hi = sharding.shard_pixels(npix, rank, world)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242 + rank)
+    data = torch.randint(0, 256, (n_img, hi - lo), dtype=torch.uint8, device=dev, generator=g)
+    t_exp = torch.linspace(0.05, 20.0, n_img, dtype=torch.float64, device=dev)
+    G_tab = torch.linspace(0.0, 255.0, 256, dtype=torch.float64, device=dev)
+    E = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+
+    def ms_of(fn, reps=5):
+        fn(); barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b) / reps, dev, world)
+    est_ms = ms_of(lambda: ctx.estep(data, t_exp, G_tab, E))
+    gsum = torch.zeros(256, dtype=torch.float64, device=dev)
+    gnum = torch.zeros(256, dtype=torch.int64, device=dev)
+    G_new = torch.zeros_like(G_tab)
+
+    def gstep():
+        ctx.rc_gstep_accumulate(data, t_exp, E, gsum, gnum, False)
+        dist.all_reduce(gsum); dist.all_reduce(gnum)
+        ctx.rc_gstep_finish(gsum, gnum, G_new)
+    g_ms = ms_of(gstep, 3)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def rmse():
+        ctx.rc_rmse_accumulate(data, t_exp, G_tab, E, acc)
+        dist.all_reduce(acc)
+    r_ms = ms_of(rmse, 3)
+    # one whole iteration of the loop (G-step, E-step, rescale, 3 x rmse) in C++ on the native communicator
+    loop_ms, how = None, "python host loop over torch.distributed"
+    nits = 3
+    E2, G2 = torch.zeros_like(E), torch.zeros_like(G_tab)
+    barrier()
+    t0 = time.perf_counter()
+    if comm is not None:
+        comm.response_calib_sharded(ctx, data, t_exp, nits, E2, G2)
+        how = "mdc_response_calib_sharded (C++, ncclAllReduce in libmdc_b200_nccl.so)"
+    else:
+        sharding.response_calib_sharded(ctx, data, t_exp, nits, E2, G2)
+    torch.cuda.synchronize()
+    loop_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / nits, dev, world)
+    # G must be identical on every rank
+    Gs = [torch.zeros_like(G2) for _ in range(world)]
+    dist.all_gather(Gs, G2)
+    same = all(bool(torch.equal(Gs[0], x) or torch.equal(torch.nan_to_num(Gs[0]), torch.nan_to_num(x))) for x in Gs[1:])
+    alg = n_img * npix + 8 * npix
+    return {"ms_per_pass": est_ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (est_ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": alg / (est_ms * 1e-3) / 1e9 / (peak * world), "workload": "n=1000 x 1 MP u8 -> f64 E[1 MP]",
+            "sharding": f"pixel-sharded over {world} ranks ({hi - lo} pixels on rank 0), strong scaling", "gstep_ms": g_ms, "rmse_ms": r_ms,
+            "loop_iteration_ms": loop_ms, "loop": how, "collectives_per_iteration": "1 x allreduce(256 f64) [+256 u64 once], 3 x allreduce(2 f64)",
+            "G_identical_on_all_ranks": same}
+
+
+def sequence_leg(args, dev, rank, world, local, numa, barrier):
+    """BASELINE configs[3]: a 1920x1080 sequence of --seq-frames frames, frame-sharded over the ranks (sharding.shard_range).
+    decode_inclusive: DatasetReader's path — JPEG entries of images.zip decoded on the host threads of the rank's NUMA node,
+    H2D, K1, D2H into pinned float images (mdc_seq_prepare; BenchmarkDatasetReader.h:247-276 + :188-243).
+    device_resident: the same number of frames through K1 alone at this geometry (batches of 256 already in HBM)."""
+    import ctypes as C
+    import zipfile
+    import torch
+    import torch.distributed as dist
+    import cv2
+    from mono_dataset_code_b200 import _lib, api, sharding, synthetic as S
+    W, H, K = 1920, 1080, 128
+    root = os.path.join(tempfile.gettempdir(), f"mdc_c4_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}")
+    if rank == 0:
+        os.makedirs(root, exist_ok=True)
+        files = S.write_dataset_dir(root, W, H, W, H, "crop")
+        sizes = []
+        with zipfile.ZipFile(os.path.join(root, "images.zip"), "w", zipfile.ZIP_STORED) as z:
+            base = S.frame(7, W, H, "gradient").reshape(H, W).astype(np.int16)
+            yy, xx = np.mgrid[0:H, 0:W]
+            for i in range(K):          # a textured, slowly changing scene (JPEG size and decode cost of a real sequence, not of noise)
+                img = np.clip(base + 40 * np.sin((xx + 13 * i) * 0.05) * np.cos((yy - 7 * i) * 0.04) + ((xx // 64 + yy // 64 + i) % 2) * 30, 0, 255).astype(np.uint8)
+                ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+                z.writestr(f"{i:05d}.jpg", enc.tobytes())
+                sizes.append(len(enc))
+        with open(os.path.join(root, "times.txt"), "w") as f:
+            for i in range(K):
+                f.write(f"{i} {i * 0.05:.3f} 1.0\n")
+        meta = {"root": root, "jpeg_mean_bytes": float(np.mean(sizes))}
+    else:
+        meta = None
+    if world > 1:
+        box = [meta]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+    root = meta["root"]
+    fov = api.UndistorterFOV(os.path.join(root, "camera.txt"))
+    photo = api.PhotometricUndistorter(os.path.join(root, "pcalib.txt"), os.path.join(root, "vignette.png"), W, H)
+    ctx = api.Context(fov, photo, local)
+    seq = api.Sequence(root + "/")
+    assert seq.getNumImages() == K
+    begin, end = sharding.shard_range(args.seq_frames, rank, world)
+    n_mine = end - begin
+    # host threads: this rank's share of the CPUs it is bound to (ranks on the same NUMA node split them)
+    nodes = [numa]
+    if world > 1:
+        nodes = [None] * world
+        dist.all_gather_object(nodes, numa)
+    same_node = sum(1 for x in nodes if x.get("node") == numa.get("node"))
+    threads = max(1, len(os.sched_getaffinity(0)) // max(1, same_node))
+    n_px = W * H
+    h_out = C.c_void_p()
+    _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_out), K * n_px * 4), "mdc_host_alloc")
+    ptrs = (C.c_void_p * 1)(h_out.value)
+
+    def run_decode(n_frames):
+        v, done = begin, 0
+        while done < n_frames:
+            first = v % K
+            cnt = min(K - first, n_frames - done)
+            _lib.check(_lib.lib.mdc_seq_prepare(ctx._h, seq._h, first, cnt, FLAGS_ALL, ptrs, 1, threads), "mdc_seq_prepare")
+            v += cnt; done += cnt
+    run_decode(min(n_mine, K))            # warm-up: page cache, thread pool, pinned staging
+    barrier()
+    t0 = time.perf_counter()
+    run_decode(n_mine)
+    barrier()
+    dec_s = max_over_ranks(time.perf_counter() - t0, dev, world)
+    _lib.lib.mdc_host_free(h_out)
+    # device-resident: the same frame count through K1 at this geometry
+    B = 256
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+    frames = torch.randint(0, 256, (B, n_px), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((B, n_px), dtype=torch.float32, device=dev)
+    launches = (n_mine + B - 1) // B
+    for _ in range(3):
+        ctx.prepare_batch(frames, FLAGS_ALL, [out])
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(launches):
+        nb = min(B, n_mine - i * B)
+        ctx.prepare_batch(frames[:nb], FLAGS_ALL, [out[:nb]])
+    b.record()
+    torch.cuda.synchronize()
+    res_s = max_over_ranks(a.elapsed_time(b) * 1e-3, dev, world)
+    ctx.close(); seq.close()
+    if rank == 0:
+        try:
+            import shutil
+            shutil.rmtree(root, ignore_errors=True)
+        except Exception:
+            pass
+    total = args.seq_frames
+    alg = total * (n_px + 4 * n_px)
+    return {"workload": f"{W}x{H} mono8 sequence of {total} frames ({K} baseline-JPEG entries of images.zip, cycled), frame-sharded over {world} rank(s) "
+                        "with shard_range; rectify|removeGamma|removeVignette",
+            "decode_inclusive": {"value": total / dec_s, "unit": "frames/s", "seconds": dec_s, "decode_threads_per_rank": threads,
+                                 "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
+                                 "path": "mdc_seq_prepare: zip read + JPEG decode (host) -> pinned -> H2D -> K1 -> D2H, chunks double-buffered"},
+            "device_resident": {"value": total / res_s, "unit": "frames/s", "seconds": res_s, "alg_gbs": alg / res_s / 1e9,
+                                "frames_per_launch": B, "launches_per_rank": launches}}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -219,6 +525,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)       # before any pinned buffer or worker thread exists
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -231,13 +538,22 @@ def run_gpu_arm(args):
     if rank == 0:
         fov = api.UndistorterFOV(files["camera"])
         photo = api.PhotometricUndistorter(files["pcalib"], files["vignette"], IN_W, IN_H)
+    comm, init_how = None, "single GPU: tables uploaded by mdc_ctx_create"
     if world == 1:
         ctx = api.Context(fov, photo, local)
     else:
         from mono_dataset_code_b200 import sharding
-        dims, tabs = sharding.broadcast_calibration(fov, photo, dev)     # one-time NCCL broadcast; no collective in steady state
-        torch.cuda.synchronize()
-        ctx = api.Context.from_device_tables(local, *dims, *tabs)
+        try:
+            # the C++ path (include/mdc_b200_nccl.h): the process group only carries the 128-byte NCCL id; the four tables travel with
+            # ncclBroadcast inside libmdc_b200_nccl.so and every rank's context adopts its copy — no collective in steady state
+            comm = sharding.NativeComm(local)
+            ctx = comm.create_context(fov, photo)
+            init_how = f"native: mdc_ctx_create_broadcast (libmdc_b200_nccl.so, ncclBroadcast x4, NCCL {comm.version})"
+        except (ImportError, OSError) as exc:
+            dims, tabs = sharding.broadcast_calibration(fov, photo, dev)     # same broadcast through torch.distributed
+            torch.cuda.synchronize()
+            ctx = api.Context.from_device_tables(local, *dims, *tabs)
+            init_how = f"torch.distributed broadcast (native helper unavailable: {exc})"
     if args.tma is not None:
         ctx.configure(use_tma=args.tma)
 
@@ -301,6 +617,8 @@ def run_gpu_arm(args):
 
     # ---- BASELINE configs[4]: responseCalib E-step, 1000 exposures x 1 MP, fp64, bit-exact kernel K3 (1 GPU only)
     estep = None
+    if world > 1 and not args.no_estep:
+        estep = sharded_estep_leg(args, ctx, comm, dev, rank, world, peak, barrier)
     if world == 1 and not args.no_estep:
         n_img, npix = 1000, 1000 * 1000
         data = torch.randint(0, 256, (n_img, npix), dtype=torch.uint8, device=dev, generator=g)
@@ -358,6 +676,18 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
     e2e = {"value": world * EB * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": EB * n_in,
            "d2h_bytes_per_step": EB * n_out * 4, "frames_per_step": EB, "steps": e2e_steps}
+    # where each rank's staging memory lives, and what a plain pinned copy reaches on this rank's PCIe link (the e2e leg moves
+    # 5 bytes per output pixel over it: 4 of them device->host)
+    link = pcie_ceiling(dev)
+    if world > 1:
+        numas, links = [None] * world, [None] * world
+        dist.all_gather_object(numas, numa)
+        dist.all_gather_object(links, link)
+    else:
+        numas, links = [numa], [link]
+    e2e["numa"] = numas
+    e2e["pcie_copy_gbs_per_rank"] = links
+    e2e["d2h_bound_frames_per_s"] = sum(l["d2h_gbs"] for l in links) * 1e9 / (n_out * 4)
     # latency of ONE frame through the same entry point (what DatasetReader::getImage does per call)
     for _ in range(3):
         ctx.prepare_batch_host(np_in[:1], FLAGS_ALL, [h_out.value])
@@ -367,23 +697,29 @@ def run_gpu_arm(args):
     e2e["single_frame_ms"] = 1e3 * (time.perf_counter() - t0) / 50
     _lib.lib.mdc_host_free(h_in); _lib.lib.mdc_host_free(h_out)
 
+    c4 = None
+    if not args.no_seq:
+        try:
+            c4 = sequence_leg(args, dev, rank, world, local, numa, barrier)
+        except Exception as exc:          # the headline line must not depend on this extra
+            c4 = {"error": repr(exc)}
     if rank == 0:
         line = {"metric": "frames_per_s_1280x1024_photometric_fov_undistort", "value": value, "unit": "frames/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (uniform random mono8 frames, synthetic TUM-style calibration; SURVEY.md §8d)",
-                "config": {"workload": "1280x1024 mono8 -> 1280x1024 f32: GInv[I]*vignetteInv + FOV crop remap, fused K1 (BASELINE configs[1])",
-                           "frames_per_step_per_gpu": B, "flags": "rectify|removeGamma|removeVignette", "pyramid_levels": 1,
-                           "parallelism": f"frame-sharded dp{world}, tables NCCL-broadcast at init, no steady-state collective",
-                           "l2_policy": f"inputs larger than L2 ({B * n_in >> 20} MiB in, {B * n_out * 4 >> 20} MiB out per step)",
-                           "loader": ({0: "ldg", 1: "tma", 2: "tex"}[args.tma] if args.tma is not None else
-                                      "auto(" + ("tex" if ctx.loader_usable("tex") else "tma" if ctx.loader_usable("tma") else "ldg") + ")")},
+                "config": config_dict(B),
+                "run_config": {"frames_per_step_per_gpu": B,
+                               "parallelism": f"frame-sharded dp{world}, tables NCCL-broadcast at init, no steady-state collective",
+                               "init": init_how,
+                               "loader": ({0: "ldg", 1: "tma", 2: "tex", 3: "hybrid"}[args.tma] if args.tma is not None else
+                                          "auto(" + ctx.auto_loader() + ")")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (TRAFFIC["dram_bytes_per_frame"] * B / 1e9 if TRAFFIC else None),
                              "traffic_note": (TRAFFIC["note"] if TRAFFIC else "no ncu capture committed"),
                              "peak_source": peak_src, "kernel": "fused_prepare_kernel",
                              "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_FRAME, "launch_ms": k1_ms},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c5_estep": estep}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c4_sequence": c4, "c5_estep": estep}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(files)
             if estep is not None:
@@ -409,6 +745,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--levels", type=int, default=1, help="pyramid levels for --only-kernel sweeps")
     ap.add_argument("--no-estep", action="store_true", help="skip the configs[4] E-step leg")
+    ap.add_argument("--no-seq", action="store_true", help="skip the configs[3] 1920x1080 sequence leg")
+    ap.add_argument("--seq-frames", type=int, default=10000, help="frames of the configs[3] sequence (whole job)")
     ap.add_argument("--only-kernel", action="store_true", help="tuning sweeps: device-resident K1 timing only (no pyramid / e2e / cpu legs)")
     ap.add_argument("--geom", default=None, help="WxH for --only-kernel sweeps (default 1280x1024)")
     args = ap.parse_args()

@@ -144,9 +144,13 @@ long long mdc_ctx_launch_count(const mdc_ctx* c);
 #define MDC_LOADER_TEX 2   /* texture gather (tld4) straight from the frames: taps on the TEX pipe, look-ups + stores on the LSU pipe
                               (row pitch multiple of the device's texture pitch alignment; enabled by a bit-exactness self-check
                               against the other loaders when the context is created) */
+#define MDC_LOADER_HYBRID 3 /* TMA-staged and texture-gather kernels side by side on every SM, the batch split between them:
+                              the LSU pipe and the TEX pipe each carry part of the tap traffic */
 int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm);
 /* 1 if `loader` (MDC_LOADER_*) can be used with this context's geometry on this device, else 0. */
 int mdc_ctx_loader_usable(const mdc_ctx* c, int loader);
+/* The MDC_LOADER_* that use_tma = -1 resolves to for this context. */
+int mdc_ctx_auto_loader(const mdc_ctx* c);
 
 /* -------------------------------------------------------------------------------------
  * Device-resident per-frame operators (all pointers are DEVICE pointers; `stream` is a
@@ -250,6 +254,20 @@ int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const doubl
 int mdc_rc_rescale(mdc_ctx* c, int npix, double* d_E, double* d_G, double* factor_host);
 int mdc_rc_rmse(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E, double out_host[2]);
 int mdc_response_calib(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, int nits, double* d_E, double* d_G, double* log_host);
+/* The two global reductions of the loop as per-rank partials, for PIXEL-SHARDED runs (pixels are independent in every pass,
+ * main_responseCalib.cpp:317-346; each rank holds its slice of every image as [n][npix_local]).  The accumulators stay on the device:
+ *   mdc_rc_gstep_accumulate  d_gsum256[b] = sum E[k]*t[i], d_gnum256[b] = count over this rank's pixels (:290-299); reuse_counts != 0
+ *                            keeps d_gnum256 (it depends on the images only) — all-reduce(sum) both arrays across ranks, then
+ *   mdc_rc_gstep_finish      G = gsum/gnum with the reference's sequential gap extrapolation (:300-304), identically on every rank;
+ *   mdc_rc_rmse_accumulate   d_acc2 = {sum (G[b]-t*E)^2 * 1e-10, count} over this rank's pixels (:50-69) — all-reduce(sum), then
+ *                            rmse = 1e5*sqrt(acc[0]/acc[1]).
+ * E-step, E-init and rescale need no collective (mdc_estep / mdc_rc_einit / mdc_rc_rescale on the local slice; G is replicated).
+ * mdc_response_calib_sharded (include/mdc_b200_nccl.h) is the whole loop over NCCL. */
+int mdc_rc_gstep_accumulate(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E,
+                            double* d_gsum256, unsigned long long* d_gnum256, int reuse_counts, mdc_stream stream);
+int mdc_rc_gstep_finish(mdc_ctx* c, const double* d_gsum256, const unsigned long long* d_gnum256, double* d_G, mdc_stream stream);
+int mdc_rc_rmse_accumulate(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E,
+                           double* d_acc2, mdc_stream stream);
 
 /* -------------------------------------------------------------------------------------
  * Host-buffer entry points (what the compat classes call): H2D copy, kernels, D2H copy.
@@ -262,8 +280,12 @@ int mdc_undistort_f32_host(mdc_ctx* c, const float* in, float* out, int n_pix_in
  * Internally chunked and double-buffered so H2D, kernel and D2H overlap. */
 int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_frames, unsigned flags,
                            float* const* out_levels, int levels);
-int mdc_host_alloc(void** p, size_t bytes);   /* pinned host memory */
+/* Pinned host memory for the calling thread's current CUDA device, placed on the NUMA node that device is attached to
+ * (MDC_NUMA_BIND=0 disables the placement). */
+int mdc_host_alloc(void** p, size_t bytes);
 void mdc_host_free(void* p);
+/* NUMA node of a CUDA device (sysfs: PCI device -> numa_node), or -1 if unknown. */
+int mdc_device_numa_node(int device);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,21 @@ extern "C" {
 int mdc_ctx_create_broadcast(void* nccl_comm, int rank, int root, int device, const mdc_fov* fov, const mdc_photo* photo,
                              mdc_ctx** out);
 
+/* Communicator set-up for hosts without an NCCL binding of their own: rank 0 calls mdc_nccl_unique_id, ships the 128 bytes to the
+ * other ranks by any means (file, socket, the launcher's store), every rank calls mdc_nccl_comm_create. */
+int mdc_nccl_unique_id(char id_out[128]);
+int mdc_nccl_comm_create(const char id[128], int world, int rank, int device, void** comm_out);
+void mdc_nccl_comm_destroy(void* comm);
+int mdc_nccl_version(void);
+
+/* responseCalib's optimisation loop (main_responseCalib.cpp:281-362) PIXEL-SHARDED over the ranks of `nccl_comm`:
+ * d_data_local = this rank's slice of every image, [n][npix_local] u8 (slices of a multiple of 16 pixels keep the fast streaming
+ * kernels); d_E_local [npix_local]; d_G [256] is replicated — identical on every rank on return.  Per iteration: one ncclAllReduce of
+ * 256 doubles (+ 256 u64 counts in the first iteration) for the G-step and three of 2 doubles for the rmse evaluations; E-step, E-init
+ * and rescale are collective-free.  log_host as in mdc_response_calib (global rmse / count).  Same call on every rank. */
+int mdc_response_calib_sharded(mdc_ctx* c, void* nccl_comm, int device, const uint8_t* d_data_local, int n, int npix_local,
+                               const double* d_t, int nits, double* d_E_local, double* d_G, double* log_host);
+
 #ifdef __cplusplus
 }
 #endif

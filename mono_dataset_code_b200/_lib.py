@@ -70,6 +70,7 @@ SIGNATURES = {
     "mdc_ctx_launch_count": (C.c_longlong, [_vp]),
     "mdc_ctx_configure": (C.c_int, [_vp, C.c_int, C.c_int]),
     "mdc_ctx_loader_usable": (C.c_int, [_vp, C.c_int]),
+    "mdc_ctx_auto_loader": (C.c_int, [_vp]),
     "mdc_unmap_u8": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_uint, _vp]),
     "mdc_undistort_u8": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "mdc_undistort_f32": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
@@ -82,12 +83,16 @@ SIGNATURES = {
     "mdc_rc_rescale": (C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(C.c_double)]),
     "mdc_rc_rmse": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     "mdc_response_calib": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(C.c_double)]),
+    "mdc_rc_gstep_accumulate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mdc_rc_gstep_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mdc_rc_rmse_accumulate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdc_unmap_u8_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint]),
     "mdc_undistort_u8_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "mdc_undistort_f32_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "mdc_prepare_batch_host": (C.c_int, [_vp, _vp, C.c_int, C.c_uint, C.POINTER(_vp), C.c_int]),
     "mdc_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "mdc_host_free": (None, [_vp]),
+    "mdc_device_numa_node": (C.c_int, [C.c_int]),
 }
 
 

@@ -242,13 +242,17 @@ class Context:
     def __del__(self):
         self.close()
 
-    LOADERS = {"auto": -1, "ldg": 0, "tma": 1, "tex": 2}
+    LOADERS = {"auto": -1, "ldg": 0, "tma": 1, "tex": 2, "hybrid": 3}
 
     def configure(self, use_tma: int = -1, ctas_per_sm: int = 0):
         """use_tma: the K1 input loader, -1 auto / 0 LDG / 1 TMA / 2 texture gather (MDC_LOADER_*), or its name."""
         if isinstance(use_tma, str):
             use_tma = self.LOADERS[use_tma]
         check(lib.mdc_ctx_configure(self._h, use_tma, ctas_per_sm), "mdc_ctx_configure")
+
+    def auto_loader(self) -> str:
+        i = int(lib.mdc_ctx_auto_loader(self._h))
+        return [k for k, v in self.LOADERS.items() if v == i][0]
 
     def loader_usable(self, loader) -> bool:
         if isinstance(loader, str):
@@ -321,6 +325,21 @@ class Context:
         check(lib.mdc_rc_rmse(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
                               C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), out), "mdc_rc_rmse")
         return out[0], out[1]
+
+    # the two reductions as per-rank partials (pixel-sharded runs; accumulators are CUDA tensors: gsum f64[256], gnum i64[256], acc f64[2])
+    def rc_gstep_accumulate(self, data, t, E, gsum, gnum, reuse_counts=False):
+        check(lib.mdc_rc_gstep_accumulate(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                                          C.c_void_p(E.data_ptr()), C.c_void_p(gsum.data_ptr()), C.c_void_p(gnum.data_ptr()),
+                                          int(bool(reuse_counts)), self._stream(data)), "mdc_rc_gstep_accumulate")
+
+    def rc_gstep_finish(self, gsum, gnum, G):
+        check(lib.mdc_rc_gstep_finish(self._h, C.c_void_p(gsum.data_ptr()), C.c_void_p(gnum.data_ptr()), C.c_void_p(G.data_ptr()),
+                                      self._stream(G)), "mdc_rc_gstep_finish")
+
+    def rc_rmse_accumulate(self, data, t, G, E, acc):
+        check(lib.mdc_rc_rmse_accumulate(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                                         C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), C.c_void_p(acc.data_ptr()), self._stream(data)),
+              "mdc_rc_rmse_accumulate")
 
     def response_calib(self, data, t, nits, E, G):
         """The optimisation loop of responseCalib's main(); returns the per-iteration log [nits, 4]."""

@@ -516,6 +516,7 @@ cudaError_t launch_fused(const FusedParams& p, const TmaMaps* maps, int grid, in
     FusedKernelFn fn = fused_variant(tma, p.use_vig != 0, p.levels > 1, min_ctas);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
+    if (p.carveout > 0 && (e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, p.carveout)) != cudaSuccess) return e;
     static const TmaMaps none = {};
     fn<<<grid, tma ? kConsumers + 32 : kConsumers, smem, stream>>>(p, tma ? *maps : none);
     return cudaGetLastError();
@@ -789,6 +790,7 @@ cudaError_t launch_fused_tex(const FusedParams& p, const TexSet& texs, int n_chu
     FusedTexFn fn = fused_tex_variant(p.use_vig != 0, p.levels > 1, min_ctas, prefetch, study);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTexSmemBytes);
     if (e != cudaSuccess) return e;
+    if (p.carveout > 0 && (e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, p.carveout)) != cudaSuccess) return e;
     const dim3 grid(static_cast<unsigned>((p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta), static_cast<unsigned>(n_chunks));
     fn<<<grid, kTexThreads, kTexSmemBytes, stream>>>(p, texs);
     return cudaGetLastError();
@@ -1557,26 +1559,40 @@ cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cud
     rc_einit_kernel<<<(npix + 255) / 256, 256, 0, s>>>(data, n, static_cast<size_t>(npix), E);
     return cudaGetLastError();
 }
-cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G,
-                            bool reuse_counts, cudaStream_t s) {
+// G-step in two halves so that a pixel-sharded run can all-reduce the 2 x 256 accumulators in between:
+//   accumulate  gsum[b] = sum E[k]*t[i], gnum[b] = count over THIS pixel range (main_responseCalib.cpp:290-299); with reuse_counts the
+//               caller's gnum (which depends on the images only) is kept and only the sums are rebuilt
+//   finish      G = gsum/gnum + sequential gap extrapolation (:300-304)
+cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
+                                  bool reuse_counts, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(gsum, 0, 256 * sizeof(double), s);
     if (e != cudaSuccess) return e;
     const bool stream = stream_ok(data, npix);
-    reuse_counts = reuse_counts && stream;
     if (!reuse_counts) {
         e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;
     }
+    if (npix <= 0 || n <= 0) return cudaSuccess;
     if (stream) {
         const StreamArgs a{data, n, static_cast<uint32_t>(npix), t};
-        e = reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, gsum, gnum}, s)
-                         : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, gsum, gnum}, s);
-        if (e != cudaSuccess) return e;
-    } else {
-        rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+        return reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, gsum, gnum}, s)
+                            : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, gsum, gnum}, s);
     }
+    if (reuse_counts) return cudaErrorNotSupported;      // the generic kernel always counts (callers check rc_counts_reusable first)
+    rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s) {
     rc_gstep_finish_kernel<<<1, 256, 0, s>>>(gsum, gnum, G);
     return cudaGetLastError();
+}
+bool rc_counts_reusable(const uint8_t* data, int npix) { return stream_ok(data, npix); }
+
+cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G,
+                            bool reuse_counts, cudaStream_t s) {
+    cudaError_t e = launch_rc_gstep_accum(data, n, npix, t, E, gsum, gnum, reuse_counts && rc_counts_reusable(data, npix), s);
+    if (e != cudaSuccess) return e;
+    return launch_rc_gstep_finish(gsum, gnum, G, s);
 }
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s) {
     rc_factor_kernel<<<1, 32, 0, s>>>(G, factor);

@@ -63,6 +63,7 @@ struct FusedParams {
     int chunk_frames;            // frames per schedule chunk (L2 residency of the inputs)
     int tma_stages;              // depth of the TMA stage ring (2..kMaxStages)
     int tiles_per_cta;           // texture-gather loader: consecutive tiles one CTA works through (grid.x = ceil(n_tiles / tiles_per_cta))
+    int carveout;                // host side only: preferred shared-memory carve-out in percent for this launch, 0 = the driver's choice
 };
 
 // Floor-study switches (profiles/r02_k1_floor_study.md): which of the three shared-memory/LSU consumers of the frame loop run.
@@ -96,6 +97,10 @@ cudaError_t launch_rc_leak_padding(const uint8_t* in, uint8_t* out, int n, int w
 cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cudaStream_t s);
 cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
                             double* G, bool reuse_counts, cudaStream_t s);
+cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
+                                  bool reuse_counts, cudaStream_t s);
+cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s);
+bool rc_counts_reusable(const uint8_t* data, int npix);      // reuse_counts is only available on the bulk-copy streaming path
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s);
 cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s);
 

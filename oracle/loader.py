@@ -69,6 +69,13 @@ class RefOracle:
         L.oref_time_frames.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, _f64p]
         L.mdc_shim_register_image.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.oref_pool_create.restype = C.c_void_p
+        L.oref_pool_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oref_pool_run.restype = C.c_double
+        L.oref_pool_run.argtypes = [C.c_void_p, C.c_int, _f64p]
+        L.oref_pool_threads.argtypes = [C.c_void_p]
+        L.oref_pool_numa_nodes.argtypes = [C.c_void_p]
+        L.oref_pool_destroy.argtypes = [C.c_void_p]
 
     # -- image registry of the shim's cv::imread (pixels decoded by the caller, e.g. with cv2)
     def register_image(self, path: str, pixels: np.ndarray) -> None:
@@ -94,6 +101,36 @@ class RefOracle:
         s = self.lib.oref_time_frames(fov.h, photo.h, _p(frames, _u8p), frames.shape[0], n_frames, threads,
                                       flags[0], flags[1], flags[2], _p(st, _f64p))
         return s, st
+
+
+class RefPool:
+    """All-core arm of the reference's per-frame path: persistent pinned workers with private buffers, one replica of the
+    reference objects and of the input frames per NUMA node, timed inside the library (oracle/ref/ref_wrapper.cpp)."""
+
+    def __init__(self, o: RefOracle, camera_txt: str, pcalib: str, vignette: str, w: int, h: int, frames: np.ndarray,
+                 threads: int = 0, flags=(1, 1, 0)):
+        self.L = o.lib
+        frames = np.ascontiguousarray(frames, np.uint8)
+        self.h = self.L.oref_pool_create(camera_txt.encode(), pcalib.encode(), vignette.encode(), w, h, _p(frames, _u8p),
+                                         frames.shape[0], threads, flags[0], flags[1], flags[2])
+        if not self.h:
+            raise RuntimeError("oref_pool_create failed (invalid calibration?)")
+        self.threads = int(self.L.oref_pool_threads(self.h))
+        self.numa_nodes = int(self.L.oref_pool_numa_nodes(self.h))
+
+    def run(self, frames_per_worker: int):
+        """(seconds measured inside the library, (min, max) per-worker busy seconds) for threads*frames_per_worker frames."""
+        mm = np.zeros(2, np.float64)
+        s = float(self.L.oref_pool_run(self.h, frames_per_worker, _p(mm, _f64p)))
+        return s, (float(mm[0]), float(mm[1]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.oref_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class RefFov:

@@ -109,4 +109,224 @@ double oref_time_frames(void* hf, void* hp, const unsigned char* frames, int n_d
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ----------------------------------------------------- all-core CPU arm: persistent worker pool
+// What a maintainer would do to run the reference's per-frame path on every core: one worker per hardware thread, pinned,
+// with PRIVATE temp/output buffers that live as long as the pool and are first-touched by the worker that uses them, one
+// replica of the two reference objects (remap tables, vignette map) and of the input frames per NUMA node, built by a
+// thread running on that node, and a start barrier so that the timed region contains frame work only (steady_clock inside
+// the library: from releasing the workers to the last one finishing).  Each frame is the reference's own sequence
+// (BenchmarkDatasetReader.h:222-223): unMapImage into the temp buffer, then undistort<float>.
+}  // extern "C" (pool internals below are C++)
+
+#include <sched.h>
+#include <unistd.h>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <mutex>
+
+namespace {
+
+struct NodeReplica {
+    UndistorterFOV* fov;
+    PhotometricUndistorter* photo;
+    std::vector<unsigned char> frames;
+    NodeReplica() : fov(0), photo(0) {}
+};
+
+struct RefPool {
+    std::string camera, pcalib, vignette;
+    int w, h, n_in, n_out, n_distinct, flags[3];
+    const unsigned char* src_frames;
+    std::vector<int> cpus;              // cpu each worker is pinned to
+    std::vector<int> node_of_worker;
+    std::vector<NodeReplica> nodes;
+    std::vector<std::thread> threads;
+    std::mutex mu, build_mu;
+    std::condition_variable cv_go, cv_done;
+    long generation;
+    int frames_per_worker, pending, ready;
+    bool quit, failed;
+    std::vector<double> busy_s;
+    std::chrono::steady_clock::time_point t_last_done;
+    RefPool() : generation(0), frames_per_worker(0), pending(0), ready(0), quit(false), failed(false) {}
+};
+
+int node_of_cpu(int cpu) {
+    for (int node = 0; node < 64; ++node) {
+        char path[128];
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+        std::ifstream f(path);
+        if (!f.good()) continue;
+        std::string list;
+        std::getline(f, list);
+        size_t pos = 0;
+        while (pos < list.size()) {
+            int a = 0, b = 0, used = 0;
+            if (sscanf(list.c_str() + pos, "%d-%d%n", &a, &b, &used) == 2) { if (cpu >= a && cpu <= b) return node; }
+            else if (sscanf(list.c_str() + pos, "%d%n", &a, &used) == 1) { if (cpu == a) return node; }
+            else break;
+            pos += used;
+            if (pos < list.size() && list[pos] == ',') ++pos;
+        }
+    }
+    return 0;
+}
+
+void pool_worker(RefPool* P, int t) {
+    const char* pin = getenv("MDC_REF_PIN");      // "0": leave placement to the kernel (A/B of the pinning itself)
+    if (!(pin && pin[0] == '0')) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(P->cpus[t], &set);
+        sched_setaffinity(0, sizeof set, &set);
+    }
+    const int node = P->node_of_worker[t];
+    {   // the first worker of a node builds that node's replica (its pages are first-touched here, on this node)
+        std::lock_guard<std::mutex> lk(P->build_mu);
+        NodeReplica& R = P->nodes[node];
+        if (!R.fov) {
+            R.fov = new UndistorterFOV(P->camera.c_str());
+            R.photo = new PhotometricUndistorter(P->pcalib, P->vignette, P->w, P->h);
+            R.frames.assign(P->src_frames, P->src_frames + (size_t)P->n_distinct * P->n_in);
+            if (!R.fov->isValid() || !R.photo->validVignette) P->failed = true;
+        }
+    }
+    std::vector<float> tmp(P->n_in, 0.0f), out(P->n_out, 0.0f);      // private, first-touched by this (pinned) thread
+    NodeReplica& R = P->nodes[node];
+    long seen = 0;
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        ++P->ready;
+        P->cv_done.notify_all();
+    }
+    for (;;) {
+        int n;
+        {
+            std::unique_lock<std::mutex> lk(P->mu);
+            P->cv_go.wait(lk, [&] { return P->quit || P->generation != seen; });
+            if (P->quit) return;
+            seen = P->generation;
+            n = P->frames_per_worker;
+        }
+        const auto a = std::chrono::steady_clock::now();
+        for (int f = 0; f < n; ++f) {
+            unsigned char* src = &R.frames[(size_t)((t + f) % P->n_distinct) * P->n_in];
+            R.photo->unMapImage(src, &tmp[0], P->n_in, P->flags[0] != 0, P->flags[1] != 0, P->flags[2] != 0);
+            R.fov->undistort<float>(&tmp[0], &out[0], P->n_in, P->n_out);
+        }
+        const auto b = std::chrono::steady_clock::now();
+        {
+            std::lock_guard<std::mutex> lk(P->mu);
+            P->busy_s[t] = std::chrono::duration<double>(b - a).count();
+            if (--P->pending == 0) { P->t_last_done = b; P->cv_done.notify_all(); }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// threads <= 0: one worker per CPU of the process's affinity mask.  Returns 0 on failure.
+void* oref_pool_create(const char* camera_txt, const char* pcalib, const char* vignette, int w, int h, const unsigned char* frames,
+                       int n_distinct, int threads, int gamma, int vignette_flag, int kill) {
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    std::vector<int> cpus;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
+    if (cpus.empty()) cpus.push_back(0);
+    if (threads <= 0) threads = (int)cpus.size();
+    RefPool* P = new RefPool();
+    P->camera = camera_txt; P->pcalib = pcalib; P->vignette = vignette;
+    P->w = w; P->h = h; P->n_distinct = n_distinct; P->src_frames = frames;
+    P->flags[0] = gamma; P->flags[1] = vignette_flag; P->flags[2] = kill;
+    {   // geometry from a throw-away object (the replicas are built by the workers)
+        UndistorterFOV probe(camera_txt);
+        if (!probe.isValid()) { delete P; return 0; }
+        P->n_in = probe.getInputDims()[0] * probe.getInputDims()[1];
+        P->n_out = probe.getOutputDims()[0] * probe.getOutputDims()[1];
+    }
+    // placement of fewer workers than CPUs: "spread" deals them round-robin over the NUMA nodes (each node's CPUs in affinity
+    // order), "compact" fills the CPUs in affinity order
+    const char* spread_env = getenv("MDC_REF_SPREAD");
+    if (spread_env && spread_env[0] == '1') {
+        std::vector<std::vector<int> > by_node;
+        for (size_t i = 0; i < cpus.size(); ++i) {
+            const size_t nd = (size_t)node_of_cpu(cpus[i]);
+            if (by_node.size() <= nd) by_node.resize(nd + 1);
+            by_node[nd].push_back(cpus[i]);
+        }
+        std::vector<int> order;
+        for (size_t k = 0; order.size() < cpus.size(); ++k)
+            for (size_t nd = 0; nd < by_node.size(); ++nd)
+                if (k < by_node[nd].size()) order.push_back(by_node[nd][k]);
+        cpus.swap(order);
+    }
+    int max_node = 0;
+    for (int t = 0; t < threads; ++t) {
+        P->cpus.push_back(cpus[t % cpus.size()]);
+        P->node_of_worker.push_back(node_of_cpu(P->cpus.back()));
+        if (P->node_of_worker.back() > max_node) max_node = P->node_of_worker.back();
+    }
+    P->nodes.resize(max_node + 1);
+    P->busy_s.assign(threads, 0.0);
+    for (int t = 0; t < threads; ++t) P->threads.push_back(std::thread(pool_worker, P, t));
+    {
+        std::unique_lock<std::mutex> lk(P->mu);
+        P->cv_done.wait(lk, [&] { return P->ready == threads; });
+    }
+    P->src_frames = 0;      // every node holds its own copy now
+    if (P->failed) { extern void oref_pool_destroy(void*); oref_pool_destroy(P); return 0; }
+    return P;
+}
+
+int oref_pool_threads(void* h) { return (int)((RefPool*)h)->threads.size(); }
+int oref_pool_numa_nodes(void* h) {
+    RefPool* P = (RefPool*)h;
+    int n = 0;
+    for (size_t i = 0; i < P->nodes.size(); ++i) n += P->nodes[i].fov != 0;
+    return n;
+}
+
+// Every worker processes frames_per_worker frames.  Returns the seconds from releasing the workers to the last one finishing
+// (steady_clock, inside this call); busy_minmax[0..1] = shortest / longest per-worker busy time.
+double oref_pool_run(void* h, int frames_per_worker, double* busy_minmax) {
+    RefPool* P = (RefPool*)h;
+    std::chrono::steady_clock::time_point t0;
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        P->frames_per_worker = frames_per_worker;
+        P->pending = (int)P->threads.size();
+        ++P->generation;
+        t0 = std::chrono::steady_clock::now();
+    }
+    P->cv_go.notify_all();
+    std::unique_lock<std::mutex> lk(P->mu);
+    P->cv_done.wait(lk, [&] { return P->pending == 0; });
+    if (busy_minmax) {
+        busy_minmax[0] = busy_minmax[1] = P->busy_s[0];
+        for (size_t t = 1; t < P->busy_s.size(); ++t) {
+            if (P->busy_s[t] < busy_minmax[0]) busy_minmax[0] = P->busy_s[t];
+            if (P->busy_s[t] > busy_minmax[1]) busy_minmax[1] = P->busy_s[t];
+        }
+    }
+    return std::chrono::duration<double>(P->t_last_done - t0).count();
+}
+
+void oref_pool_destroy(void* h) {
+    RefPool* P = (RefPool*)h;
+    if (!P) return;
+    {
+        std::lock_guard<std::mutex> lk(P->mu);
+        P->quit = true;
+    }
+    P->cv_go.notify_all();
+    for (size_t t = 0; t < P->threads.size(); ++t) P->threads[t].join();
+    for (size_t i = 0; i < P->nodes.size(); ++i) { delete P->nodes[i].fov; delete P->nodes[i].photo; }
+    delete P;
+}
+
 }  // extern "C"

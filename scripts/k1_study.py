@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--geom", default="1280x1024")
     ap.add_argument("--quick", action="store_true", help="loader A/B only, no study / sweeps")
+    ap.add_argument("--hybrid", action="store_true", help="sweep the hybrid loader's split and residency knobs")
     args = ap.parse_args()
     import torch
     from mono_dataset_code_b200 import api, synthetic as S
@@ -48,14 +49,14 @@ def main():
         pass
 
     def run(name, loader, env, levels=1):
-        for k in ("MDC_K1_STUDY", "MDC_TEX_TILES", "MDC_TEX_PREFETCH", "MDC_CTAS_PER_SM", "MDC_CHUNK_FRAMES", "MDC_TEX_MAX_ROWS"):
+        for k in ("MDC_K1_STUDY", "MDC_TEX_TILES", "MDC_TEX_PREFETCH", "MDC_CTAS_PER_SM", "MDC_CHUNK_FRAMES", "MDC_TEX_MAX_ROWS", "MDC_HYB_TEX_PCT", "MDC_HYB_STG_CTAS", "MDC_K1_CARVEOUT"):
             os.environ.pop(k, None)
         os.environ.update({k: str(v) for k, v in env.items()})
         ctx = api.Context(fov, photo, 0)
         if not ctx.loader_usable(loader):
             print(json.dumps({"config": name, "loader": loader, "skipped": "loader not usable"}), flush=True)
             return
-        ctx.configure(use_tma=loader)
+        ctx.configure(use_tma=loader, ctas_per_sm=int(env.get("MDC_CTAS_PER_SM", 0)))
         try:
             for _ in range(3):
                 ctx.prepare_batch(frames, 7, outs[:levels])
@@ -77,6 +78,15 @@ def main():
 
     for loader in ("tex", "tma"):
         run("product", loader, {})
+    if args.hybrid:
+        for stg in (2, 1):
+            for pct in (25, 38, 50, 63):
+                for tex_ctas in (3, 4):
+                    run(f"hybrid tex {pct}% stg_ctas={stg} tex_ctas={tex_ctas}", "hybrid", {"MDC_HYB_TEX_PCT": pct, "MDC_HYB_STG_CTAS": stg, "MDC_CTAS_PER_SM": tex_ctas})
+        run("hybrid tex 38% stg_ctas=2 prefetch", "hybrid", {"MDC_HYB_TEX_PCT": 38, "MDC_HYB_STG_CTAS": 2, "MDC_TEX_PREFETCH": 1})
+        run("hybrid tex 38% stg_ctas=1 prefetch tex_ctas=2", "hybrid", {"MDC_HYB_TEX_PCT": 38, "MDC_HYB_STG_CTAS": 1, "MDC_TEX_PREFETCH": 1, "MDC_CTAS_PER_SM": 2})
+        run("hybrid tex 38% pyramid", "hybrid", {"MDC_HYB_TEX_PCT": 38, "MDC_HYB_STG_CTAS": 2}, levels=5)
+        return
     if args.quick:
         return
     names = {0: "none (loop skeleton)", 1: "taps only", 2: "LUT only", 3: "taps + LUT", 4: "stores only", 5: "taps + stores", 6: "LUT + stores"}

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CALIBS, BIG_CALIBS, assert_bits_equal
+from conftest import CALIBS, BIG_CALIBS, ROOT, assert_bits_equal
 from mono_dataset_code_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
@@ -46,11 +46,11 @@ def mixed_frames(n, w, h):
     return np.stack([S.frame(i, w, h, kinds[i % len(kinds)]) for i in range(n)])
 
 
-LOADER_ID = {"ldg": 0, "tma": 1, "tex": 2}
+LOADER_ID = {"ldg": 0, "tma": 1, "tex": 2, "hybrid": 3}
 
 
 def select_loader(prep, loader):
-    """Force one of K1's three input loaders (include/mdc_b200.h MDC_LOADER_*); skip where it cannot describe the geometry."""
+    """Force one of K1's input loaders (include/mdc_b200.h MDC_LOADER_*); skip where it cannot describe the geometry."""
     if not prep.ctx.loader_usable(loader):
         pytest.skip(f"the {loader} loader is not usable for this geometry on this device (the other loaders cover it)")
     prep.ctx.configure(use_tma=LOADER_ID[loader])
@@ -493,3 +493,125 @@ def test_unusual_geometries(cfg, api, port, dataset_dir):
                 exp = port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], *flags), ow, oh, levels)
                 for l in range(levels):
                     assert_bits_equal(outs[l][i], exp[l], f"{cfg[:4]} tma={use_tma} flags={flags} frame={i} level={l}")
+
+
+@pytest.mark.parametrize("npix,split", [(96 * 64, 3072), (50 * 30, 701)], ids=["bulk_loader_slices", "ragged_slices"])
+def test_pixel_sharded_calibrator_partials_one_gpu(api, port, npix, split):
+    """SURVEY.md §8e row 2 on one device: the image stack cut into two pixel slices, each processed as a rank would
+    (mdc_rc_gstep_accumulate / mdc_rc_rmse_accumulate on its slice), the partial accumulators summed like the all-reduce does,
+    then finished — against the unsharded kernels and the oracle; then the whole sharded host loop (world size 1) against
+    mdc_response_calib."""
+    from mono_dataset_code_b200 import sharding
+    rng = np.random.default_rng(77)
+    n = 19
+    data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+    data[:, 40:90] = 255
+    t = rng.uniform(0.05, 20.0, n).astype(np.float32).astype(np.float64)
+    ctx = api.Context(None, None, 0)
+    dev = torch.device("cuda", 0)
+    dt = torch.from_numpy(t).to(dev)
+    slices = [torch.from_numpy(np.ascontiguousarray(data[:, :split])).to(dev), torch.from_numpy(np.ascontiguousarray(data[:, split:])).to(dev)]
+    E_ref = port.einit(data)
+    Es = []
+    for s in slices:
+        E = torch.zeros(s.shape[1], dtype=torch.float64, device=dev)
+        ctx.rc_einit(s, E)
+        Es.append(E)
+    assert_bits_equal(torch.cat(Es).cpu().numpy(), E_ref, "sliced E-init")
+    gsum = torch.zeros(256, dtype=torch.float64, device=dev)
+    gnum = torch.zeros(256, dtype=torch.int64, device=dev)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    tot_sum, tot_num = torch.zeros_like(gsum), torch.zeros_like(gnum)
+    for s, E in zip(slices, Es):
+        ctx.rc_gstep_accumulate(s, dt, E, gsum, gnum, False)
+        tot_sum += gsum
+        tot_num += gnum
+    G = torch.zeros(256, dtype=torch.float64, device=dev)
+    ctx.rc_gstep_finish(tot_sum, tot_num, G)
+    G_ref = port.gstep(data, t, E_ref)
+    g = G.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(G_ref))
+    m = ~np.isnan(G_ref)
+    assert np.max(np.abs(g[m] - G_ref[m]) / np.maximum(np.abs(G_ref[m]), 1e-300)) < 1e-10
+    counts = np.array([np.count_nonzero(data == b) for b in range(256)])
+    counts[255] = 0
+    assert np.array_equal(tot_num.cpu().numpy(), counts)
+    tot = torch.zeros_like(acc)
+    for s, E in zip(slices, Es):
+        ctx.rc_rmse_accumulate(s, dt, G, E, acc)
+        tot += acc
+    r_ref = port.rmse(data, t, g, E_ref)
+    a = tot.cpu().numpy()
+    assert a[1] == r_ref[1] and abs(1e5 * np.sqrt(a[0] / a[1]) - r_ref[0]) <= 1e-9 * abs(r_ref[0])
+    # the sharded host loop with a single rank == the C loop
+    full = torch.from_numpy(data).to(dev)
+    E1, G1 = torch.zeros(npix, dtype=torch.float64, device=dev), torch.zeros(256, dtype=torch.float64, device=dev)
+    E2, G2 = torch.zeros_like(E1), torch.zeros_like(G1)
+    log1 = ctx.response_calib(full, dt, 3, E1, G1)
+    log2 = sharding.response_calib_sharded(ctx, full, dt, 3, E2, G2)
+    np.testing.assert_allclose(G2.cpu().numpy(), G1.cpu().numpy(), rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(E2.cpu().numpy(), E1.cpu().numpy(), rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(log2, log1, rtol=1e-9)
+
+
+def _sharded_calib_worker(rank, world, port_no, data_path, out_dir, nits):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mono_dataset_code_b200 import api as A, sharding as sh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    z = np.load(data_path)
+    data, t = z["data"], z["t"]
+    lo, hi = sh.shard_pixels(data.shape[1], rank, world)
+    local = torch.from_numpy(np.ascontiguousarray(data[:, lo:hi])).to(dev)
+    dt = torch.from_numpy(t).to(dev)
+    ctx = A.Context(None, None, rank)
+    out = {}
+    # (a) host loop in Python, all-reduces through torch.distributed (NCCL)
+    E, G = torch.zeros(hi - lo, dtype=torch.float64, device=dev), torch.zeros(256, dtype=torch.float64, device=dev)
+    out["log_py"] = sh.response_calib_sharded(ctx, local, dt, nits, E, G)
+    out["E_py"], out["G_py"] = E.cpu().numpy(), G.cpu().numpy()
+    # (b) the same loop entirely in C++ on a native communicator (libmdc_b200_nccl.so)
+    comm = sh.NativeComm(rank)
+    E2, G2 = torch.zeros_like(E), torch.zeros_like(G)
+    out["log_cc"] = comm.response_calib_sharded(ctx, local, dt, nits, E2, G2)
+    out["E_cc"], out["G_cc"] = E2.cpu().numpy(), G2.cpu().numpy()
+    out["nccl_version"] = comm.version
+    comm.close()
+    np.savez(os.path.join(out_dir, f"gpu_calib{rank}.npz"), lo=lo, hi=hi, **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pixel_sharded_calibrator_two_gpus_nccl(api, port, tmp_path):
+    """SURVEY.md §8e row 2 on two GPUs: both ranks end with the same G, equal (<= 1e-10) to the single-GPU loop, through the Python
+    host loop (torch.distributed NCCL all-reduce) and through the native C++ loop (ncclAllReduce in libmdc_b200_nccl.so)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(9)
+    n, npix, nits = 40, 256 * 192, 3
+    t = np.linspace(0.5, 12.0, n)
+    scene = rng.uniform(2.0, 30.0, npix)
+    data = np.clip(scene[None, :] * t[:, None] ** 0.9 + rng.normal(0, 1.5, (n, npix)), 0, 255).astype(np.uint8)
+    np.savez(tmp_path / "stack.npz", data=data, t=t)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    mp.spawn(_sharded_calib_worker, args=(2, port_no, str(tmp_path / "stack.npz"), str(tmp_path), nits), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "gpu_calib0.npz"), np.load(tmp_path / "gpu_calib1.npz")
+    ctx = api.Context(None, None, 0)
+    d, dt = torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda()
+    E1, G1 = torch.zeros(npix, dtype=torch.float64, device="cuda"), torch.zeros(256, dtype=torch.float64, device="cuda")
+    log1 = ctx.response_calib(d, dt, nits, E1, G1)
+    for tag in ("py", "cc"):
+        assert np.array_equal(a["G_" + tag], b["G_" + tag], equal_nan=True), tag
+        np.testing.assert_allclose(a["G_" + tag], G1.cpu().numpy(), rtol=1e-10, equal_nan=True)
+        np.testing.assert_allclose(np.concatenate([a["E_" + tag], b["E_" + tag]]), E1.cpu().numpy(), rtol=1e-10, equal_nan=True)
+        np.testing.assert_allclose(a["log_" + tag], log1, rtol=1e-9)
+        assert np.array_equal(a["log_" + tag], b["log_" + tag])

@@ -56,3 +56,115 @@ def test_table_broadcast_world2_gloo(dataset_dir, tmp_path):
     ref = api.UndistorterFOV(files["camera"]).remap_tables()
     assert np.array_equal(b["rx"].view(np.uint32), ref[0].view(np.uint32))
     assert list(a["shard"]) == [0, 501] and list(b["shard"]) == [501, 1001]
+
+
+# ------------------------------------------------------------------------------------------------ pixel-sharded responseCalib
+class NumpyCalibOps:
+    """CPU stand-in for api.Context's calibrator passes (torch CPU tensors in, numpy inside): lets the world-size-2 gloo test run the
+    SAME host loop (sharding.response_calib_sharded) that drives the CUDA kernels on GPUs.  Test infrastructure."""
+    can_reuse_counts = True
+
+    def __init__(self, port):
+        self.port = port
+
+    def rc_einit(self, data, E):
+        E.copy_(__import__("torch").from_numpy(self.port.einit(data.numpy())))
+
+    def rc_gstep_accumulate(self, data, t, E, gsum, gnum, reuse_counts):
+        import torch
+        d = data.numpy()
+        keep = d != 255
+        w = (E.numpy()[None, :] * t.numpy()[:, None])[keep]
+        gsum.copy_(torch.from_numpy(np.bincount(d[keep].ravel(), weights=w.ravel(), minlength=256)[:256]))
+        if not reuse_counts:
+            gnum.copy_(torch.from_numpy(np.bincount(d[keep].ravel(), minlength=256)[:256].astype(np.int64)))
+
+    def rc_gstep_finish(self, gsum, gnum, G):
+        import torch
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = gsum.numpy() / gnum.numpy().astype(np.float64)
+        for i in range(2, 256):                         # main_responseCalib.cpp:300-304, sequential
+            if not np.isfinite(g[i]):
+                g[i] = g[i - 1] + (g[i - 1] - g[i - 2])
+        G.copy_(torch.from_numpy(g))
+
+    def estep(self, data, t, G, E):
+        E.copy_(__import__("torch").from_numpy(self.port.estep(data.numpy(), t.numpy(), G.numpy())))
+
+    def rc_rmse_accumulate(self, data, t, G, E, acc):
+        d = data.numpy()
+        r = G.numpy()[d] - t.numpy()[:, None] * E.numpy()[None, :]
+        ok = (d != 255) & np.isfinite(r)
+        acc[0] = float(np.sum(r[ok] * r[ok] * 1e-10))
+        acc[1] = float(np.count_nonzero(ok))
+
+    def rc_rescale(self, E, G):
+        e, g = E.numpy(), G.numpy()          # views: scaled in place
+        return self.port.rescale(e, g)
+
+
+def _calib_worker(rank, world, port_no, data_path, out_dir, nits):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mono_dataset_code_b200 import sharding as sh
+    from oracle import loader
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z = np.load(data_path)
+    data, t = z["data"], z["t"]
+    lo, hi = sh.shard_pixels(data.shape[1], rank, world, align=16)
+    local = torch.from_numpy(np.ascontiguousarray(data[:, lo:hi]))
+    E = torch.zeros(hi - lo, dtype=torch.float64)
+    G = torch.zeros(256, dtype=torch.float64)
+    log = sh.response_calib_sharded(NumpyCalibOps(loader.PortOracle()), local, torch.from_numpy(t), nits, E, G)
+    np.savez(os.path.join(out_dir, f"calib{rank}.npz"), lo=lo, hi=hi, E=E.numpy(), G=G.numpy(), log=log)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pixel_sharded_response_calib_world2_gloo(port, tmp_path):
+    """the calibrator's loop with the image stack split by pixel range over 2 ranks (gloo) reproduces the unsharded
+    loop: identical G on both ranks, E slices that tile the unsharded E, the same rmse log (sums regrouped: <= 1e-10 relative)."""
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(5)
+    n, npix, nits = 24, 1000, 3                                    # 1000 pixels: ranks get 512 and 488 (ragged, not a multiple of 16)
+    t = np.linspace(0.5, 12.0, n)
+    scene = rng.uniform(2.0, 30.0, npix)
+    data = np.clip(scene[None, :] * t[:, None] ** 0.9 + rng.normal(0, 1.5, (n, npix)), 0, 255).astype(np.uint8)
+    data[:, 17] = 255                                              # a pixel that is saturated in every image: E = 0/0
+    np.savez(tmp_path / "stack.npz", data=data, t=t)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    mp.spawn(_calib_worker, args=(2, port_no, str(tmp_path / "stack.npz"), str(tmp_path), nits), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "calib0.npz"), np.load(tmp_path / "calib1.npz")
+    assert (int(a["lo"]), int(a["hi"]), int(b["lo"]), int(b["hi"])) == (0, 512, 512, 1000)
+    assert np.array_equal(a["G"], b["G"], equal_nan=True) and np.array_equal(a["log"], b["log"])
+    # the unsharded loop (oracle restatement of main_responseCalib.cpp:281-362)
+    E = port.einit(data)
+    exp_log = np.zeros((nits, 4))
+    for it in range(nits):
+        G = port.gstep(data, t, E)
+        exp_log[it, 0] = port.rmse(data, t, G, E)[0]
+        E = port.estep(data, t, G)
+        exp_log[it, 1] = port.rmse(data, t, G, E)[0]
+        port.rescale(E, G)
+        exp_log[it, 2:] = port.rmse(data, t, G, E)
+    got_E = np.concatenate([a["E"], b["E"]])
+    np.testing.assert_allclose(a["G"], G, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(got_E, E, rtol=1e-10, atol=0, equal_nan=True)
+    assert np.isnan(got_E[17]) and np.isnan(E[17])
+    np.testing.assert_allclose(a["log"], exp_log, rtol=1e-9)
+    assert a["log"][-1, 3] == exp_log[-1, 3]                      # sample counts are exact
+
+
+def test_pixel_shards_tile_the_image():
+    for npix in (0, 1, 127, 128, 1000, 1000 * 1000, 1920 * 1080):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_pixels(npix, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == npix
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(b % 128 == 0 or b == npix for b, _ in spans)
