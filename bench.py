@@ -43,6 +43,8 @@ def set_geometry(w, h):
     PYR_EXTRA_BYTES = sum((w >> l) * (h >> l) * 4 for l in range(1, 5))
 FLAGS_ALL = 1 | 2 | 4        # rectify + removeGamma + removeVignette (the reference viewer's full correction)
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
+CPU_FRAMES_PER_THREAD = 16   # frames per worker and step of the CPU arm (also the length of its thread-count sweep runs)
+ORIG_AFFINITY = None         # the process's CPU set before the GPU arm bound it to its GPU's NUMA node
 
 
 def log(*a):
@@ -166,8 +168,8 @@ class CpuReference:
                 os.environ["MDC_REF_SPREAD"] = spread
                 pool = loader.RefPool(R, files["camera"], files["pcalib"], files["vignette"], IN_W, IN_H, self.frames, t, (1, 1, 0))
                 pool.run(2)
-                s = min(pool.run(6)[0], pool.run(6)[0])
-                fps = t * 6 / s
+                s = pool.run(CPU_FRAMES_PER_THREAD)[0]      # as long as a timed step: short bursts overstate the steady rate by up to 2x
+                fps = t * CPU_FRAMES_PER_THREAD / s
                 self.sweep.append({"threads": t, "spread_over_numa_nodes": spread == "1", "frames_per_s": round(fps, 1)})
                 if best is None or fps > best[0]:
                     if best is not None:
@@ -219,10 +221,13 @@ def cpu_baseline(files):
     ref = CpuReference(files)
     one = ref.single_thread()
     ref.all_cores(2)                                   # warm-up: page in, spin up
-    fpt = 24
-    n, s = ref.all_cores(fpt)
+    fpt, n, s = CPU_FRAMES_PER_THREAD, 0, 0.0
+    for _ in range(5):                                 # the same step the --impl reference arm times
+        a, b = ref.all_cores(fpt)
+        n += a
+        s += b
     out = {"value": n / s, "unit": "frames/s", "cores": ref.threads, "kind": ref.kind,
-           "sample": f"{n} frames of {IN_W}x{IN_H} (16 distinct, cycled), {fpt} per thread; " + ref.describe(),
+           "sample": f"{n} frames of {IN_W}x{IN_H} (16 distinct, cycled), 5 steps of {fpt} per thread; " + ref.describe(),
            "single_thread": one, "thread_sweep": getattr(ref, "sweep", None)}
     ref.close()
     return out
@@ -254,7 +259,7 @@ def run_reference_arm(args):
     files = write_calibration(tmp)
     ref = CpuReference(files)
     one = ref.single_thread()
-    fpt = 16                                           # frames per thread and step: ~1-2 s of work per step on all cores
+    fpt = CPU_FRAMES_PER_THREAD
     for _ in range(max(args.warmup, 1)):
         ref.all_cores(2)
     frames = secs = 0.0
@@ -297,6 +302,8 @@ def bind_to_gpu_numa(local):
     buffers, decode threads and the copy engine's host side are local to the GPU's PCIe root (8-GPU e2e 0.55)."""
     from mono_dataset_code_b200 import _lib
     info = {"gpu": local, "node": None, "cpus_bound": None}
+    global ORIG_AFFINITY
+    ORIG_AFFINITY = os.sched_getaffinity(0)
     if os.environ.get("MDC_NUMA_BIND", "1") == "0":
         info["disabled"] = True
         return info
@@ -426,10 +433,12 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
         files = S.write_dataset_dir(root, W, H, W, H, "crop")
         sizes = []
         with zipfile.ZipFile(os.path.join(root, "images.zip"), "w", zipfile.ZIP_STORED) as z:
-            base = S.frame(7, W, H, "gradient").reshape(H, W).astype(np.int16)
             yy, xx = np.mgrid[0:H, 0:W]
-            for i in range(K):          # a textured, slowly changing scene (JPEG size and decode cost of a real sequence, not of noise)
-                img = np.clip(base + 40 * np.sin((xx + 13 * i) * 0.05) * np.cos((yy - 7 * i) * 0.04) + ((xx // 64 + yy // 64 + i) % 2) * 30, 0, 255).astype(np.uint8)
+            rng = np.random.default_rng(11)
+            for i in range(K):          # a textured, slowly changing scene with mild sensor noise (JPEG size / decode cost of a real sequence, not of white noise)
+                img = (xx * (150.0 / W) + yy * (60.0 / H) + 40 * np.sin((xx + 13 * i) * 0.05) * np.cos((yy - 7 * i) * 0.04)
+                       + ((xx // 64 + yy // 64 + i) % 2) * 30 + rng.normal(0, 1.5, (H, W)))
+                img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
                 ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
                 z.writestr(f"{i:05d}.jpg", enc.tobytes())
                 sizes.append(len(enc))
@@ -471,6 +480,18 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
             _lib.check(_lib.lib.mdc_seq_prepare(ctx._h, seq._h, first, cnt, FLAGS_ALL, ptrs, 1, threads), "mdc_seq_prepare")
             v += cnt; done += cnt
     run_decode(min(n_mine, K))            # warm-up: page cache, thread pool, pinned staging
+    # more decode threads are not always faster on these hosts (SMT siblings, shared memory bandwidth): short sweep, keep the best
+    sweep, cap = [], threads
+    for cand in sorted({max(1, cap // 4), max(1, cap // 2), cap}):
+        threads = cand
+        t0 = time.perf_counter()
+        run_decode(min(n_mine, 2 * K))
+        sweep.append({"threads": cand, "frames_per_s_this_rank": round(min(n_mine, 2 * K) / (time.perf_counter() - t0), 1)})
+    threads = max(sweep, key=lambda r: r["frames_per_s_this_rank"])["threads"]
+    if world > 1:                          # all ranks use the same count (the slowest rank sets the job's rate anyway)
+        box = [threads]
+        dist.broadcast_object_list(box, src=0)
+        threads = box[0]
     barrier()
     t0 = time.perf_counter()
     run_decode(n_mine)
@@ -507,7 +528,7 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
     return {"workload": f"{W}x{H} mono8 sequence of {total} frames ({K} baseline-JPEG entries of images.zip, cycled), frame-sharded over {world} rank(s) "
                         "with shard_range; rectify|removeGamma|removeVignette",
             "decode_inclusive": {"value": total / dec_s, "unit": "frames/s", "seconds": dec_s, "decode_threads_per_rank": threads,
-                                 "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
+                                 "decode_thread_sweep": sweep, "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
                                  "path": "mdc_seq_prepare: zip read + JPEG decode (host) -> pinned -> H2D -> K1 -> D2H, chunks double-buffered"},
             "device_resident": {"value": total / res_s, "unit": "frames/s", "seconds": res_s, "alg_gbs": alg / res_s / 1e9,
                                 "frames_per_launch": B, "launches_per_rank": launches}}
@@ -721,6 +742,8 @@ def run_gpu_arm(args):
                              "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_FRAME, "launch_ms": k1_ms},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c4_sequence": c4, "c5_estep": estep}
         if world == 1 and not args.no_cpu:
+            if ORIG_AFFINITY:
+                os.sched_setaffinity(0, ORIG_AFFINITY)      # the CPU arm may use every core of the box, not just the GPU's node
             line["cpu_baseline"] = cpu_baseline(files)
             if estep is not None:
                 try:

@@ -176,6 +176,11 @@ int mdc_undistort_f32(mdc_ctx* c, const float* d_in, float* d_out, int n_pix_in,
  * levels = 1 gives exactly getImage.  This is the hot path (kernel K1). */
 int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_frames, unsigned flags,
                       float* const* d_out_levels, int levels, mdc_stream stream);
+/* Same with padded input rows: d_frames is [n_frames][in_h][row_pitch_bytes] (row_pitch_bytes >= in_w; rectifying mode only).
+ * A pitch that is a multiple of 16 bytes keeps image widths that are NOT a multiple of 16 on the TMA loader (a tightly packed odd
+ * width can only use the ~2x slower LDG loader); mdc_prepare_batch_host pads such rows itself during its host-to-device copy. */
+int mdc_prepare_batch_pitched(mdc_ctx* c, const uint8_t* d_frames, size_t row_pitch_bytes, int n_frames, unsigned flags,
+                              float* const* d_out_levels, int levels, mdc_stream stream);
 
 /* Stand-alone pyramid level (kernel K2): dst[x,y] = 0.25f*(((a+b)+c)+d) over the 2x2 block. */
 int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h, float* d_dst, int n_frames, mdc_stream stream);

@@ -281,6 +281,13 @@ class Context:
         check(lib.mdc_prepare_batch(self._h, C.c_void_p(frames.data_ptr()), n, flags, arr, len(out_levels), self._stream(frames)),
               "mdc_prepare_batch")
 
+    def prepare_batch_pitched(self, frames, pitch: int, flags: int, out_levels):
+        """frames: uint8 CUDA tensor [n, H, pitch] whose rows hold in_w pixels followed by padding (rectifying mode only)."""
+        n = frames.shape[0]
+        arr = (C.c_void_p * len(out_levels))(*[t.data_ptr() for t in out_levels])
+        check(lib.mdc_prepare_batch_pitched(self._h, C.c_void_p(frames.data_ptr()), pitch, n, flags, arr, len(out_levels), self._stream(frames)),
+              "mdc_prepare_batch_pitched")
+
     def unmap_device(self, image_in, image_out, n, flags, n_frames=1):
         check(lib.mdc_unmap_u8(self._h, C.c_void_p(image_in.data_ptr()), C.c_void_p(image_out.data_ptr()), n, n_frames, flags,
                                self._stream(image_in)), "mdc_unmap_u8")

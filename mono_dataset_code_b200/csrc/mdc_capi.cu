@@ -76,11 +76,12 @@ struct mdc_ctx {
     TmaMaps* maps[kMapSlots] = {};
     const void* map_key_ptr[kMapSlots] = {};
     int map_key_frames[kMapSlots] = {};
+    int map_key_pitch[kMapSlots] = {};
     int map_next = 0;
     // texture-gather loader: device limits, self-check verdict, cache of texture-object sets (one object per chunk of frames)
     int tex_max_rows = 0, tex_max_width = 0, tex_pitch_align = 32, tex_base_align = 512;
     bool tex_ok = false;                 // the context-creation self-check found the texture path bit-identical to the staged path
-    struct TexEntry { const void* ptr = nullptr; int n_frames = 0, chunk = 0; std::vector<cudaTextureObject_t> objs; };
+    struct TexEntry { const void* ptr = nullptr; int n_frames = 0, chunk = 0, pitch = 0; std::vector<cudaTextureObject_t> objs; };
     TexEntry tex_cache[kTexSlots];
     int tex_next = 0;
     // knobs (loader: -1 auto, 0 LDG, 1 TMA, 2 texture gather)
@@ -100,7 +101,7 @@ struct mdc_ctx {
     // scratch for the single-op host entry points
     void* scratch_a = nullptr; size_t scratch_a_bytes = 0;
     void* scratch_b = nullptr; size_t scratch_b_bytes = 0;
-    double* d_rc = nullptr;      // responseCalib scratch: gsum[256] gnum[256] factor[1] acc[2]
+    double* d_rc = nullptr;      // responseCalib scratch: gsum[256] gnum[256] factor[1] acc[2] partials[2*kRmsePartialPairs]
     long long launches = 0;
 };
 
@@ -122,7 +123,9 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     c->tiles_y = (OH + kTile - 1) / kTile;
     const int n_tiles = c->tiles_x * c->tiles_y;
     c->tiles.assign(n_tiles, TileDesc{0, 0, 0, TILE_EMPTY});
-    const bool tma_geom_ok = (W % 16 == 0) && (static_cast<long long>(W) * H % 16 == 0);
+    // box origins are always 16-byte aligned: whether TMA can be used is decided per call from the ROW PITCH of the frames (a width
+    // that is not a multiple of 16 is fine once the rows are padded, which the host pipeline does during its H2D copy)
+    const bool tma_geom_ok = true;
     const char* e;
     const bool pitch_search = (e = getenv("MDC_PITCH_SEARCH")) ? atoi(e) != 0 : true;
     // TMA box classes: box heights are rounded up to `gran` rows; coarsen until the shapes fit kMaxClasses
@@ -225,7 +228,8 @@ void build_plan(mdc_ctx* c, const float* rx, const float* ry) {
     }
     if (static_cast<int>(c->classes.size()) <= kMaxClasses) break;
     }
-    c->plan_tma_ok = tma_geom_ok && !c->classes.empty() && static_cast<int>(c->classes.size()) <= kMaxClasses && encode_tiled_fn() != nullptr;
+    c->plan_tma_ok = !c->classes.empty() && static_cast<int>(c->classes.size()) <= kMaxClasses && encode_tiled_fn() != nullptr;
+    (void)W; (void)H;
 }
 
 int upload_plan(mdc_ctx* c) {
@@ -243,7 +247,7 @@ int ctx_common_init(mdc_ctx* c, int device) {
     c->sm_count = v;
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&c->d_counters, kCounterRing * sizeof(int)));
-    CU_CHECK(cudaMalloc(&c->d_rc, (256 + 256 + 1 + 2) * sizeof(double)));
+    CU_CHECK(cudaMalloc(&c->d_rc, (256 + 256 + 1 + 2 + 2 * kRmsePartialPairs) * sizeof(double)));
     const char* e = getenv("MDC_USE_TMA");
     if (e) c->use_tma = atoi(e);
     e = getenv("MDC_CTAS_PER_SM");
@@ -278,13 +282,18 @@ int ctx_common_init(mdc_ctx* c, int device) {
     return MDC_OK;
 }
 
+// TMA needs 16-byte aligned rows and frames (tensor-map strides), the LDG loader takes anything
+bool tma_pitch_ok(const mdc_ctx* c, const uint8_t* frames, int pitch) {
+    return c->plan_tma_ok && pitch % 16 == 0 && (static_cast<long long>(pitch) * c->in_h) % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0;
+}
+
 // ---- texture-gather loader plumbing -------------------------------------------------------------------------------
 // Frames per chunk (= per texture object) for `frames`: as many as the gather height limit allows (at most `want`), such that
 // every chunk starts on a texture-aligned address.  0 = this geometry / pointer cannot use the texture path.
-int tex_chunk_frames(const mdc_ctx* c, const uint8_t* frames, int want) {
-    if (c->in_w % c->tex_pitch_align != 0 || c->in_w > c->tex_max_width || c->in_h < 2) return 0;
+int tex_chunk_frames(const mdc_ctx* c, const uint8_t* frames, int pitch, int want) {
+    if (pitch % c->tex_pitch_align != 0 || c->in_w > c->tex_max_width || c->in_h < 2) return 0;
     if (reinterpret_cast<uintptr_t>(frames) % static_cast<uintptr_t>(c->tex_base_align) != 0) return 0;
-    const long long frame_bytes = static_cast<long long>(c->in_w) * c->in_h;
+    const long long frame_bytes = static_cast<long long>(pitch) * c->in_h;
     for (int n = std::min(want, c->tex_max_rows / c->in_h); n >= 1; --n)
         if ((frame_bytes * n) % c->tex_base_align == 0) return n;
     return 0;
@@ -297,10 +306,10 @@ void tex_entry_release(mdc_ctx::TexEntry& e) {
 }
 
 // texture objects for `frames` ([n_frames][H][W] u8) cut into chunks of `chunk` frames; cached on the host
-int get_textures(mdc_ctx* c, const uint8_t* frames, int n_frames, int chunk, const std::vector<cudaTextureObject_t>** out) {
+int get_textures(mdc_ctx* c, const uint8_t* frames, int pitch, int n_frames, int chunk, const std::vector<cudaTextureObject_t>** out) {
     for (int s = 0; s < kTexSlots; ++s) {
         mdc_ctx::TexEntry& e = c->tex_cache[s];
-        if (e.ptr == frames && e.n_frames == n_frames && e.chunk == chunk) { *out = &e.objs; return MDC_OK; }
+        if (e.ptr == frames && e.n_frames == n_frames && e.chunk == chunk && e.pitch == pitch) { *out = &e.objs; return MDC_OK; }
     }
     mdc_ctx::TexEntry& e = c->tex_cache[c->tex_next];
     c->tex_next = (c->tex_next + 1) % kTexSlots;
@@ -309,7 +318,7 @@ int get_textures(mdc_ctx* c, const uint8_t* frames, int n_frames, int chunk, con
         tex_entry_release(e);
     }
     const int n_chunks = (n_frames + chunk - 1) / chunk;
-    const size_t frame_bytes = static_cast<size_t>(c->in_w) * c->in_h;
+    const size_t frame_bytes = static_cast<size_t>(pitch) * c->in_h;
     for (int k = 0; k < n_chunks; ++k) {
         const int nf = std::min(chunk, n_frames - k * chunk);
         cudaResourceDesc rd;
@@ -319,7 +328,7 @@ int get_textures(mdc_ctx* c, const uint8_t* frames, int n_frames, int chunk, con
         rd.res.pitch2D.desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
         rd.res.pitch2D.width = static_cast<size_t>(c->in_w);
         rd.res.pitch2D.height = static_cast<size_t>(c->in_h) * nf;
-        rd.res.pitch2D.pitchInBytes = static_cast<size_t>(c->in_w);
+        rd.res.pitch2D.pitchInBytes = static_cast<size_t>(pitch);
         cudaTextureDesc td;
         memset(&td, 0, sizeof td);
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
@@ -335,15 +344,15 @@ int get_textures(mdc_ctx* c, const uint8_t* frames, int n_frames, int chunk, con
         }
         e.objs.push_back(t);
     }
-    e.ptr = frames; e.n_frames = n_frames; e.chunk = chunk;
+    e.ptr = frames; e.n_frames = n_frames; e.chunk = chunk; e.pitch = pitch;
     *out = &e.objs;
     return MDC_OK;
 }
 
 // descriptors for `frames` ([n_frames][H][W] u8): one per box class; encoded sets are cached on the host
-int get_tensor_maps(mdc_ctx* c, const uint8_t* frames, int n_frames, const TmaMaps** out) {
+int get_tensor_maps(mdc_ctx* c, const uint8_t* frames, int pitch, int n_frames, const TmaMaps** out) {
     for (int s = 0; s < kMapSlots; ++s)
-        if (c->maps[s] && c->map_key_ptr[s] == frames && c->map_key_frames[s] == n_frames) { *out = c->maps[s]; return MDC_OK; }
+        if (c->maps[s] && c->map_key_ptr[s] == frames && c->map_key_frames[s] == n_frames && c->map_key_pitch[s] == pitch) { *out = c->maps[s]; return MDC_OK; }
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { mdc_set_error("cuTensorMapEncodeTiled unavailable"); return MDC_ERR_CUDA; }
     const int slot = c->map_next;
@@ -357,7 +366,7 @@ int get_tensor_maps(mdc_ctx* c, const uint8_t* frames, int n_frames, const TmaMa
     c->map_key_ptr[slot] = nullptr;
     for (size_t i = 0; i < c->classes.size(); ++i) {
         const cuuint64_t dims[3] = {static_cast<cuuint64_t>(c->in_w), static_cast<cuuint64_t>(c->in_h), static_cast<cuuint64_t>(n_frames)};
-        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(c->in_w), static_cast<cuuint64_t>(c->in_w) * c->in_h};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch), static_cast<cuuint64_t>(pitch) * c->in_h};
         const cuuint32_t box[3] = {static_cast<cuuint32_t>(c->classes[i].first), static_cast<cuuint32_t>(c->classes[i].second), 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         CUresult r = enc(&c->maps[slot]->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(frames), dims, strides, box, estr,
@@ -367,6 +376,7 @@ int get_tensor_maps(mdc_ctx* c, const uint8_t* frames, int n_frames, const TmaMa
     }
     c->map_key_ptr[slot] = frames;
     c->map_key_frames[slot] = n_frames;
+    c->map_key_pitch[slot] = pitch;
     *out = c->maps[slot];
     return MDC_OK;
 }
@@ -408,10 +418,10 @@ int run_deep_levels(mdc_ctx* c, int n_frames, float* const* d_out_levels, int in
 }
 
 // K1 through the texture-gather loader.  One launch covers up to kMaxTex chunks (= texture objects).
-int run_fused_tex(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chunk, UnmapFlags u, float* const* d_out_levels, int levels,
+int run_fused_tex(mdc_ctx* c, const uint8_t* d_frames, int pitch, int n_frames, int chunk, UnmapFlags u, float* const* d_out_levels, int levels,
                   cudaStream_t stream) {
     const std::vector<cudaTextureObject_t>* objs = nullptr;
-    int rc = get_textures(c, d_frames, n_frames, chunk, &objs);
+    int rc = get_textures(c, d_frames, pitch, n_frames, chunk, &objs);
     if (rc != MDC_OK) return rc;
     const int in_kernel = std::min(levels, kInKernelLevels);
     const int n_chunks = static_cast<int>(objs->size());
@@ -421,8 +431,8 @@ int run_fused_tex(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chunk, 
         const int f0 = c0 * chunk, nf = std::min(n_frames - f0, nc * chunk);
         FusedParams p;
         memset(&p, 0, sizeof p);
-        p.frames = d_frames + static_cast<size_t>(f0) * c->in_w * c->in_h; p.n_frames = nf;
-        p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h;
+        p.frames = d_frames + static_cast<size_t>(f0) * pitch * c->in_h; p.n_frames = nf;
+        p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h; p.in_pitch = pitch;
         p.remap_x = c->d_rx; p.remap_y = c->d_ry; p.vinv = c->d_vinv; p.ginv = c->d_ginv;
         p.tiles = c->d_tiles; p.work_counter = nullptr;
         p.tiles_x = c->tiles_x; p.n_tiles = static_cast<int>(c->tiles.size());
@@ -446,21 +456,22 @@ int run_fused_tex(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chunk, 
 
 // What "auto" resolves to (measured order on B200, profiles/r02_k1_loaders.md); a loader that turns out unusable for a particular
 // frames pointer falls back to the next one.
-int auto_loader(const mdc_ctx* c) {
-    if (c->tex_ok && c->plan_tma_ok && c->auto_hybrid) return 3;
-    if (c->plan_tma_ok) return 1;
+int auto_loader(const mdc_ctx* c, const uint8_t* frames, int pitch) {
+    const bool tma = tma_pitch_ok(c, frames, pitch);
+    if (c->tex_ok && tma && c->auto_hybrid) return 3;
+    if (tma) return 1;
     if (c->tex_ok) return 2;
     return 0;
 }
 
 // K1 through the staged loaders (TMA ring or LDG double buffer), levels 0..in_kernel-1 only.  cap_per_sm > 0 bounds the persistent
 // grid (hybrid mode leaves room for the texture kernel's CTAs on every SM).
-int run_fused_staged(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, float* const* d_out_levels, int in_kernel,
+int run_fused_staged(mdc_ctx* c, const uint8_t* d_frames, int pitch, int n_frames, UnmapFlags u, float* const* d_out_levels, int in_kernel,
                      cudaStream_t stream, int loader, int cap_per_sm) {
     FusedParams p;
     memset(&p, 0, sizeof p);
     p.frames = d_frames; p.n_frames = n_frames;
-    p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h;
+    p.in_w = c->in_w; p.in_h = c->in_h; p.out_w = c->out_w; p.out_h = c->out_h; p.in_pitch = pitch;
     p.remap_x = c->d_rx; p.remap_y = c->d_ry; p.vinv = c->d_vinv; p.ginv = c->d_ginv;
     p.tiles = c->d_tiles;
     p.work_counter = c->d_counters + (c->counter_next++ % kCounterRing);
@@ -473,11 +484,11 @@ int run_fused_staged(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFla
     p.box_px_max = c->box_px_max;
     p.carveout = c->carveout;
     p.chunk_frames = c->chunk_frames > 0 ? c->chunk_frames : 48;
-    bool tma = c->plan_tma_ok && loader != 0 && (reinterpret_cast<uintptr_t>(d_frames) % 16 == 0);
+    bool tma = loader != 0 && tma_pitch_ok(c, d_frames, pitch);
     if (loader == 1 && !tma) { mdc_set_error("TMA loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
     const TmaMaps* maps = nullptr;
     if (tma) {
-        int rc = get_tensor_maps(c, d_frames, n_frames, &maps);
+        int rc = get_tensor_maps(c, d_frames, pitch, n_frames, &maps);
         if (rc != MDC_OK) return rc;
     }
     // Register budget / residency the kernel variant was compiled for.  Measured optimum: 3 CTAs/SM (72 registers) for
@@ -500,16 +511,16 @@ int run_fused_staged(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFla
 // stores on the LSU / shared-memory pipe) with a reduced persistent grid, and the texture-gather kernel (taps on the TEX pipe) in
 // the register / shared-memory space that is left.  Neither pipe alone can feed HBM; side by side they add up.
 // The leading whole chunks go to the texture kernel, the rest to the staged kernel; fork/join with events around an auxiliary stream.
-int run_fused_hybrid(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chunk, UnmapFlags u, float* const* d_out_levels, int levels,
+int run_fused_hybrid(mdc_ctx* c, const uint8_t* d_frames, int pitch, int n_frames, int chunk, UnmapFlags u, float* const* d_out_levels, int levels,
                      cudaStream_t stream) {
     const int in_kernel = std::min(levels, kInKernelLevels);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
     int tex_chunks = static_cast<int>((static_cast<long long>(n_chunks) * c->hyb_tex_pct + 50) / 100);
     tex_chunks = std::max(0, std::min(tex_chunks, n_chunks));
     const int n_tex = std::min(n_frames, tex_chunks * chunk), n_stg = n_frames - n_tex;
-    if (n_tex == 0 || n_stg == 0 || !c->plan_tma_ok) {
-        if (n_stg == 0) return run_fused_tex(c, d_frames, n_frames, chunk, u, d_out_levels, levels, stream);
-        int rc = run_fused_staged(c, d_frames, n_frames, u, d_out_levels, in_kernel, stream, -1, 0);
+    if (n_tex == 0 || n_stg == 0 || !tma_pitch_ok(c, d_frames, pitch)) {
+        if (n_stg == 0) return run_fused_tex(c, d_frames, pitch, n_frames, chunk, u, d_out_levels, levels, stream);
+        int rc = run_fused_staged(c, d_frames, pitch, n_frames, u, d_out_levels, in_kernel, stream, -1, 0);
         return rc != MDC_OK ? rc : run_deep_levels(c, n_frames, d_out_levels, in_kernel, levels, stream);
     }
     if (!c->aux_stream) {
@@ -523,31 +534,36 @@ int run_fused_hybrid(mdc_ctx* c, const uint8_t* d_frames, int n_frames, int chun
     CU_CHECK(cudaEventRecord(c->ev_fork, stream));
     CU_CHECK(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     // staged kernel first: its persistent CTAs take their slots on every SM, the texture kernel's short CTAs fill what is left
-    int rc = run_fused_staged(c, d_frames + static_cast<size_t>(n_tex) * c->in_w * c->in_h, n_stg, u, stg_out, in_kernel, stream, 1, c->hyb_stg_ctas);
+    int rc = run_fused_staged(c, d_frames + static_cast<size_t>(n_tex) * pitch * c->in_h, pitch, n_stg, u, stg_out, in_kernel, stream, 1, c->hyb_stg_ctas);
     if (rc != MDC_OK) return rc;
-    rc = run_fused_tex(c, d_frames, n_tex, chunk, u, d_out_levels, in_kernel, c->aux_stream);
+    rc = run_fused_tex(c, d_frames, pitch, n_tex, chunk, u, d_out_levels, in_kernel, c->aux_stream);
     if (rc != MDC_OK) return rc;
     CU_CHECK(cudaEventRecord(c->ev_join, c->aux_stream));
     CU_CHECK(cudaStreamWaitEvent(stream, c->ev_join, 0));
     return run_deep_levels(c, n_frames, d_out_levels, in_kernel, levels, stream);
 }
 
-// loader: -1 = the context's setting (auto: see mdc_ctx_configure)
+// loader: -1 = the context's setting (auto: see mdc_ctx_configure); pitch = bytes between input rows (0 = tightly packed)
 int run_fused(mdc_ctx* c, const uint8_t* d_frames, int n_frames, UnmapFlags u, float* const* d_out_levels, int levels,
-              cudaStream_t stream, int loader = -1) {
+              cudaStream_t stream, int loader = -1, int pitch = 0) {
+    if (pitch <= 0) pitch = c->in_w;
     if (loader < 0) loader = c->use_tma;
-    if (loader < 0) loader = auto_loader(c);
+    if (loader < 0) loader = auto_loader(c, d_frames, pitch);
     if (loader == 2 || loader == 3) {
-        const int chunk = tex_chunk_frames(c, d_frames, c->chunk_frames > 0 ? c->chunk_frames : 48);
+        if (c->use_tma >= 2 && !c->tex_ok) {
+            mdc_set_error("texture-gather loader requested, but its self-check did not pass on this device / geometry");
+            return MDC_ERR_UNSUPPORTED;
+        }
+        const int chunk = tex_chunk_frames(c, d_frames, pitch, c->chunk_frames > 0 ? c->chunk_frames : 48);
         if (chunk > 0) {
-            if (loader == 3) return run_fused_hybrid(c, d_frames, n_frames, chunk, u, d_out_levels, levels, stream);
-            return run_fused_tex(c, d_frames, n_frames, chunk, u, d_out_levels, levels, stream);
+            if (loader == 3) return run_fused_hybrid(c, d_frames, pitch, n_frames, chunk, u, d_out_levels, levels, stream);
+            return run_fused_tex(c, d_frames, pitch, n_frames, chunk, u, d_out_levels, levels, stream);
         }
         if (c->use_tma >= 2) { mdc_set_error("texture-gather loader requested but unusable for this geometry/pointer"); return MDC_ERR_UNSUPPORTED; }
-        loader = c->plan_tma_ok ? 1 : 0;      // auto: this pointer / batch cannot go through textures
+        loader = tma_pitch_ok(c, d_frames, pitch) ? 1 : 0;      // auto: this pointer / batch cannot go through textures
     }
     const int in_kernel = std::min(levels, kInKernelLevels);
-    int rc = run_fused_staged(c, d_frames, n_frames, u, d_out_levels, in_kernel, stream, loader, 0);
+    int rc = run_fused_staged(c, d_frames, pitch, n_frames, u, d_out_levels, in_kernel, stream, loader, 0);
     return rc != MDC_OK ? rc : run_deep_levels(c, n_frames, d_out_levels, in_kernel, levels, stream);
 }
 
@@ -567,16 +583,20 @@ void tex_selfcheck(mdc_ctx* c) {
     float *out_a = nullptr, *out_b = nullptr;
     unsigned long long* d_bad = nullptr;
     auto cleanup = [&]() { cudaFree(raw); cudaFree(out_a); cudaFree(out_b); cudaFree(d_bad); cudaGetLastError(); };
-    if (cudaMalloc(&raw, nf * n_in + 1024) != cudaSuccess || cudaMalloc(&out_a, nf * n_out * 4) != cudaSuccess ||
+    // rows padded to the texture pitch alignment when the width itself is not describable (the check is about the device's texture
+    // gather semantics; whether a particular call can use the loader is decided from its own pointer and pitch)
+    const int pitch = (c->in_w + c->tex_pitch_align - 1) / c->tex_pitch_align * c->tex_pitch_align;
+    if (cudaMalloc(&raw, static_cast<size_t>(nf) * pitch * c->in_h + 1024) != cudaSuccess || cudaMalloc(&out_a, nf * n_out * 4) != cudaSuccess ||
         cudaMalloc(&out_b, nf * n_out * 4) != cudaSuccess || cudaMalloc(&d_bad, 8) != cudaSuccess) { cleanup(); return; }
     uint8_t* frames = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 511) & ~static_cast<uintptr_t>(511));
-    const int chunk = tex_chunk_frames(c, frames, c->chunk_frames > 0 ? c->chunk_frames : 48);
+    const int chunk = tex_chunk_frames(c, frames, pitch, c->chunk_frames > 0 ? c->chunk_frames : 48);
     if (chunk < 1) { if (verbose) fprintf(stderr, "[mdc] texture-gather loader: geometry not describable (pitch %d, limit %d rows)\n", c->in_w, c->tex_max_rows); cleanup(); return; }
     std::vector<uint8_t> h(nf * n_in);
     uint32_t lcg = 12345u;
     for (size_t i = 0; i < h.size(); ++i) { lcg = lcg * 1664525u + 1013904223u; h[i] = static_cast<uint8_t>(lcg >> 24); }
     for (size_t i = 0; i < h.size(); i += 97) h[i] = 255;
-    bool ok = cudaMemcpy(frames, h.data(), h.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+    bool ok = cudaMemcpy2D(frames, static_cast<size_t>(pitch), h.data(), static_cast<size_t>(c->in_w), static_cast<size_t>(c->in_w),
+                           static_cast<size_t>(c->in_h) * nf, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemset(out_a, 0xff, nf * n_out * 4) == cudaSuccess && cudaMemset(out_b, 0, nf * n_out * 4) == cudaSuccess &&
               cudaMemset(d_bad, 0, 8) == cudaSuccess;
     const UnmapFlags u{c->have_gamma, c->have_gamma && c->have_vig, true};
@@ -585,8 +605,9 @@ void tex_selfcheck(mdc_ctx* c) {
     const long long launches0 = c->launches;
     const int study0 = c->k1_study;
     c->k1_study = kStudyAll;             // the floor-study variants compute garbage by design
-    ok = ok && run_fused(c, frames, nf, u, la, 1, c->stream, 2) == MDC_OK;
-    ok = ok && run_fused(c, frames, nf, u, lb, 1, c->stream, c->plan_tma_ok ? 1 : 0) == MDC_OK;
+    ok = ok && run_fused(c, frames, nf, u, la, 1, c->stream, 2, pitch) == MDC_OK;
+    const bool tma_ref = tma_pitch_ok(c, frames, pitch);
+    ok = ok && run_fused(c, frames, nf, u, lb, 1, c->stream, tma_ref ? 1 : 0, pitch) == MDC_OK;
     c->k1_study = study0;
     ok = ok && launch_count_mismatch(out_a, out_b, nf * n_out, d_bad, c->stream) == cudaSuccess;
     unsigned long long bad = ~0ull;
@@ -596,7 +617,7 @@ void tex_selfcheck(mdc_ctx* c) {
     c->tex_ok = ok && bad == 0;
     if (verbose || (ok && bad != 0))
         fprintf(stderr, "[mdc] texture-gather loader self-check: %s (%llu of %zu output words differ from the %s loader; chunk = %d frames)\n",
-                c->tex_ok ? "bit-identical, enabled" : "DISABLED", ok ? bad : 0ull, nf * n_out, c->plan_tma_ok ? "TMA" : "LDG", chunk);
+                c->tex_ok ? "bit-identical, enabled" : "DISABLED", ok ? bad : 0ull, nf * n_out, tma_ref ? "TMA" : "LDG", chunk);
     cleanup();
 }
 
@@ -737,15 +758,15 @@ extern "C" int mdc_ctx_configure(mdc_ctx* c, int use_tma, int ctas_per_sm) {
     return MDC_OK;
 }
 
-extern "C" int mdc_ctx_auto_loader(const mdc_ctx* c) { return c && c->have_fov ? auto_loader(c) : 0; }
+extern "C" int mdc_ctx_auto_loader(const mdc_ctx* c) { return c && c->have_fov ? auto_loader(c, nullptr, c->in_w) : 0; }
 
 extern "C" int mdc_ctx_loader_usable(const mdc_ctx* c, int loader) {
     if (!c || !c->have_fov) return 0;
     switch (loader) {
         case MDC_LOADER_LDG: return 1;
-        case MDC_LOADER_TMA: return c->plan_tma_ok ? 1 : 0;
-        case MDC_LOADER_TEX: return c->tex_ok ? 1 : 0;
-        case MDC_LOADER_HYBRID: return (c->tex_ok && c->plan_tma_ok) ? 1 : 0;
+        case MDC_LOADER_TMA: return tma_pitch_ok(c, nullptr, c->in_w) ? 1 : 0;      // for tightly packed frames
+        case MDC_LOADER_TEX: return (c->tex_ok && c->in_w % c->tex_pitch_align == 0) ? 1 : 0;      // for tightly packed frames
+        case MDC_LOADER_HYBRID: return (c->tex_ok && c->in_w % c->tex_pitch_align == 0 && tma_pitch_ok(c, nullptr, c->in_w)) ? 1 : 0;
         default: return 0;
     }
 }
@@ -813,8 +834,25 @@ extern "C" int mdc_pyr_down(mdc_ctx* c, const float* d_src, int src_w, int src_h
     return finish(c, stream, s);
 }
 
+static int prepare_batch_impl(mdc_ctx* c, const uint8_t* d_frames, int pitch, int n_frames, unsigned flags,
+                              float* const* d_out_levels, int levels, mdc_stream stream);
+
 extern "C" int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_frames, unsigned flags,
                                  float* const* d_out_levels, int levels, mdc_stream stream) {
+    return prepare_batch_impl(c, d_frames, 0, n_frames, flags, d_out_levels, levels, stream);
+}
+
+extern "C" int mdc_prepare_batch_pitched(mdc_ctx* c, const uint8_t* d_frames, size_t row_pitch_bytes, int n_frames, unsigned flags,
+                                         float* const* d_out_levels, int levels, mdc_stream stream) {
+    if (c && (row_pitch_bytes < static_cast<size_t>(c->in_w) || row_pitch_bytes > (1u << 30))) {
+        mdc_set_error("mdc_prepare_batch_pitched: row pitch %zu for %d-pixel rows", row_pitch_bytes, c->in_w);
+        return MDC_ERR_INVALID_ARG;
+    }
+    return prepare_batch_impl(c, d_frames, static_cast<int>(row_pitch_bytes), n_frames, flags, d_out_levels, levels, stream);
+}
+
+static int prepare_batch_impl(mdc_ctx* c, const uint8_t* d_frames, int pitch, int n_frames, unsigned flags,
+                              float* const* d_out_levels, int levels, mdc_stream stream) {
     if (!c || !d_frames || !d_out_levels || n_frames < 0 || levels < 1 || levels > MDC_MAX_PYR_LEVELS) {
         mdc_set_error("mdc_prepare_batch: bad argument");
         return MDC_ERR_INVALID_ARG;
@@ -834,9 +872,10 @@ extern "C" int mdc_prepare_batch(mdc_ctx* c, const uint8_t* d_frames, int n_fram
     UnmapFlags u{false, false, false};
     if (photometric) u = sanitise(c, flags);
     if (rectify) {
-        int rc = run_fused(c, d_frames, n_frames, u, d_out_levels, levels, s);
+        int rc = run_fused(c, d_frames, n_frames, u, d_out_levels, levels, s, -1, pitch);
         if (rc != MDC_OK) return rc;
     } else {
+        if (pitch > 0 && pitch != c->in_w) { mdc_set_error("padded rows are supported in rectifying mode only"); return MDC_ERR_UNSUPPORTED; }
         const size_t n = static_cast<size_t>(c->in_w) * c->in_h;
         CU_CHECK(launch_unmap(d_frames, d_out_levels[0], n, n_frames, u.gamma ? c->d_ginv : nullptr, u.vig ? c->d_vinv : nullptr, u.kill, s));
         c->launches++;
@@ -964,7 +1003,7 @@ extern "C" int mdc_rc_rmse_accumulate(mdc_ctx* c, const uint8_t* d_data, int n, 
     }
     CU_CHECK(cudaSetDevice(c->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    if (npix > 0 && n > 0) { CU_CHECK(launch_rc_rmse(d_data, n, npix, d_t, d_G, d_E, d_acc2, s)); c->launches++; }
+    if (npix > 0 && n > 0) { CU_CHECK(launch_rc_rmse(d_data, n, npix, d_t, d_G, d_E, d_acc2, c->d_rc + 515, s)); c->launches += 2; }
     else CU_CHECK(cudaMemsetAsync(d_acc2, 0, 2 * sizeof(double), s));
     return finish(c, stream, s);
 }
@@ -982,8 +1021,8 @@ extern "C" int mdc_rc_rescale(mdc_ctx* c, int npix, double* d_E, double* d_G, do
 extern "C" int mdc_rc_rmse(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E, double out_host[2]) {
     if (!c || !d_data || !d_t || !d_G || !d_E || !out_host || n < 0 || npix < 0) { mdc_set_error("mdc_rc_rmse: bad argument"); return MDC_ERR_INVALID_ARG; }
     CU_CHECK(cudaSetDevice(c->device));
-    CU_CHECK(launch_rc_rmse(d_data, n, npix, d_t, d_G, d_E, c->d_rc + 513, c->stream));
-    c->launches++;
+    CU_CHECK(launch_rc_rmse(d_data, n, npix, d_t, d_G, d_E, c->d_rc + 513, c->d_rc + 515, c->stream));
+    c->launches += 2;
     double acc[2];
     CU_CHECK(cudaMemcpyAsync(acc, c->d_rc + 513, sizeof acc, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
@@ -1121,7 +1160,10 @@ extern "C" int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_f
     const char* e = getenv("MDC_HOST_CHUNK");
     int chunk = e ? atoi(e) : 16;
     chunk = std::max(1, std::min(chunk, n_frames));
-    const size_t in_bytes = static_cast<size_t>(chunk) * n_in, out_bytes = static_cast<size_t>(chunk) * px_per_frame * 4;
+    // Rows that are not a multiple of 16 bytes cannot be described to TMA — but the H2D copy can pad them for free (2-D copy into a
+    // device buffer with a 32-byte multiple pitch), which keeps such widths on the fast loaders instead of the 2x slower LDG one.
+    const int pitch = (rectify && c->in_w % 16 != 0 && c->plan_tma_ok) ? ((c->in_w + 31) & ~31) : c->in_w;
+    const size_t in_bytes = static_cast<size_t>(chunk) * pitch * c->in_h, out_bytes = static_cast<size_t>(chunk) * px_per_frame * 4;
     if (c->pipe_in_bytes < in_bytes || c->pipe_out_bytes < out_bytes) {
         for (int s = 0; s < kHostPipeDepth; ++s) {
             if (c->pipe_stream[s]) cudaStreamSynchronize(c->pipe_stream[s]);
@@ -1149,11 +1191,14 @@ extern "C" int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_f
         const int nf = std::min(chunk, n_frames - f0);
         const int s = k % kHostPipeDepth;
         cudaStream_t st = c->pipe_stream[s];
-        cudaError_t ce = cudaMemcpyAsync(c->pipe_in[s], frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(nf) * n_in, cudaMemcpyHostToDevice, st);
+        cudaError_t ce = pitch == c->in_w
+            ? cudaMemcpyAsync(c->pipe_in[s], frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(nf) * n_in, cudaMemcpyHostToDevice, st)
+            : cudaMemcpy2DAsync(c->pipe_in[s], static_cast<size_t>(pitch), frames + static_cast<size_t>(f0) * n_in, static_cast<size_t>(c->in_w),
+                                static_cast<size_t>(c->in_w), static_cast<size_t>(c->in_h) * nf, cudaMemcpyHostToDevice, st);
         float* lv[MDC_MAX_PYR_LEVELS];
         size_t off = 0;
         for (int l = 0; l < levels; ++l) { lv[l] = c->pipe_out[s] + off; off += static_cast<size_t>(nf) * lvl_px[l]; }
-        if (ce == cudaSuccess) rc = mdc_prepare_batch(c, c->pipe_in[s], nf, flags, lv, levels, st);
+        if (ce == cudaSuccess) rc = prepare_batch_impl(c, c->pipe_in[s], pitch == c->in_w ? 0 : pitch, nf, flags, lv, levels, st);
         for (int l = 0; l < levels && rc == MDC_OK && ce == cudaSuccess; ++l)
             ce = cudaMemcpyAsync(out_levels[l] + static_cast<size_t>(f0) * lvl_px[l], lv[l], static_cast<size_t>(nf) * lvl_px[l] * 4, cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) { mdc_set_error("mdc_prepare_batch_host: copy failed: %s", cudaGetErrorString(ce)); rc = MDC_ERR_CUDA; }

@@ -279,7 +279,10 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
             // is subsampled and a grey read would need upsampling, which is not supported
             if (!single && (Y.h != hmax || Y.v != vmax)) return fail("JPEG with a subsampled luminance component is not supported");
             const size_t pw = static_cast<size_t>(mcus_x) * yh * 8, ph = static_cast<size_t>(mcus_y) * yv * 8;
-            std::vector<uint8_t> plane(pw * ph);
+            // per-thread scratch, reused from frame to frame: a fresh 2 MB vector per frame means mmap + page faults + munmap on
+            // every decode, and with dozens of decode threads those serialise on the process's address-space lock
+            static thread_local std::vector<uint8_t> plane;
+            plane.resize(pw * ph);      // every block of the padded plane is written by the loop below
             BitReader br{d + pos, d + n};
             int32_t coef[64];
             int until_restart = restart_interval;

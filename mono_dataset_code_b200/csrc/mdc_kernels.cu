@@ -210,7 +210,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
     }
 
     // ================================================================ consumer warps
-    const size_t n_in = static_cast<size_t>(p.in_w) * p.in_h;
+    const size_t n_in = static_cast<size_t>(p.in_pitch) * p.in_h;      // bytes from one frame to the next (rows may be padded)
     const uint32_t lut_lane = smem_u32(lut) + 4u * lane;
     uint32_t st = 0, phase = 0;   // ring position / parity of the next staged frame to consume
     uint32_t st_addr = stage0;    // = stage0 + st * stage_bytes
@@ -236,7 +236,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         const int bw = td.bw_bh & 0xffff, bh = td.bw_bh >> 16;
         const int tx0 = (tile % p.tiles_x) * kTile, ty0 = (tile / p.tiles_x) * kTile;
         const int ox = tx0 + lane, oy0 = ty0 + 4 * warp;
-        const int pitch = staged ? bw : p.in_w;       // distance between the two tap rows
+        const int pitch = staged ? bw : p.in_pitch;   // distance between the two tap rows
 
         float w[4][4], vi[4][4];
         uint32_t off[4];
@@ -265,8 +265,8 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                 w[q][2] = __fsub_rn(fy, fxy);
                 w[q][1] = __fsub_rn(fx, fxy);
                 w[q][0] = __fadd_rn(__fsub_rn(__fsub_rn(1.0f, fx), fy), fxy);
-                const int g = yi * p.in_w + xi;
-                off[q] = static_cast<uint32_t>(staged ? (yi - td.y0) * bw + (xi - td.x0) : g);
+                const int g = yi * p.in_w + xi;               // index into the (tightly packed) vignette table
+                off[q] = static_cast<uint32_t>(staged ? (yi - td.y0) * bw + (xi - td.x0) : yi * p.in_pitch + xi);
                 if (kVig) {
                     vi[q][0] = __ldg(p.vinv + g);
                     vi[q][1] = __ldg(p.vinv + g + 1);
@@ -282,7 +282,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
         const int ld_col = tid & ((1 << lg) - 1), ld_row = tid >> lg, ld_rstep = kConsumers >> lg;
         const int ld_pass = (staged && !kTma) ? (bh + ld_rstep - 1) / ld_rstep : 0;
         const bool ld_col_ok = (ld_col * 4) < bw;
-        const bool ld_fast = ((p.in_w & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0);
+        const bool ld_fast = ((p.in_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0);
         uint32_t pre[kMaxBoxWordsPerThread];
         auto ldg_box = [&](int frame) {   // issue the global loads of `frame`'s box into registers
             const uint8_t* src = p.frames + static_cast<size_t>(frame) * n_in;
@@ -292,7 +292,7 @@ fused_prepare_kernel(const __grid_constant__ FusedParams p, const __grid_constan
                 if (k < ld_pass) {
                     const int row = ld_row + k * ld_rstep, gy = td.y0 + row, gx = td.x0 + ld_col * 4;
                     if (ld_col_ok && row < bh && gy < p.in_h && gx < p.in_w) {
-                        const uint8_t* a = src + static_cast<size_t>(gy) * p.in_w + gx;
+                        const uint8_t* a = src + static_cast<size_t>(gy) * p.in_pitch + gx;
                         if (ld_fast) v = __ldg(reinterpret_cast<const uint32_t*>(a));
                         else {
                             v = __ldg(a);
@@ -1141,12 +1141,18 @@ constexpr int kEbThreads = (kEbWarps + 1) * 32;
 constexpr int kEbTile = kEbWarps * 128;          // pixels (= bytes) of one plane per stage row
 constexpr int kEbPlanes = 8;                     // exposures per stage
 constexpr int kEbStages = 3;
-constexpr int kEbMaxN = 1024;                    // exposure times cached in shared memory up to this n
+constexpr int kEbMaxN = 1024;                    // exposure times served from constant memory up to this n
 constexpr int kEbStageBytes = kEbPlanes * kEbTile;
 constexpr int kEbRegionBytes = kEstepTableBytes; // op-specific region: lookup table (E-step, rmse) or histograms (G-step)
-constexpr int kEbSmemBytes = kEbRegionBytes + kEbMaxN * 8 + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
+constexpr int kEbSmemBytes = kEbRegionBytes + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
 
 struct StreamArgs { const uint8_t* data; int n; uint32_t npix; const double* t; };
+
+// Exposure times of the current pass in CONSTANT memory (n <= kEbMaxN): every lane of a warp needs the same t[i], so a shared-memory
+// copy costs one (broadcast) LDS.64 wavefront per warp and exposure on the pipe that bounds these kernels — 1 of 10 for the E-step —
+// while the constant cache serves it for free (LDC with a warp-uniform index).  The symbol is refilled device-to-device on the
+// launching stream before every pass; an event keeps a refill (from any stream of this device) behind the last pass that read it.
+__constant__ double c_exposure_t[kEbMaxN];
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1176,8 +1182,8 @@ __device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_t
     }
 }
 
-template <class Op, bool kTimesInSmem>
-__device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_tiles, const double* sT, uint32_t stages, uint32_t bar_full,
+template <class Op, bool kTimesInConst>
+__device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_tiles, uint32_t stages, uint32_t bar_full,
                                                uint32_t bar_empty, Op& op) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t mine = stages + warp * 128u + lane * 4u;
@@ -1193,7 +1199,7 @@ __device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_t
             auto plane = [&](int p) {
                 uint32_t v;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + static_cast<uint32_t>(p) * kEbTile));
-                op.word(v, kTimesInSmem ? sT[i0 + p] : __ldg(a.t + i0 + p));
+                op.word(v, kTimesInConst ? c_exposure_t[i0 + p] : __ldg(a.t + i0 + p));
             };
             if (i0 + kEbPlanes <= a.n) {
                 if (Op::kUnroll) {
@@ -1217,16 +1223,13 @@ __device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_t
 template <class Op>
 __global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, typename Op::Params prm) {
     extern __shared__ __align__(128) uint8_t smem_b[];
-    double* sT = reinterpret_cast<double*>(smem_b + kEbRegionBytes);                  // [min(n, kEbMaxN)]
-    const uint32_t stages = smem_u32(smem_b + kEbRegionBytes + kEbMaxN * 8);          // [kEbStages][kEbPlanes][kEbTile]
+    const uint32_t stages = smem_u32(smem_b + kEbRegionBytes);                        // [kEbStages][kEbPlanes][kEbTile]
     const uint32_t bar_full = stages + kEbStages * kEbStageBytes, bar_empty = bar_full + 8u * kEbStages;
-    const bool times_in_smem = a.n <= kEbMaxN;
+    const bool times_in_const = a.n <= kEbMaxN;                                        // launch_stream filled c_exposure_t
     if (threadIdx.x == 0) {
         for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, kEbWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (times_in_smem)
-        for (int i = threadIdx.x; i < a.n; i += blockDim.x) sT[i] = a.t[i];
     Op::prologue(smem_b, prm);
     __syncthreads();
     const uint32_t n_tiles = (a.npix + kEbTile - 1) / kEbTile;
@@ -1235,8 +1238,8 @@ __global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, 
         return;
     }
     Op op(smem_b, prm);
-    if (times_in_smem) stream_consume<Op, true>(a, n_tiles, sT, stages, bar_full, bar_empty, op);
-    else stream_consume<Op, false>(a, n_tiles, sT, stages, bar_full, bar_empty, op);
+    if (times_in_const) stream_consume<Op, true>(a, n_tiles, stages, bar_full, bar_empty, op);
+    else stream_consume<Op, false>(a, n_tiles, stages, bar_full, bar_empty, op);
     op.epilogue(smem_b, prm);
 }
 
@@ -1331,7 +1334,7 @@ struct GstepOp {
 
 // rmse() (main_responseCalib.cpp:50-69): e = sum (G[b] - t*E)^2 * 1e-10 over finite residuals of unsaturated samples, num = count
 struct RmseOp {
-    struct Params { const double* G; const double* E; double* acc; };
+    struct Params { const double* G; const double* E; double* partials; };      // partials[2*cta] = {error, count} of one CTA
     static constexpr bool kUnroll = true;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
     uint32_t table, lane8;
@@ -1380,14 +1383,14 @@ struct RmseOp {
         if (threadIdx.x == 0) {
             double se = 0.0, sc = 0.0;
             for (int w = 0; w < kEbWarps; ++w) { se = __dadd_rn(se, part[2 * w]); sc = __dadd_rn(sc, part[2 * w + 1]); }
-            atomicAdd(p.acc, se);
-            atomicAdd(p.acc + 1, sc);
+            p.partials[2 * blockIdx.x] = se;            // no atomics: the CTA partials are folded in CTA order by rc_fold_pairs_kernel,
+            p.partials[2 * blockIdx.x + 1] = sc;        // so two runs over the same data give the same bits
         }
     }
 };
 
 template <class Op>
-static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params& prm, cudaStream_t stream) {
+static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params& prm, cudaStream_t stream, int* grid_out = nullptr) {
     int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1399,8 +1402,18 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
     const long long tiles = (static_cast<long long>(a.npix) + kEbTile - 1) / kEbTile;
     long long grid = static_cast<long long>(sms) * per_sm;
     if (grid > tiles) grid = tiles;
+    if (grid_out) *grid_out = static_cast<int>(grid);
+    // exposure times -> constant memory (device-to-device, on this stream), behind the last pass that read the symbol
+    static cudaEvent_t last_reader[64] = {};
+    const bool use_const = a.n <= kEbMaxN && dev >= 0 && dev < 64;
+    if (use_const) {
+        if (!last_reader[dev] && (e = cudaEventCreateWithFlags(&last_reader[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
+        else if ((e = cudaStreamWaitEvent(stream, last_reader[dev], 0)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbolAsync(c_exposure_t, a.t, static_cast<size_t>(a.n) * sizeof(double), 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+    }
     rc_stream_kernel<Op><<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(a, prm);
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return use_const ? cudaEventRecord(last_reader[dev], stream) : cudaSuccess;
 }
 // the bulk-copy loader needs 16-byte aligned rows
 static bool stream_ok(const uint8_t* data, int npix) {
@@ -1543,7 +1556,15 @@ __global__ void __launch_bounds__(256) rc_rmse_kernel(const uint8_t* __restrict_
         if (threadIdx.x < s) { s_e[threadIdx.x] += s_e[threadIdx.x + s]; s_n[threadIdx.x] += s_n[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { atomicAdd(&acc[0], s_e[0]); atomicAdd(&acc[1], s_n[0]); }
+    if (threadIdx.x == 0) { acc[2 * blockIdx.x] = s_e[0]; acc[2 * blockIdx.x + 1] = s_n[0]; }      // per-CTA partials, folded in order afterwards
+}
+
+// out[0..1] = the per-CTA {error, count} pairs summed in CTA order (fixed order => run-to-run identical bits)
+__global__ void rc_fold_pairs_kernel(const double* __restrict__ partials, int n_pairs, double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < n_pairs; ++i) { a = __dadd_rn(a, partials[2 * i]); b = __dadd_rn(b, partials[2 * i + 1]); }
+    out[0] = a; out[1] = b;
 }
 
 static unsigned rc_blocks(size_t work) {
@@ -1600,11 +1621,21 @@ cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cu
     rc_scale_kernel<<<1, 256, 0, s>>>(G, 256, factor);
     return cudaGetLastError();
 }
-cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s);
-    if (e != cudaSuccess) return e;
-    if (stream_ok(data, npix)) return launch_stream<RmseOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, RmseOp::Params{G, E, acc2}, s);
-    rc_rmse_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, G, E, acc2);
+// partials: scratch for one {error, count} pair per CTA (kRmsePartialPairs pairs)
+cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, double* partials,
+                           cudaStream_t s) {
+    int grid = 0;
+    cudaError_t e;
+    if (stream_ok(data, npix)) {
+        e = launch_stream<RmseOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, RmseOp::Params{G, E, partials}, s, &grid);
+        if (e != cudaSuccess) return e;
+    } else {
+        grid = static_cast<int>(rc_blocks(static_cast<size_t>(npix)));
+        rc_rmse_kernel<<<grid, 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, G, E, partials);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (grid > kRmsePartialPairs) return cudaErrorInvalidValue;
+    rc_fold_pairs_kernel<<<1, 32, 0, s>>>(partials, grid, acc2);
     return cudaGetLastError();
 }
 

@@ -45,9 +45,10 @@ struct TexSet {
 };
 
 struct FusedParams {
-    const uint8_t* frames;       // [n_frames][in_w*in_h]
+    const uint8_t* frames;       // [n_frames][in_h][in_pitch]
     int n_frames;
     int in_w, in_h, out_w, out_h;
+    int in_pitch;                // bytes from one input row to the next (>= in_w; the vignette / remap tables stay tightly packed)
     const float* remap_x;        // [out_w*out_h]
     const float* remap_y;
     const float* vinv;           // [in_w*in_h] or nullptr
@@ -102,6 +103,8 @@ cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const do
 cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s);
 bool rc_counts_reusable(const uint8_t* data, int npix);      // reuse_counts is only available on the bulk-copy streaming path
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s);
-cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, cudaStream_t s);
+constexpr int kRmsePartialPairs = 2048;      // rmse: capacity of the per-CTA partial scratch ({error, count} pairs)
+cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t, const double* G, const double* E, double* acc2, double* partials,
+                           cudaStream_t s);
 
 }  // namespace mdc

@@ -15,7 +15,8 @@
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
-#include <future>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -173,9 +174,10 @@ void load_times(mdc_seq* s) {
 
 // 8-bit grey pixels of frame `id` (decoded); 16-bit sources keep the high byte
 bool read_gray8_unguarded(const mdc_seq* s, int id, std::vector<uint8_t>* px, int* w, int* h) {
-    mdc_gray_image img;
+    // per-thread scratch (file bytes, decoded image): no multi-megabyte allocation per frame, see mdc_jpeg.cpp
+    static thread_local mdc_gray_image img;
+    static thread_local std::vector<uint8_t> file;
     if (s->zipped) {
-        std::vector<uint8_t> file;
         if (!read_zip_entry(s, s->entries[static_cast<size_t>(id)], &file)) return false;
         if (!mdc_decode_gray_image(file, s->files[static_cast<size_t>(id)], &img)) return false;
     } else if (!mdc_read_gray_image(s->files[static_cast<size_t>(id)], &img)) {
@@ -280,56 +282,90 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     for (int l = 0; l < levels; ++l)      // level l of getImage's result: (w >> l) x (h >> l), mdc_prepare_batch
         level_px[static_cast<size_t>(l)] = static_cast<size_t>((rectify ? out_w : in_w) >> l) * static_cast<size_t>((rectify ? out_h : in_h) >> l);
     if (threads < 1) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
-    // one frame per decode thread and chunk, so that a JPEG sequence keeps all of them busy; 32..256 frames per chunk
-    const int chunk = std::min(256, std::max(32, threads));
+    // several frames per decode thread and chunk: decode times vary from frame to frame, and a chunk is as slow as its slowest thread
+    const int chunk = std::min(256, std::max(32, 4 * threads));
     void* stage[2] = {nullptr, nullptr};
     for (int b = 0; b < 2; ++b)
         if (mdc_host_alloc(&stage[b], static_cast<size_t>(chunk) * n_in) != MDC_OK) { if (stage[0]) mdc_host_free(stage[0]); return MDC_ERR_CUDA; }
 
-    // decode frames [f0, f0+n) into `dst` on `threads` workers; returns "" or the first error text
-    auto decode_chunk = [&](int f0, int n, uint8_t* dst) -> std::string {
-        std::vector<std::future<std::string>> jobs;
-        const int workers = std::min(threads, n);
-        for (int t = 0; t < workers; ++t)
-            jobs.push_back(std::async(std::launch::async, [&, t]() -> std::string {
-                std::vector<uint8_t> px;
-                for (int i = t; i < n; i += workers) {
-                    int w = 0, h = 0;
-                    if (!read_gray8(s, f0 + i, &px, &w, &h)) return std::string(mdc_last_error());
-                    if (w != in_w || h != in_h) {      // BenchmarkDatasetReader.h:194-199
-                        char msg[256];
-                        snprintf(msg, sizeof msg, "expected image dimensions %d x %d; found %d x %d (image %s)", in_w, in_h, w, h, s->files[static_cast<size_t>(f0 + i)].c_str());
-                        return std::string(msg);
-                    }
+    // Decode pool: `threads` workers live for the whole call.  Worker t decodes frames t, t+threads, ... of chunk k into stage[k & 1],
+    // then moves on to chunk k+1 as soon as the GPU side has released that chunk's buffer (chunk k-1 consumed), so decode of chunk k+1
+    // overlaps H2D / K1 / D2H of chunk k, and nobody creates threads or multi-megabyte buffers per frame.
+    const int n_chunks = (count + chunk - 1) / chunk;
+    const int workers = std::min(threads, std::min(count, chunk));
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> decoded(static_cast<size_t>(n_chunks), 0);      // workers finished with chunk k
+    int released = 1;                 // chunks whose buffer may be written: 0 .. released (stage[0] and stage[1] are free at the start)
+    bool abort = false;
+    std::string first_error;
+    auto worker = [&](int t) {
+        std::vector<uint8_t> px;
+        for (int k = 0; k < n_chunks; ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort || k <= released; });
+                if (abort) return;
+            }
+            const int f0 = k * chunk, n = std::min(chunk, count - f0);
+            uint8_t* dst = static_cast<uint8_t*>(stage[k & 1]);
+            std::string err;
+            for (int i = t; i < n && err.empty(); i += workers) {
+                int w = 0, h = 0;
+                if (!read_gray8(s, first + f0 + i, &px, &w, &h)) err = mdc_last_error();
+                else if (w != in_w || h != in_h) {      // BenchmarkDatasetReader.h:194-199
+                    char msg[256];
+                    snprintf(msg, sizeof msg, "expected image dimensions %d x %d; found %d x %d (image %s)", in_w, in_h, w, h, s->files[static_cast<size_t>(first + f0 + i)].c_str());
+                    err = msg;
+                } else {
                     memcpy(dst + static_cast<size_t>(i) * n_in, px.data(), n_in);
                 }
-                return std::string();
-            }));
-        std::string err;
-        for (size_t j = 0; j < jobs.size(); ++j) { const std::string e = jobs[j].get(); if (err.empty()) err = e; }
-        return err;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (!err.empty() && first_error.empty()) first_error = err;
+            ++decoded[static_cast<size_t>(k)];
+            cv.notify_all();
+        }
     };
-
+    std::vector<std::thread> pool;
+    try {
+        for (int t = 0; t < workers; ++t) pool.emplace_back(worker, t);
+    } catch (const std::exception& e) {
+        { std::lock_guard<std::mutex> lk(mu); abort = true; }
+        cv.notify_all();
+        for (auto& th : pool) th.join();
+        mdc_host_free(stage[0]); mdc_host_free(stage[1]);
+        mdc_set_error("mdc_seq_prepare: cannot start decode threads (%s)", e.what());
+        return MDC_ERR_IO;
+    }
     int rc = MDC_OK;
-    const int n_chunks = (count + chunk - 1) / chunk;
-    std::future<std::string> ahead = std::async(std::launch::async, decode_chunk, first, std::min(chunk, count), static_cast<uint8_t*>(stage[0]));
     for (int k = 0; k < n_chunks && rc == MDC_OK; ++k) {
-        const std::string err = ahead.get();
-        const int f0 = k * chunk, n = std::min(chunk, count - f0);
-        if (k + 1 < n_chunks)
-            ahead = std::async(std::launch::async, decode_chunk, first + f0 + chunk, std::min(chunk, count - f0 - chunk), static_cast<uint8_t*>(stage[(k + 1) & 1]));
+        std::string err;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return decoded[static_cast<size_t>(k)] == workers; });
+            err = first_error;
+        }
         if (!err.empty()) {
             printf("ERROR: %s\n", err.c_str());
             mdc_set_error("mdc_seq_prepare: %s", err.c_str());
             rc = MDC_ERR_FORMAT;
-            if (k + 1 < n_chunks) ahead.get();
             break;
         }
+        const int f0 = k * chunk, n = std::min(chunk, count - f0);
         std::vector<float*> outs(static_cast<size_t>(levels));
         for (int l = 0; l < levels; ++l) outs[static_cast<size_t>(l)] = h_out_levels[l] ? h_out_levels[l] + static_cast<size_t>(f0) * level_px[static_cast<size_t>(l)] : nullptr;
-        rc = mdc_prepare_batch_host(c, static_cast<const uint8_t*>(stage[k & 1]), n, flags, outs.data(), levels);
-        if (rc != MDC_OK && k + 1 < n_chunks) ahead.get();
+        rc = mdc_prepare_batch_host(c, static_cast<const uint8_t*>(stage[k & 1]), n, flags, outs.data(), levels);      // returns after the D2H copy
+        std::lock_guard<std::mutex> lk(mu);
+        released = k + 2;             // stage[k & 1] is free again: chunk k+2 may be decoded into it
+        cv.notify_all();
     }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        abort = true;                 // error path: wake workers that wait for a buffer that will not be released
+    }
+    cv.notify_all();
+    for (auto& th : pool) th.join();
     mdc_host_free(stage[0]);
     mdc_host_free(stage[1]);
     return rc;

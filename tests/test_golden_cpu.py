@@ -84,3 +84,27 @@ def test_restated_response_calib_loop_reproduces_the_programs_golden_output(port
     assert np.max(np.abs(G[fin] - g["G"][fin]) / np.maximum(np.abs(g["G"][fin]), 1e-300)) < 5e-14
     assert np.array_equal(np.array(nums), g["log_num"])
     assert np.max(np.abs(np.array(rmses) - g["log_rmse"]) / g["log_rmse"]) < 5e-14
+
+
+def test_pyramid_restatement_is_pinned_by_an_independent_formulation(port):
+    """Row P has no reference source; oracle/port's pyramid is compared here, bit for bit, with a second formulation written from
+    DSO's makeImages (tests/pyramid_spec.py): odd sizes, NaN / inf pixels, denormal-range sums."""
+    import pyramid_spec as spec
+    rng = np.random.default_rng(3)
+    for (w, h, levels) in [(64, 48, 5), (67, 45, 5), (1, 1, 3), (3, 2, 2), (130, 70, 7)]:
+        img = rng.uniform(-50, 300, w * h).astype(np.float32)
+        img[rng.integers(0, w * h, 5)] = np.nan
+        img[rng.integers(0, w * h, 3)] = np.inf
+        img[rng.integers(0, w * h, 3)] = np.float32(1e-42)
+        got = port.pyramid(img, w, h, levels)
+        exp = spec.pyramid(img, w, h, levels)
+        assert len(got) == len(exp) == levels
+        for l in range(levels):
+            assert got[l].shape == exp[l].shape == ((w >> l) * (h >> l),)
+            assert np.array_equal(np.isnan(got[l]), np.isnan(exp[l]))
+            m = ~np.isnan(exp[l])
+            assert np.array_equal(got[l][m].view(np.uint32), exp[l][m].view(np.uint32)), (w, h, l)
+    # tap order matters: ((a+b)+c)+d differs from (a+c)+(b+d) in the last bit on suitable data, and the spec takes the former
+    a, b, c, d = np.float32(1e8), np.float32(1.0), np.float32(-1e8), np.float32(1.0)
+    blk = np.array([[a, b], [c, d]], np.float32)
+    assert spec.pyr_down(blk)[0, 0] == np.float32(0.25) * (((a + b) + c) + d) != np.float32(0.25) * ((a + c) + (b + d))

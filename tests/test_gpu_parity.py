@@ -9,6 +9,7 @@ import os
 import numpy as np
 import pytest
 
+import pyramid_spec
 from conftest import CALIBS, BIG_CALIBS, ROOT, assert_bits_equal
 from mono_dataset_code_b200 import synthetic as S
 
@@ -96,9 +97,11 @@ def test_pyramid_levels(name, loader, api, port, dataset_dir):
         for i in range(frames.shape[0]):
             lvl0 = port.get_image(rx, ry, iw, ih, ginv, vinv, frames[i], *flags)
             exp = port.pyramid(lvl0, w0, h0, levels)
+            spec = pyramid_spec.pyramid(lvl0, w0, h0, levels)      # second, independently written formulation (DSO makeImages)
             for l in range(levels):
                 assert outs[l].shape[1] == (w0 >> l) * (h0 >> l)
                 assert_bits_equal(outs[l][i], exp[l], f"{name}/{loader} levels={levels} flags={flags} frame={i} level={l}")
+                assert_bits_equal(outs[l][i], spec[l], f"{name}/{loader} vs DSO spec levels={levels} flags={flags} frame={i} level={l}")
 
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
@@ -615,3 +618,42 @@ def test_pixel_sharded_calibrator_two_gpus_nccl(api, port, tmp_path):
         np.testing.assert_allclose(np.concatenate([a["E_" + tag], b["E_" + tag]]), E1.cpu().numpy(), rtol=1e-10, equal_nan=True)
         np.testing.assert_allclose(a["log_" + tag], log1, rtol=1e-9)
         assert np.array_equal(a["log_" + tag], b["log_" + tag])
+
+
+@pytest.mark.parametrize("name", ["odd_sizes", "c1_crop_640"])
+def test_padded_rows_keep_odd_widths_on_the_fast_loaders(name, api, port, dataset_dir):
+    """a width that is not a multiple of 16 bytes cannot be described to TMA when the rows are tightly packed, but it
+    can with a padded row pitch — mdc_prepare_batch_pitched on the device, and mdc_prepare_batch_host pads during its H2D copy.
+    Every loader that accepts the padded layout must reproduce the oracle bit for bit, pyramid included."""
+    iw, ih, ow, oh, mode, calib = CALIBS[name]
+    files = dataset_dir(name)
+    u, p = make_models(api, files, iw, ih)
+    prep = api.FramePreparer(u, p)
+    rx, ry, ginv, vinv = oracle_tables(port, files)
+    frames = mixed_frames(9, iw, ih)
+    exp = [port.pyramid(port.get_image(rx, ry, iw, ih, ginv, vinv, f, 1, 1, 1, 1), ow, oh, 4) for f in frames]
+    pitch = (iw + 63) & ~31                       # 32-byte multiple, strictly larger than the width
+    padded = torch.full((frames.shape[0], ih, pitch), 77, dtype=torch.uint8, device="cuda")
+    padded[:, :, :iw] = torch.from_numpy(frames.reshape(-1, ih, iw)).cuda()
+    shapes = prep.level_shapes(True, 4)
+    ran = []
+    for loader in (-1, 0, 1, 2, 3):
+        prep.ctx.configure(use_tma=loader)
+        outs = [torch.zeros((frames.shape[0], w * h), dtype=torch.float32, device="cuda") for (w, h) in shapes]
+        try:
+            prep.ctx.prepare_batch_pitched(padded, pitch, 1 | 2 | 4 | 8, outs)
+        except api.MdcError as exc:                # a loader that cannot take this layout says so instead of computing something else
+            assert exc.code == 6 and loader > 0, (loader, str(exc))
+            continue
+        ran.append(loader)
+        for i in range(frames.shape[0]):
+            for l in range(4):
+                assert_bits_equal(outs[l][i].cpu().numpy(), exp[i][l], f"{name} pitched loader={loader} frame={i} level={l}")
+    assert -1 in ran and 0 in ran and 1 in ran, ran       # auto, LDG and — thanks to the padding — TMA
+    # host path: tightly packed odd-width frames in, padded on the way to the device
+    prep.ctx.configure(use_tma=-1)
+    host_out = [np.zeros((frames.shape[0], w * h), np.float32) for (w, h) in shapes]
+    prep.ctx.prepare_batch_host(frames, 1 | 2 | 4 | 8, host_out)
+    for i in range(frames.shape[0]):
+        for l in range(4):
+            assert_bits_equal(host_out[l][i], exp[i][l], f"{name} host path frame={i} level={l}")
