@@ -59,13 +59,23 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_frame():
-    """dram__bytes_read+write of K1 per frame from the committed `ncu --set full` capture (profiles/), or None."""
+def ncu_traffic(name):
+    """Per-launch DRAM traffic of a kernel from a committed `ncu --set full` capture (profiles/<name>, written by
+    scripts/ncu_summary.py) — only if it was captured from the kernel sources that are being benchmarked: the file carries their
+    SHA-256, and a capture of older sources is reported as absent rather than passed off as a measurement of this binary."""
+    import hashlib
     try:
-        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            doc = json.load(f)
+        h = hashlib.sha256()
+        for rel in doc["kernel_sources"]:
+            with open(os.path.join(ROOT, rel), "rb") as src:
+                h.update(src.read())
+        if h.hexdigest() != doc["kernel_sources_sha256"]:
+            return None, f"profiles/{name} was captured at commit {doc.get('captured_at_commit')} from different kernel sources: stale, not reported"
+        return doc, doc["note"] + f" [captured at commit {doc.get('captured_at_commit')}, kernel sources unchanged since]"
+    except Exception as exc:
+        return None, f"no usable ncu capture ({exc.__class__.__name__})"
 
 
 def write_calibration(tmp):
@@ -426,7 +436,7 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
     import torch.distributed as dist
     import cv2
     from mono_dataset_code_b200 import _lib, api, sharding, synthetic as S
-    W, H, K = 1920, 1080, 128
+    W, H, K, UNIQUE, CALL = 1920, 1080, 1024, 128, 256      # zip entries, distinct JPEG payloads among them, frames per mdc_seq_prepare call
     root = os.path.join(tempfile.gettempdir(), f"mdc_c4_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}")
     if rank == 0:
         os.makedirs(root, exist_ok=True)
@@ -435,13 +445,16 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
         with zipfile.ZipFile(os.path.join(root, "images.zip"), "w", zipfile.ZIP_STORED) as z:
             yy, xx = np.mgrid[0:H, 0:W]
             rng = np.random.default_rng(11)
-            for i in range(K):          # a textured, slowly changing scene with mild sensor noise (JPEG size / decode cost of a real sequence, not of white noise)
+            blobs = []
+            for i in range(UNIQUE):     # a textured, slowly changing scene with mild sensor noise (JPEG size / decode cost of a real sequence, not of white noise)
                 img = (xx * (150.0 / W) + yy * (60.0 / H) + 40 * np.sin((xx + 13 * i) * 0.05) * np.cos((yy - 7 * i) * 0.04)
                        + ((xx // 64 + yy // 64 + i) % 2) * 30 + rng.normal(0, 1.5, (H, W)))
                 img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
                 ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
-                z.writestr(f"{i:05d}.jpg", enc.tobytes())
+                blobs.append(enc.tobytes())
                 sizes.append(len(enc))
+            for i in range(K):
+                z.writestr(f"{i:05d}.jpg", blobs[i % UNIQUE])
         with open(os.path.join(root, "times.txt"), "w") as f:
             for i in range(K):
                 f.write(f"{i} {i * 0.05:.3f} 1.0\n")
@@ -469,25 +482,37 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
     threads = max(1, len(os.sched_getaffinity(0)) // max(1, same_node))
     n_px = W * H
     h_out = C.c_void_p()
-    _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_out), K * n_px * 4), "mdc_host_alloc")
+    _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_out), CALL * n_px * 4), "mdc_host_alloc")
     ptrs = (C.c_void_p * 1)(h_out.value)
 
     def run_decode(n_frames):
         v, done = begin, 0
         while done < n_frames:
             first = v % K
-            cnt = min(K - first, n_frames - done)
+            cnt = min(K - first, n_frames - done, CALL)
             _lib.check(_lib.lib.mdc_seq_prepare(ctx._h, seq._h, first, cnt, FLAGS_ALL, ptrs, 1, threads), "mdc_seq_prepare")
             v += cnt; done += cnt
-    run_decode(min(n_mine, K))            # warm-up: page cache, thread pool, pinned staging
+    run_decode(min(n_mine, CALL))         # warm-up: page cache, thread pool, pinned staging
     # more decode threads are not always faster on these hosts (SMT siblings, shared memory bandwidth): short sweep, keep the best
     sweep, cap = [], threads
     for cand in sorted({max(1, cap // 4), max(1, cap // 2), cap}):
         threads = cand
         t0 = time.perf_counter()
-        run_decode(min(n_mine, 2 * K))
-        sweep.append({"threads": cand, "frames_per_s_this_rank": round(min(n_mine, 2 * K) / (time.perf_counter() - t0), 1)})
+        run_decode(min(n_mine, 2 * CALL))
+        sweep.append({"threads": cand, "frames_per_s_this_rank": round(min(n_mine, 2 * CALL) / (time.perf_counter() - t0), 1)})
     threads = max(sweep, key=lambda r: r["frames_per_s_this_rank"])["threads"]
+    # what the host side alone delivers at that thread count (zip read + JPEG decode into per-thread buffers, no GPU work)
+    from concurrent.futures import ThreadPoolExecutor
+    bufs = [np.empty(n_px, np.uint8) for _ in range(threads)]
+
+    def decode_some(t):
+        w_, h_ = C.c_int(), C.c_int()
+        for i in range(t, 2 * CALL, threads):
+            _lib.lib.mdc_seq_read_gray8(seq._h, i % K, bufs[t].ctypes.data_as(C.c_void_p), n_px, C.byref(w_), C.byref(h_))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(decode_some, range(threads)))
+    decode_only = 2 * CALL / (time.perf_counter() - t0)
     if world > 1:                          # all ranks use the same count (the slowest rank sets the job's rate anyway)
         box = [threads]
         dist.broadcast_object_list(box, src=0)
@@ -525,10 +550,11 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
             pass
     total = args.seq_frames
     alg = total * (n_px + 4 * n_px)
-    return {"workload": f"{W}x{H} mono8 sequence of {total} frames ({K} baseline-JPEG entries of images.zip, cycled), frame-sharded over {world} rank(s) "
+    return {"workload": f"{W}x{H} mono8 sequence of {total} frames ({K} baseline-JPEG entries of images.zip, {UNIQUE} distinct, cycled; {CALL} frames per mdc_seq_prepare call), frame-sharded over {world} rank(s) "
                         "with shard_range; rectify|removeGamma|removeVignette",
             "decode_inclusive": {"value": total / dec_s, "unit": "frames/s", "seconds": dec_s, "decode_threads_per_rank": threads,
-                                 "decode_thread_sweep": sweep, "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
+                                 "decode_thread_sweep": sweep, "host_decode_only_frames_per_s_rank0": decode_only,
+                                 "d2h_bytes_per_frame": n_px * 4, "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
                                  "path": "mdc_seq_prepare: zip read + JPEG decode (host) -> pinned -> H2D -> K1 -> D2H, chunks double-buffered"},
             "device_resident": {"value": total / res_s, "unit": "frames/s", "seconds": res_s, "alg_gbs": alg / res_s / 1e9,
                                 "frames_per_launch": B, "launches_per_rank": launches}}
@@ -616,7 +642,7 @@ def run_gpu_arm(args):
             total_ms = float(t.item())
         return total_ms, per_launch_ms, ctx.launch_count - l0, clocks
 
-    TRAFFIC = ncu_traffic_per_frame()
+    TRAFFIC, TRAFFIC_NOTE = ncu_traffic("k1_traffic.json")
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, per_launch_ms, launches, clocks = timed(args.levels if args.only_kernel else 1, args.steps, args.warmup, sampler)
     value = world * B * args.steps / (total_ms * 1e-3)
@@ -633,7 +659,9 @@ def run_gpu_arm(args):
     # configs[2]: + 5-level pyramid fused in the same kernel's epilogue
     p_total_ms, p_launch_ms, _, _ = timed(5, max(2, args.steps // 2), 2)
     p_steps = max(2, args.steps // 2)
+    pyr_traffic, pyr_note = ncu_traffic("c3_pyramid_traffic.json")
     pyr = {"value": world * B * p_steps / (p_total_ms * 1e-3), "unit": "frames/s", "levels": 5,
+           "traffic": (pyr_traffic["dram_bytes_per_frame"] * B / 1e9 if pyr_traffic else None), "traffic_note": pyr_note,
            "achieved_gbs": B * (ALG_BYTES_PER_FRAME + PYR_EXTRA_BYTES) / (float(np.mean(p_launch_ms)) * 1e-3) / 1e9}
 
     # ---- BASELINE configs[4]: responseCalib E-step, 1000 exposures x 1 MP, fp64, bit-exact kernel K3 (1 GPU only)
@@ -655,7 +683,10 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
         alg = n_img * npix + 8 * npix
+        es_traffic, es_note = ncu_traffic("c5_estep_traffic.json")
         estep = {"ms_per_pass": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                 "traffic": (es_traffic["dram_bytes_read_per_launch"] + es_traffic["dram_bytes_write_per_launch"]) / 1e9 if es_traffic else None,
+                 "traffic_note": es_note,
                  "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "workload": "n=1000 x 1 MP u8 -> f64 E[1 MP]"}
         # the other passes of the calibrator over the same stack, and one whole iteration of its loop
         # (G-step, E-step, rescale, 3 x rmse; main_responseCalib.cpp:281-362)
@@ -736,8 +767,8 @@ def run_gpu_arm(args):
                                "loader": ({0: "ldg", 1: "tma", 2: "tex", 3: "hybrid"}[args.tma] if args.tma is not None else
                                           "auto(" + ctx.auto_loader() + ")")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": (TRAFFIC["dram_bytes_per_frame"] * B / 1e9 if TRAFFIC else None),
-                             "traffic_note": (TRAFFIC["note"] if TRAFFIC else "no ncu capture committed"),
+                             "traffic": (TRAFFIC["dram_bytes_per_frame"] * B / 1e9 if TRAFFIC else None), "traffic_unit": "GB per launch",
+                             "traffic_note": TRAFFIC_NOTE,
                              "peak_source": peak_src, "kernel": "fused_prepare_kernel",
                              "algorithmic_bytes_per_launch": B * ALG_BYTES_PER_FRAME, "launch_ms": k1_ms},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "c3_pyramid": pyr, "c4_sequence": c4, "c5_estep": estep}

@@ -57,6 +57,11 @@ struct mdc_seq {
     std::vector<ZipEntry> entries;     // parallel to files when zipped
     std::vector<double> timestamps;
     std::vector<float> exposures;
+    // pinned staging buffers of the decode-ahead feed, kept between mdc_seq_prepare calls (pinning hundreds of MB costs tens of
+    // milliseconds — more than decoding the frames of a short call); one feed at a time per sequence object
+    mutable void* stage[2] = {nullptr, nullptr};
+    mutable size_t stage_bytes = 0;
+    mutable std::mutex feed_mutex;
 };
 
 namespace {
@@ -237,6 +242,7 @@ extern "C" int mdc_seq_open(const char* folder, mdc_seq** out) {
 
 extern "C" void mdc_seq_close(mdc_seq* s) {
     if (!s) return;
+    for (int b = 0; b < 2; ++b) if (s->stage[b]) mdc_host_free(s->stage[b]);
     if (s->zip_fd >= 0) close(s->zip_fd);
     delete s;
 }
@@ -284,9 +290,20 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     if (threads < 1) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
     // several frames per decode thread and chunk: decode times vary from frame to frame, and a chunk is as slow as its slowest thread
     const int chunk = std::min(256, std::max(32, 4 * threads));
-    void* stage[2] = {nullptr, nullptr};
-    for (int b = 0; b < 2; ++b)
-        if (mdc_host_alloc(&stage[b], static_cast<size_t>(chunk) * n_in) != MDC_OK) { if (stage[0]) mdc_host_free(stage[0]); return MDC_ERR_CUDA; }
+    std::lock_guard<std::mutex> feed_lock(s->feed_mutex);
+    const size_t need = static_cast<size_t>(chunk) * n_in;
+    if (s->stage_bytes < need) {
+        for (int b = 0; b < 2; ++b) { if (s->stage[b]) mdc_host_free(s->stage[b]); s->stage[b] = nullptr; }
+        s->stage_bytes = 0;
+        for (int b = 0; b < 2; ++b)
+            if (mdc_host_alloc(&s->stage[b], need) != MDC_OK) {
+                if (s->stage[0]) mdc_host_free(s->stage[0]);
+                s->stage[0] = s->stage[1] = nullptr;
+                return MDC_ERR_CUDA;
+            }
+        s->stage_bytes = need;
+    }
+    void* const stage[2] = {s->stage[0], s->stage[1]};
 
     // Decode pool: `threads` workers live for the whole call.  Worker t decodes frames t, t+threads, ... of chunk k into stage[k & 1],
     // then moves on to chunk k+1 as soon as the GPU side has released that chunk's buffer (chunk k-1 consumed), so decode of chunk k+1
@@ -334,7 +351,6 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
         { std::lock_guard<std::mutex> lk(mu); abort = true; }
         cv.notify_all();
         for (auto& th : pool) th.join();
-        mdc_host_free(stage[0]); mdc_host_free(stage[1]);
         mdc_set_error("mdc_seq_prepare: cannot start decode threads (%s)", e.what());
         return MDC_ERR_IO;
     }
@@ -366,7 +382,5 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     }
     cv.notify_all();
     for (auto& th : pool) th.join();
-    mdc_host_free(stage[0]);
-    mdc_host_free(stage[1]);
     return rc;
 }
