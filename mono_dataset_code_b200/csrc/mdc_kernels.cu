@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -1128,15 +1129,15 @@ __global__ void __launch_bounds__(kEstepThreads, 2) estep_kernel(const uint8_t* 
 }
 
 // ---- K3, bulk-copy loader (image sizes that are a multiple of 16 pixels): the same arithmetic, but the u8 planes come in
-// through the async proxy.  A CTA owns a tile of 12 x 128 pixels; a producer warp streams it plane by plane with 1-D
+// through the async proxy.  A CTA owns a tile of kEbWarps x 128 pixels; a producer warp streams it plane by plane with 1-D
 // cp.async.bulk copies (1536 contiguous bytes each, 8 planes per stage) into a shared-memory ring, full/empty mbarriers
-// connect it to the 12 consumer warps (warp = 128 pixels, lane = 4 pixels, one LDS.32 per exposure).  The ring keeps
+// connect it to the kEbWarps consumer warps (warp = 128 pixels, lane = 4 pixels, one LDS.32 per exposure).  The ring keeps
 // 24 planes x 1.5 KB per CTA in flight without holding a register, runs ahead across tile boundaries, and DRAM sees
 // 1.5 KB bursts instead of independent 128-byte requests.
 //
 // The streaming skeleton is shared by the three passes of the calibrator that walk the whole image stack (E-step,
 // G-step, rmse); what happens to a word of 4 samples is the `Op`.
-constexpr int kEbWarps = 12;
+constexpr int kEbWarps = 14;
 constexpr int kEbThreads = (kEbWarps + 1) * 32;
 constexpr int kEbTile = kEbWarps * 128;          // pixels (= bytes) of one plane per stage row
 constexpr int kEbPlanes = 8;                     // exposures per stage
@@ -1146,7 +1147,8 @@ constexpr int kEbStageBytes = kEbPlanes * kEbTile;
 constexpr int kEbRegionBytes = kEstepTableBytes; // op-specific region: lookup table (E-step, rmse) or histograms (G-step)
 constexpr int kEbSmemBytes = kEbRegionBytes + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
 
-struct StreamArgs { const uint8_t* data; int n; uint32_t npix; const double* t; };
+// warps: consumer warps that take part (1..kEbWarps); a tile is warps x 128 pixels (chosen per launch, see launch_stream).
+struct StreamArgs { const uint8_t* data; int n; uint32_t npix; const double* t; int warps; };
 
 // Exposure times of the current pass in CONSTANT memory (n <= kEbMaxN): every lane of a warp needs the same t[i], so a shared-memory
 // copy costs one (broadcast) LDS.64 wavefront per warp and exposure on the pipe that bounds these kernels — 1 of 10 for the E-step —
@@ -1158,15 +1160,16 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void stream_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEbWarps * 32) : "memory"); }
+__device__ __forceinline__ void stream_consumer_barrier(int warps) { asm volatile("bar.sync 1, %0;" ::"r"(warps * 32) : "memory"); }
 
 // producer lane: streams this CTA's tiles, plane group by plane group, as far ahead as the ring allows
 __device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_tiles, uint32_t stages, uint32_t bar_full, uint32_t bar_empty) {
     const int n_groups = (a.n + kEbPlanes - 1) / kEbPlanes;
     uint32_t s = 0, ph = 0, it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t k0 = tile * kEbTile;
-        const uint32_t bytes = a.npix - k0 < static_cast<uint32_t>(kEbTile) ? a.npix - k0 : kEbTile;      // multiple of 16 (npix is)
+        const uint32_t tile_px = static_cast<uint32_t>(a.warps) * 128u;
+        const uint32_t k0 = tile * tile_px;
+        const uint32_t bytes = a.npix - k0 < tile_px ? a.npix - k0 : tile_px;      // multiple of 16 (npix is)
         const uint8_t* src = a.data + k0;
         for (int g = 0; g < n_groups; ++g, ++it) {
             if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
@@ -1190,7 +1193,7 @@ __device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_t
     const int n_groups = (a.n + kEbPlanes - 1) / kEbPlanes;
     uint32_t s = 0, ph = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const size_t k0 = static_cast<size_t>(tile) * kEbTile + warp * 128u + lane * 4u;
+        const size_t k0 = static_cast<size_t>(tile) * (static_cast<uint32_t>(a.warps) * 128u) + warp * 128u + lane * 4u;
         op.begin_tile(k0, k0 < a.npix);
         for (int g = 0; g < n_groups; ++g) {
             mbar_wait(bar_full + 8u * s, ph);
@@ -1227,17 +1230,20 @@ __global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, 
     const uint32_t bar_full = stages + kEbStages * kEbStageBytes, bar_empty = bar_full + 8u * kEbStages;
     const bool times_in_const = a.n <= kEbMaxN;                                        // launch_stream filled c_exposure_t
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, kEbWarps); }
+        for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, static_cast<uint32_t>(a.warps)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     Op::prologue(smem_b, prm);
     __syncthreads();
-    const uint32_t n_tiles = (a.npix + kEbTile - 1) / kEbTile;
+    const uint32_t tile_px = static_cast<uint32_t>(a.warps) * 128u;
+    const uint32_t n_tiles = (a.npix + tile_px - 1) / tile_px;
+    if ((threadIdx.x >> 5) >= a.warps && (threadIdx.x >> 5) != kEbWarps) return;      // consumer warps beyond the tile width sit this launch out
     if ((threadIdx.x >> 5) == kEbWarps) {
         if ((threadIdx.x & 31) == 0) stream_produce(a, n_tiles, stages, bar_full, bar_empty);
         return;
     }
     Op op(smem_b, prm);
+    op.warps = a.warps;
     if (times_in_const) stream_consume<Op, true>(a, n_tiles, stages, bar_full, bar_empty, op);
     else stream_consume<Op, false>(a, n_tiles, stages, bar_full, bar_empty, op);
     op.epilogue(smem_b, prm);
@@ -1255,6 +1261,7 @@ struct EstepOp {
     static constexpr bool kUnroll = true;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
     uint32_t table, lane8;
+    int warps = kEbWarps;         // active consumer warps of this launch (set by the kernel)
     double* E;
     double esum[4], enumr[4];
     __device__ __forceinline__ EstepOp(uint8_t* region, const Params& p) : table(smem_u32(region)), lane8((threadIdx.x & 31) * 8u), E(p.E) {}
@@ -1291,6 +1298,7 @@ struct GstepOp {
         for (int i = threadIdx.x; i < kEbRegionBytes / 4; i += blockDim.x) z[i] = 0u;
     }
     uint8_t* hist;
+    int warps = kEbWarps;             // active consumer warps of this launch (set by the kernel)
     uint32_t lane_sum, lane_cnt;      // byte offsets of this lane's slots inside a row
     const double* E;
     double e[4];
@@ -1316,8 +1324,8 @@ struct GstepOp {
     }
     __device__ __forceinline__ void end_tile(size_t, bool) {}
     __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
-        stream_consumer_barrier();
-        for (int b = threadIdx.x; b < 255; b += kEbWarps * 32) {
+        stream_consumer_barrier(warps);
+        for (int b = threadIdx.x; b < 255; b += warps * 32) {
             const double* hs = reinterpret_cast<const double*>(region + b * 256);
             const unsigned* hc = reinterpret_cast<const unsigned*>(region + b * 256 + 128);
             double sum = 0.0;
@@ -1338,6 +1346,7 @@ struct RmseOp {
     static constexpr bool kUnroll = true;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
     uint32_t table, lane8;
+    int warps = kEbWarps;             // active consumer warps of this launch (set by the kernel)
     const double* E;
     double e[4];
     double err;
@@ -1376,13 +1385,13 @@ struct RmseOp {
             err = __dadd_rn(err, __shfl_xor_sync(0xffffffffu, err, o));
             c = __dadd_rn(c, __shfl_xor_sync(0xffffffffu, c, o));
         }
-        stream_consumer_barrier();                      // every warp is done with the lookup table: reuse its first bytes
+        stream_consumer_barrier(warps);                 // every warp is done with the lookup table: reuse its first bytes
         double* part = reinterpret_cast<double*>(region);
         if ((threadIdx.x & 31) == 0) { part[2 * (threadIdx.x >> 5)] = err; part[2 * (threadIdx.x >> 5) + 1] = c; }
-        stream_consumer_barrier();
+        stream_consumer_barrier(warps);
         if (threadIdx.x == 0) {
             double se = 0.0, sc = 0.0;
-            for (int w = 0; w < kEbWarps; ++w) { se = __dadd_rn(se, part[2 * w]); sc = __dadd_rn(sc, part[2 * w + 1]); }
+            for (int w = 0; w < warps; ++w) { se = __dadd_rn(se, part[2 * w]); sc = __dadd_rn(sc, part[2 * w + 1]); }
             p.partials[2 * blockIdx.x] = se;            // no atomics: the CTA partials are folded in CTA order by rc_fold_pairs_kernel,
             p.partials[2 * blockIdx.x + 1] = sc;        // so two runs over the same data give the same bits
         }
@@ -1399,8 +1408,28 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rc_stream_kernel<Op>, kEbThreads, kEbSmemBytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const long long tiles = (static_cast<long long>(a.npix) + kEbTile - 1) / kEbTile;
-    long long grid = static_cast<long long>(sms) * per_sm;
+    // Tile width (consumer warps per CTA).  A CTA works through its tiles one after the other; measured per-tile time grows like
+    // (2.6 + warps) (profiles/r02_k3_stream_tile_width_sweep.jsonl), so the width that minimises rounds x (2.6 + warps) fills the
+    // persistent CTAs best: 14 warps = 2 rounds at 1 MP (12 warps: 3 uneven rounds).  Only widths 10..14 are candidates — narrower
+    // tiles lose more to the thinner ring than they gain in balance — and an image with fewer full-width tiles than CTAs keeps 14.
+    const long long slots = static_cast<long long>(sms) * per_sm;
+    int best_w = kEbWarps;
+    if ((static_cast<long long>(a.npix) + kEbWarps * 128 - 1) / (kEbWarps * 128) > slots) {
+        double best_cost = -1.0;
+        for (int w = kEbWarps; w >= 10; --w) {
+            const long long tiles_w = (static_cast<long long>(a.npix) + w * 128 - 1) / (w * 128);
+            const double cost = static_cast<double>((tiles_w + slots - 1) / slots) * (2.6 + w);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
+        }
+    }
+    if (const char* ov = getenv("MDC_STREAM_WARPS")) {      // measurement knob
+        const int w = atoi(ov);
+        if (w >= 1 && w <= kEbWarps) best_w = w;
+    }
+    StreamArgs args = a;
+    args.warps = best_w;
+    const long long tiles = (static_cast<long long>(a.npix) + best_w * 128 - 1) / (best_w * 128);
+    long long grid = slots;
     if (grid > tiles) grid = tiles;
     if (grid_out) *grid_out = static_cast<int>(grid);
     // exposure times -> constant memory (device-to-device, on this stream), behind the last pass that read the symbol
@@ -1411,7 +1440,7 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
         else if ((e = cudaStreamWaitEvent(stream, last_reader[dev], 0)) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbolAsync(c_exposure_t, a.t, static_cast<size_t>(a.n) * sizeof(double), 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
     }
-    rc_stream_kernel<Op><<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(a, prm);
+    rc_stream_kernel<Op><<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(args, prm);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return use_const ? cudaEventRecord(last_reader[dev], stream) : cudaSuccess;
 }
@@ -1427,7 +1456,7 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (stream_ok(data, npix))
-        return launch_stream<EstepOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, EstepOp::Params{G, E}, stream);
+        return launch_stream<EstepOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t, kEbWarps}, EstepOp::Params{G, E}, stream);
     const int vec_ok = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
     const size_t smem = kEstepTableBytes + static_cast<size_t>(kEstepMaxN) * sizeof(double);      // 96 KB
     cudaError_t e = cudaFuncSetAttribute(estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1595,7 +1624,7 @@ cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const do
     }
     if (npix <= 0 || n <= 0) return cudaSuccess;
     if (stream) {
-        const StreamArgs a{data, n, static_cast<uint32_t>(npix), t};
+        const StreamArgs a{data, n, static_cast<uint32_t>(npix), t, kEbWarps};
         return reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, gsum, gnum}, s)
                             : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, gsum, gnum}, s);
     }
@@ -1627,7 +1656,7 @@ cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t
     int grid = 0;
     cudaError_t e;
     if (stream_ok(data, npix)) {
-        e = launch_stream<RmseOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t}, RmseOp::Params{G, E, partials}, s, &grid);
+        e = launch_stream<RmseOp>(StreamArgs{data, n, static_cast<uint32_t>(npix), t, kEbWarps}, RmseOp::Params{G, E, partials}, s, &grid);
         if (e != cudaSuccess) return e;
     } else {
         grid = static_cast<int>(rc_blocks(static_cast<size_t>(npix)));
