@@ -404,6 +404,10 @@ def sharded_estep_leg(args, ctx, comm, dev, rank, world, peak, barrier):
     loop_ms, how = None, "python host loop over torch.distributed"
     nits = 3
     E2, G2 = torch.zeros_like(E), torch.zeros_like(G_tab)
+    if comm is not None:                  # first use of the communicator for all-reduces: NCCL connects its channels lazily (tens of ms)
+        comm.response_calib_sharded(ctx, data, t_exp, 1, E2, G2)
+    else:
+        sharding.response_calib_sharded(ctx, data, t_exp, 1, E2, G2)
     barrier()
     t0 = time.perf_counter()
     if comm is not None:
@@ -702,6 +706,15 @@ def run_gpu_arm(args):
         G_new = torch.zeros_like(G_tab)
         estep["gstep_ms"] = ms_of(lambda: ctx.rc_gstep(data, t_exp, E_out, G_new))
         estep["rmse_ms"] = ms_of(lambda: ctx.rc_rmse(data, t_exp, G_tab, E_out))
+        E2, G2 = torch.zeros_like(E_out), torch.zeros_like(G_tab)
+        ctx.response_calib(data, t_exp, 1, E2, G2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.response_calib(data, t_exp, 3, E2, G2)
+        torch.cuda.synchronize()
+        estep["loop_iteration_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+        estep["loop"] = "mdc_response_calib (G-step, E-step, rescale, 3 x rmse per iteration)"
+        del E2
         del data, E_out
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region)

@@ -10,6 +10,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fuse
     python bench.py --steps 3 --warmup 3 --only-kernel > gpurun_out/ncu_full_k1.log 2>&1; echo "ncu k1 rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:fused_prepare|pyr_down2" -s 6 -c 2 -o gpurun_out/prof_k1_pyr -f \
     python bench.py --steps 3 --warmup 3 --only-kernel --levels 5 > gpurun_out/ncu_full_k1_pyr.log 2>&1; echo "ncu k1 pyramid rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rc_stream_kernel -s 6 -c 4 -o gpurun_out/prof_calib -f \
+# rc_stream_kernel launches of scripts/estep_time.py: #1-13 E-step, #14-17 G-step, #18-21 rmse -> capture #13 .. #19
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rc_stream_kernel -s 12 -c 7 -o gpurun_out/prof_calib -f \
     python scripts/estep_time.py > gpurun_out/ncu_full_calib.log 2>&1; echo "ncu calibrator rc=$?"
 ls -la gpurun_out/*.ncu-rep
