@@ -806,7 +806,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU (device-resident)")
-    ap.add_argument("--e2e-batch", type=int, default=64, help="frames per host-buffer call")
+    ap.add_argument("--e2e-batch", type=int, default=256, help="frames per host-buffer call (16 pipeline chunks of 16 frames: fill / drain of the 3-deep pipeline < 2 %%)")
     ap.add_argument("--tma", "--loader", type=int, default=None, dest="tma",
                     help="force K1's input loader: 2 = texture gather, 1 = TMA, 0 = LDG (default: auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

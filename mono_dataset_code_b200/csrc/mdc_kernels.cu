@@ -1589,10 +1589,13 @@ __global__ void __launch_bounds__(256) rc_rmse_kernel(const uint8_t* __restrict_
 }
 
 // out[0..1] = the per-CTA {error, count} pairs summed in CTA order (fixed order => run-to-run identical bits)
-__global__ void rc_fold_pairs_kernel(const double* __restrict__ partials, int n_pairs, double* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) rc_fold_pairs_kernel(const double* __restrict__ partials, int n_pairs, double* __restrict__ out) {
+    __shared__ double s[2 * kRmsePartialPairs];      // fetched by the whole block (one pass of coalesced loads), summed by one thread in order
+    for (int i = threadIdx.x; i < 2 * n_pairs; i += blockDim.x) s[i] = partials[i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < n_pairs; ++i) { a = __dadd_rn(a, partials[2 * i]); b = __dadd_rn(b, partials[2 * i + 1]); }
+    for (int i = 0; i < n_pairs; ++i) { a = __dadd_rn(a, s[2 * i]); b = __dadd_rn(b, s[2 * i + 1]); }
     out[0] = a; out[1] = b;
 }
 
@@ -1664,7 +1667,7 @@ cudaError_t launch_rc_rmse(const uint8_t* data, int n, int npix, const double* t
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (grid > kRmsePartialPairs) return cudaErrorInvalidValue;
-    rc_fold_pairs_kernel<<<1, 32, 0, s>>>(partials, grid, acc2);
+    rc_fold_pairs_kernel<<<1, 256, 0, s>>>(partials, grid, acc2);
     return cudaGetLastError();
 }
 
