@@ -57,6 +57,7 @@ constexpr int kTexSlots = 32;       // host-side cache of texture-object sets, k
 
 }  // namespace
 
+constexpr size_t kRcFxOffset = 256 + 256 + 1 + 2 + 2 * kRmsePartialPairs + 1;      // doubles before the fixed-point scratch in d_rc (8-byte units, 16-byte aligned start)
 struct mdc_ctx {
     int device = 0, sm_count = 148;
     int in_w = 0, in_h = 0, out_w = 0, out_h = 0;
@@ -101,7 +102,7 @@ struct mdc_ctx {
     // scratch for the single-op host entry points
     void* scratch_a = nullptr; size_t scratch_a_bytes = 0;
     void* scratch_b = nullptr; size_t scratch_b_bytes = 0;
-    double* d_rc = nullptr;      // responseCalib scratch: gsum[256] gnum[256] factor[1] acc[2] partials[2*kRmsePartialPairs]
+    double* d_rc = nullptr;      // responseCalib scratch: gsum[256] gnum[256] factor[1] acc[2] partials[2*kRmsePartialPairs] | fixed-point G-step accumulators (kRcFxOffset)
     long long launches = 0;
 };
 
@@ -247,7 +248,7 @@ int ctx_common_init(mdc_ctx* c, int device) {
     c->sm_count = v;
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&c->d_counters, kCounterRing * sizeof(int)));
-    CU_CHECK(cudaMalloc(&c->d_rc, (256 + 256 + 1 + 2 + 2 * kRmsePartialPairs) * sizeof(double)));
+    CU_CHECK(cudaMalloc(&c->d_rc, kRcFxOffset * sizeof(double) + kGstepFxScratchBytes));
     const char* e = getenv("MDC_USE_TMA");
     if (e) c->use_tma = atoi(e);
     e = getenv("MDC_CTAS_PER_SM");
@@ -960,8 +961,8 @@ static int rc_gstep_impl(mdc_ctx* c, const uint8_t* d_data, int n, int npix, con
     if (!c || !d_data || !d_t || !d_E || !d_G || n < 0 || npix < 0) { mdc_set_error("mdc_rc_gstep: bad argument"); return MDC_ERR_INVALID_ARG; }
     CU_CHECK(cudaSetDevice(c->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    CU_CHECK(launch_rc_gstep(d_data, n, npix, d_t, d_E, c->d_rc, reinterpret_cast<unsigned long long*>(c->d_rc + 256), d_G, reuse_counts, s));
-    c->launches += 2;
+    CU_CHECK(launch_rc_gstep(d_data, n, npix, d_t, d_E, c->d_rc, reinterpret_cast<unsigned long long*>(c->d_rc + 256), d_G, reuse_counts, c->d_rc + kRcFxOffset, s));
+    c->launches += 4;      // scale, accumulate, convert, finish
     return finish(c, stream, s);
 }
 extern "C" int mdc_rc_gstep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E, double* d_G, mdc_stream stream) {
@@ -983,8 +984,8 @@ extern "C" int mdc_rc_gstep_accumulate(mdc_ctx* c, const uint8_t* d_data, int n,
         mdc_set_error("mdc_rc_gstep_accumulate: reuse_counts needs a 16-byte aligned slice of a multiple of 16 pixels");
         return MDC_ERR_UNSUPPORTED;
     }
-    CU_CHECK(launch_rc_gstep_accum(d_data, n, npix, d_t, d_E, d_gsum256, d_gnum256, reuse_counts != 0, s));
-    c->launches++;
+    CU_CHECK(launch_rc_gstep_accum(d_data, n, npix, d_t, d_E, d_gsum256, d_gnum256, reuse_counts != 0, c->d_rc + kRcFxOffset, s));
+    c->launches += (npix > 0 && n > 0) ? 3 : 1;      // scale, accumulate, convert
     return finish(c, stream, s);
 }
 extern "C" int mdc_rc_gstep_finish(mdc_ctx* c, const double* d_gsum256, const unsigned long long* d_gnum256, double* d_G, mdc_stream stream) {

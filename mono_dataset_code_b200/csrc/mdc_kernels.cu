@@ -1137,17 +1137,22 @@ __global__ void __launch_bounds__(kEstepThreads, 2) estep_kernel(const uint8_t* 
 //
 // The streaming skeleton is shared by the three passes of the calibrator that walk the whole image stack (E-step,
 // G-step, rmse); what happens to a word of 4 samples is the `Op`.
-constexpr int kEbWarps = 14;
-constexpr int kEbThreads = (kEbWarps + 1) * 32;
-constexpr int kEbTile = kEbWarps * 128;          // pixels (= bytes) of one plane per stage row
+constexpr int kEbWarps = 14;                     // consumer warps of the table ops (E-step, rmse: 2 CTAs per SM)
 constexpr int kEbPlanes = 8;                     // exposures per stage
 constexpr int kEbStages = 3;
 constexpr int kEbMaxN = 1024;                    // exposure times served from constant memory up to this n
-constexpr int kEbStageBytes = kEbPlanes * kEbTile;
-constexpr int kEbRegionBytes = kEstepTableBytes; // op-specific region: lookup table (E-step, rmse) or histograms (G-step)
-constexpr int kEbSmemBytes = kEbRegionBytes + kEbStages * kEbStageBytes + 2 * kEbStages * 8;
+// Shape of a streaming kernel, fixed by its Op: Op::kWarps consumer warps (+1 producer warp), a tile of kWarps x 128 pixels,
+// Op::kRegionBytes of shared memory for the op (lookup table / histograms) in front of the ring, Op::kCtasPerSm resident CTAs.
+template <class Op> struct StreamShape {
+    static constexpr int kWarps = Op::kWarps;
+    static constexpr int kThreads = (kWarps + 1) * 32;
+    static constexpr int kTile = kWarps * 128;                       // pixels (= bytes) of one plane per stage row
+    static constexpr int kStageBytes = kEbPlanes * kTile;
+    static constexpr int kRegionBytes = Op::kRegionBytes;
+    static constexpr int kSmemBytes = kRegionBytes + kEbStages * kStageBytes + 2 * kEbStages * 8;
+};
 
-// warps: consumer warps that take part (1..kEbWarps); a tile is warps x 128 pixels (chosen per launch, see launch_stream).
+// warps: consumer warps that take part (1..Op::kWarps); a tile is warps x 128 pixels (chosen per launch, see launch_stream).
 struct StreamArgs { const uint8_t* data; int n; uint32_t npix; const double* t; int warps; };
 
 // Exposure times of the current pass in CONSTANT memory (n <= kEbMaxN): every lane of a warp needs the same t[i], so a shared-memory
@@ -1163,6 +1168,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 __device__ __forceinline__ void stream_consumer_barrier(int warps) { asm volatile("bar.sync 1, %0;" ::"r"(warps * 32) : "memory"); }
 
 // producer lane: streams this CTA's tiles, plane group by plane group, as far ahead as the ring allows
+template <class Shape>
 __device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_tiles, uint32_t stages, uint32_t bar_full, uint32_t bar_empty) {
     const int n_groups = (a.n + kEbPlanes - 1) / kEbPlanes;
     uint32_t s = 0, ph = 0, it = 0;
@@ -1175,9 +1181,9 @@ __device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_t
             if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
             const int planes = a.n - g * kEbPlanes < kEbPlanes ? a.n - g * kEbPlanes : kEbPlanes;
             mbar_expect_tx(bar_full + 8u * s, static_cast<uint32_t>(planes) * bytes);
-            const uint32_t dst = stages + s * static_cast<uint32_t>(kEbStageBytes);
+            const uint32_t dst = stages + s * static_cast<uint32_t>(Shape::kStageBytes);
             for (int p = 0; p < planes; ++p) {
-                bulk_load_1d(dst + static_cast<uint32_t>(p) * kEbTile, src, bytes, bar_full + 8u * s);
+                bulk_load_1d(dst + static_cast<uint32_t>(p) * Shape::kTile, src, bytes, bar_full + 8u * s);
                 src += a.npix;
             }
             if (++s == kEbStages) { s = 0; ph ^= 1u; }
@@ -1197,11 +1203,11 @@ __device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_t
         op.begin_tile(k0, k0 < a.npix);
         for (int g = 0; g < n_groups; ++g) {
             mbar_wait(bar_full + 8u * s, ph);
-            const uint32_t src = mine + s * static_cast<uint32_t>(kEbStageBytes);
+            const uint32_t src = mine + s * static_cast<uint32_t>(StreamShape<Op>::kStageBytes);
             const int i0 = g * kEbPlanes;
             auto plane = [&](int p) {
                 uint32_t v;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + static_cast<uint32_t>(p) * kEbTile));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + static_cast<uint32_t>(p) * StreamShape<Op>::kTile));
                 op.word(v, kTimesInConst ? c_exposure_t[i0 + p] : __ldg(a.t + i0 + p));
             };
             if (i0 + kEbPlanes <= a.n) {
@@ -1218,16 +1224,18 @@ __device__ __forceinline__ void stream_consume(const StreamArgs& a, uint32_t n_t
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
             if (++s == kEbStages) { s = 0; ph ^= 1u; }
+            op.after_group();
         }
         op.end_tile(k0, k0 < a.npix);
     }
 }
 
 template <class Op>
-__global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, typename Op::Params prm) {
+__global__ void __launch_bounds__(StreamShape<Op>::kThreads, Op::kCtasPerSm) rc_stream_kernel(StreamArgs a, typename Op::Params prm) {
+    using Shape = StreamShape<Op>;
     extern __shared__ __align__(128) uint8_t smem_b[];
-    const uint32_t stages = smem_u32(smem_b + kEbRegionBytes);                        // [kEbStages][kEbPlanes][kEbTile]
-    const uint32_t bar_full = stages + kEbStages * kEbStageBytes, bar_empty = bar_full + 8u * kEbStages;
+    const uint32_t stages = smem_u32(smem_b + Shape::kRegionBytes);                   // [kEbStages][kEbPlanes][kTile]
+    const uint32_t bar_full = stages + kEbStages * Shape::kStageBytes, bar_empty = bar_full + 8u * kEbStages;
     const bool times_in_const = a.n <= kEbMaxN;                                        // launch_stream filled c_exposure_t
     if (threadIdx.x == 0) {
         for (int i = 0; i < kEbStages; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, static_cast<uint32_t>(a.warps)); }
@@ -1237,9 +1245,9 @@ __global__ void __launch_bounds__(kEbThreads, 2) rc_stream_kernel(StreamArgs a, 
     __syncthreads();
     const uint32_t tile_px = static_cast<uint32_t>(a.warps) * 128u;
     const uint32_t n_tiles = (a.npix + tile_px - 1) / tile_px;
-    if ((threadIdx.x >> 5) >= a.warps && (threadIdx.x >> 5) != kEbWarps) return;      // consumer warps beyond the tile width sit this launch out
-    if ((threadIdx.x >> 5) == kEbWarps) {
-        if ((threadIdx.x & 31) == 0) stream_produce(a, n_tiles, stages, bar_full, bar_empty);
+    if ((threadIdx.x >> 5) >= a.warps && (threadIdx.x >> 5) != Shape::kWarps) return;  // consumer warps beyond the tile width sit this launch out
+    if ((threadIdx.x >> 5) == Shape::kWarps) {
+        if ((threadIdx.x & 31) == 0) stream_produce<Shape>(a, n_tiles, stages, bar_full, bar_empty);
         return;
     }
     Op op(smem_b, prm);
@@ -1259,6 +1267,7 @@ __device__ __forceinline__ void fill_lane_table(uint8_t* region, const double* _
 struct EstepOp {
     struct Params { const double* G; double* E; };
     static constexpr bool kUnroll = true;
+    static constexpr int kWarps = kEbWarps, kRegionBytes = kEstepTableBytes, kCtasPerSm = 2;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
     uint32_t table, lane8;
     int warps = kEbWarps;         // active consumer warps of this launch (set by the kernel)
@@ -1279,63 +1288,188 @@ struct EstepOp {
             E[k0 + j] = e;
         }
     }
+    __device__ __forceinline__ void after_group() {}
     __device__ __forceinline__ void epilogue(uint8_t*, const Params&) {}
 };
 
-// G-step accumulation (main_responseCalib.cpp:290-299): GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.  The CTA keeps one
-// histogram in shared memory, laid out like the lookup table: one 256-byte row per value = 16 fp64 sum slots (slot =
-// lane & 15, so the two half-warps of a 64-bit access each touch 16 different bank pairs) followed by 32 u32 count slots
-// (slot = lane).  Shared-memory atomics are therefore bank-conflict-free and only collide when two threads hit the same
-// (value, slot) at the same moment; one PRMT builds each address.  The slots are folded in a fixed order at the end and
-// flushed with one global atomic per bin per CTA.  kCount = false: the caller already holds GNum (it depends on the images only,
-// so the optimisation loop computes it once).
+// ---- G-step sums in fixed point.  GSum[b] (main_responseCalib.cpp:295) is one sequential fp64 chain over 10^9 samples in the
+// reference; no parallel order reproduces its roundings, and fp64 atomics make the result depend on the order in which threads
+// happen to arrive.  So every product E[k]*t[i] — rounded to fp64 exactly as the reference rounds it — is turned into an integer
+// multiple of 2^-s and summed in integer arithmetic, which is associative: the bits of G do not depend on the launch
+// geometry, on the timing of the atomics or on how often the pass is repeated.  s is chosen from the data (GstepScale: the
+// largest finite |E| and |t| of the pass) such that every product is below 2^48 units; the conversion is one DADD with
+// 1.5 * 2^52 (round to nearest even), so a sample is off by at most 2^-48 of the largest product — the sum of 4 * 10^6 samples
+// of a bin is closer to the exact sum than the reference's own chain is.  Non-finite products (E = NaN of an all-saturated
+// pixel meeting t = 0 ...) go to a separate fp64 accumulator so that they poison G as they do in the reference.
+//
+// Integer sums are also what makes the histogram cheap: shared memory has native 32-bit integer atomics (ATOMS.ADD, one
+// wavefront per conflict-free warp instruction) but only a compare-and-swap loop for 64-bit ones (LDS.64 + ATOMS.CAS.64, ~10
+// clocks per warp update against 3.2 for three ATOMS.ADD: scripts/probes/smem_atomic_probe.cu, profiles/r02_smem_atomic_probe.txt).
+// A sample is therefore split into three limbs — bits 0-15, bits 16-31 and the signed rest, which are one LOP, one SHF and one
+// IADD away from the two words of the DADD's result — that are added to three u32 histograms, and the histograms are folded
+// into 64-bit totals long before a limb can overflow.
+constexpr double kFxMagic = 6755399441055744.0;      // 1.5 * 2^52
+constexpr double kFxLimit = 281474976710656.0;       // 2^48: scaled products stay below it
+struct GstepScale { unsigned long long max_e_bits, max_t_bits; unsigned bad_t; };      // bit patterns of max finite |E[k]|, |t[i]| (non-negative doubles order like integers); bad_t: a non-finite exposure time exists
+
+// power of two 2^s with |E*t| * 2^s < 2^48 for all finite samples; kFxNoScale if no such bound exists (the largest product overflows
+// or an exposure time is not finite): every sample is then range-checked on its own
+constexpr int kFxNoScale = -100000;
+__device__ __forceinline__ int gstep_scale_exponent(const GstepScale& sc) {
+    const double p = __dmul_rn(__longlong_as_double(static_cast<long long>(sc.max_e_bits)), __longlong_as_double(static_cast<long long>(sc.max_t_bits)));
+    if (!isfinite(p) || sc.bad_t) return kFxNoScale;
+    if (!(p > 0.0)) return 0;
+    int s = 48 - (ilogb(p) + 1);
+    return s < -1000 ? -1000 : (s > 1000 ? 1000 : s);
+}
+// x (|x| < 2^48, already scaled) -> the integer nearest to it, as three limbs: value = l0 + l1 * 2^16 + l2 * 2^32, 0 <= l0, l1 < 2^16,
+// -2^16 <= l2 < 2^16.  bits(x + 1.5 * 2^52) = 0x4338000000000000 + value, so the limbs are bit fields of the sum.
+struct FxLimbs { uint32_t l0, l1; int l2; };
+__device__ __forceinline__ FxLimbs fx_limbs(double x) {
+    const double y = __dadd_rn(x, kFxMagic);
+    const uint32_t lo = static_cast<uint32_t>(__double2loint(y));
+    FxLimbs r;
+    r.l0 = lo & 0xffffu;
+    r.l1 = lo >> 16;
+    r.l2 = __double2hiint(y) - 0x43380000;
+    return r;
+}
+__device__ __forceinline__ bool fx_in_range(double x) { return fabs(x) < kFxLimit; }      // false for NaN
+// 128-bit two's complement accumulators in global memory: {lo, hi} += {lo_part, hi_part} (order-independent: modular arithmetic)
+__device__ __forceinline__ void fx_flush(unsigned long long* g_lo, unsigned long long* g_hi, unsigned long long lo_part, long long hi_part) {
+    const unsigned long long old = atomicAdd(g_lo, lo_part);
+    const unsigned long long carry = old + lo_part < old ? 1ull : 0ull;
+    const unsigned long long h = static_cast<unsigned long long>(hi_part) + carry;
+    if (h) atomicAdd(g_hi, h);
+}
+__device__ __forceinline__ void fx_flush_limb_totals(unsigned long long* g_lo, unsigned long long* g_hi, long long t0, long long t1, long long t2) {
+    const __int128 v = static_cast<__int128>(t0) + (static_cast<__int128>(t1) << 16) + (static_cast<__int128>(t2) << 32);
+    const unsigned long long lo = static_cast<unsigned long long>(v);
+    const long long hi = static_cast<long long>(v >> 64);
+    if (lo | static_cast<unsigned long long>(hi)) fx_flush(g_lo, g_hi, lo, hi);
+}
+// device scratch of one G-step pass (all zeroed by launch_rc_gstep_accum before the pass)
+struct GstepFx {
+    GstepScale* scale;
+    unsigned long long* lo;      // [256]
+    unsigned long long* hi;      // [256]
+    double* special;             // [256] fp64 sums of the samples fixed point cannot hold
+};
+
+// G-step accumulation (main_responseCalib.cpp:290-299): GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.  One CTA per SM with 28
+// consumer warps keeps the histograms in shared memory as planes of [256 values][32 slots] u32 (slot = lane, 128 bytes per value:
+// every warp-wide ATOMS.ADD is bank-conflict-free, and two threads only collide when the same lane of two warps meets the same
+// value at the same moment): three limb planes and, in the first pass, a count plane (kCount = false: the caller already holds
+// GNum — it depends on the images only, so the optimisation loop computes it once).  One PRMT + one LEA build each address.
+// A slot receives at most 4 x 28 adds per exposure, i.e. a limb could overflow after 2^15 / 112 = 292 exposures; every 160
+// exposures each warp therefore folds its share of the (plane, value) rows into 64-bit totals: it reads a slot, subtracts what it
+// read with another ATOMS.ADD — which commutes with the adds of the other warps, so no barrier is needed — and sums the 32 slots
+// with REDUX.  The ring lets warps drift apart by at most 24 exposures, so a slot sees at most 4 x 28 x (160 + 48) = 23 296 adds
+// between folds.  At the end the three totals of a bin are combined into one 128-bit number and added to the global accumulators.
+constexpr int kGstepWarps = 28;
+constexpr int kGstepPlaneBytes = 256 * 128;
+constexpr int kGstepDrainGroups = 20;      // plane groups (of kEbPlanes exposures) between two folds
 template <bool kCount>
 struct GstepOp {
-    struct Params { const double* E; double* gsum; unsigned long long* gnum; };
-    static constexpr bool kUnroll = false;
+    struct Params { const double* E; GstepFx fx; unsigned long long* gnum; };
+    static constexpr bool kUnroll = true;
+    static constexpr int kPlanes = kCount ? 4 : 3;
+    static constexpr int kWarps = kGstepWarps, kCtasPerSm = 1;
+    static constexpr int kRegionBytes = kPlanes * (kGstepPlaneBytes + 256 * 8);      // the planes, then long long totals[kPlanes][256]
+    static_assert(4 * kGstepWarps * (kGstepDrainGroups * kEbPlanes + 2 * kEbStages * kEbPlanes) < (1 << 15), "a limb slot could overflow between two folds");
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params&) {
         uint32_t* z = reinterpret_cast<uint32_t*>(region);
-        for (int i = threadIdx.x; i < kEbRegionBytes / 4; i += blockDim.x) z[i] = 0u;
+        for (int i = threadIdx.x; i < kRegionBytes / 4; i += blockDim.x) z[i] = 0u;
     }
     uint8_t* hist;
-    int warps = kEbWarps;             // active consumer warps of this launch (set by the kernel)
-    uint32_t lane_sum, lane_cnt;      // byte offsets of this lane's slots inside a row
+    int warps = kWarps;               // active consumer warps of this launch (set by the kernel)
+    uint32_t lane8;
+    int groups_since_fold;
     const double* E;
+    double* special;
+    double scale;                     // 2^s
     double e[4];
-    bool active;
+    uint32_t mode;                    // 0: fast path; 1: every sample range-checked (a non-finite E among this lane's pixels, or no usable scale); 2: no pixels
+    bool no_scale;
     __device__ __forceinline__ GstepOp(uint8_t* region, const Params& p)
-        : hist(region), lane_sum((threadIdx.x & 15) * 8u), lane_cnt(128u + (threadIdx.x & 31) * 4u), E(p.E), active(false) {}
-    __device__ __forceinline__ void begin_tile(size_t k0, bool act) {
-        active = act;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) e[j] = act ? E[k0 + j] : 0.0;
+        : hist(region), lane8((threadIdx.x & 31) * 8u), groups_since_fold(0), E(p.E), special(p.fx.special), mode(2u) {
+        const int s = gstep_scale_exponent(*p.fx.scale);
+        no_scale = s == kFxNoScale;
+        scale = no_scale ? 1.0 : scalbn(1.0, s);
     }
-    __device__ __forceinline__ void sample(uint32_t a_sum, uint32_t a_cnt, double ek, double ti) {
-        if (a_sum >= 0xff00u) return;      // saturated, :293
-        atomicAdd(reinterpret_cast<double*>(hist + a_sum), __dmul_rn(ek, ti));
-        if (kCount) atomicAdd(reinterpret_cast<unsigned*>(hist + a_cnt), 1u);
+    __device__ __forceinline__ void begin_tile(size_t k0, bool act) {
+        mode = !act ? 2u : (no_scale ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double ek = act ? E[k0 + j] : 0.0;
+            if (!isfinite(ek)) mode |= 1u;
+            e[j] = __dmul_rn(ek, scale);      // exact: (E * 2^s) * t == (E * t) * 2^s
+        }
+    }
+    // a: (value << 8) | lane * 8, i.e. twice the byte offset of this lane's slot in a plane.  Saturated samples (:293) are not skipped:
+    // they land in the rows of value 255, which nobody reads — cheaper than a predicate or a branch around the atomics.
+    __device__ __forceinline__ void add(uint32_t a, const FxLimbs& v) {
+        uint8_t* p = hist + (a >> 1);
+        atomicAdd(reinterpret_cast<unsigned*>(p), v.l0);
+        atomicAdd(reinterpret_cast<unsigned*>(p + kGstepPlaneBytes), v.l1);
+        atomicAdd(reinterpret_cast<int*>(p + 2 * kGstepPlaneBytes), v.l2);
+        if (kCount) atomicAdd(reinterpret_cast<unsigned*>(p + 3 * kGstepPlaneBytes), 1u);
+    }
+    __device__ __noinline__ void word_checked(uint32_t v, double ti) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t a = ((v >> (8 * j)) & 0xffu) << 8 | lane8;
+            if (a >= 0xff00u) continue;      // saturated, :293
+            const double x = __dmul_rn(e[j], ti);
+            if (fx_in_range(x)) {
+                add(a, fx_limbs(x));
+            } else {
+                atomicAdd(special + (a >> 8), __ddiv_rn(x, scale));
+                if (kCount) atomicAdd(reinterpret_cast<unsigned*>(hist + (a >> 1) + 3 * kGstepPlaneBytes), 1u);
+            }
+        }
     }
     __device__ __forceinline__ void word(uint32_t v, double ti) {
-        if (!active) return;
-        sample(__byte_perm(v, lane_sum, 0x5504), __byte_perm(v, lane_cnt, 0x5504), e[0], ti);
-        sample(__byte_perm(v, lane_sum, 0x5514), __byte_perm(v, lane_cnt, 0x5514), e[1], ti);
-        sample(__byte_perm(v, lane_sum, 0x5524), __byte_perm(v, lane_cnt, 0x5524), e[2], ti);
-        sample(__byte_perm(v, lane_sum, 0x5534), __byte_perm(v, lane_cnt, 0x5534), e[3], ti);
+        if (mode) {
+            if (mode == 1u) word_checked(v, ti);
+            return;
+        }
+        add(__byte_perm(v, lane8, 0x5504), fx_limbs(__dmul_rn(e[0], ti)));
+        add(__byte_perm(v, lane8, 0x5514), fx_limbs(__dmul_rn(e[1], ti)));
+        add(__byte_perm(v, lane8, 0x5524), fx_limbs(__dmul_rn(e[2], ti)));
+        add(__byte_perm(v, lane8, 0x5534), fx_limbs(__dmul_rn(e[3], ti)));
+    }
+    // this warp's share of the (plane, value) rows -> totals; safe while other warps keep adding (see above)
+    __device__ __forceinline__ void fold() {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        long long* totals = reinterpret_cast<long long*>(hist + kPlanes * kGstepPlaneBytes);
+#pragma unroll 2
+        for (int r = warp; r < kPlanes * 256; r += warps) {
+            unsigned* slot = reinterpret_cast<unsigned*>(hist + r * 128) + lane;
+            const unsigned cur = *reinterpret_cast<volatile unsigned*>(slot);
+            if (cur) atomicAdd(slot, 0u - cur);
+            long long sum;
+            if ((r >> 8) == 2) {            // the signed limb
+                const int c = static_cast<int>(cur);
+                sum = static_cast<long long>(__reduce_add_sync(0xffffffffu, c & 0xffff)) + (static_cast<long long>(__reduce_add_sync(0xffffffffu, c >> 16)) << 16);
+            } else {
+                sum = static_cast<long long>(__reduce_add_sync(0xffffffffu, cur & 0xffffu)) + (static_cast<long long>(__reduce_add_sync(0xffffffffu, cur >> 16)) << 16);
+            }
+            if (lane == 0 && sum) totals[r] += sum;
+        }
+    }
+    __device__ __forceinline__ void after_group() {
+        if (++groups_since_fold == kGstepDrainGroups) { groups_since_fold = 0; fold(); }
     }
     __device__ __forceinline__ void end_tile(size_t, bool) {}
     __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
+        stream_consumer_barrier(warps);      // all adds of all warps are in
+        fold();
         stream_consumer_barrier(warps);
+        const long long* totals = reinterpret_cast<const long long*>(region + kPlanes * kGstepPlaneBytes);
         for (int b = threadIdx.x; b < 255; b += warps * 32) {
-            const double* hs = reinterpret_cast<const double*>(region + b * 256);
-            const unsigned* hc = reinterpret_cast<const unsigned*>(region + b * 256 + 128);
-            double sum = 0.0;
-            unsigned long long cnt = 0ull;
-            for (int q = 0; q < 16; ++q) sum = __dadd_rn(sum, hs[q]);
-            atomicAdd(p.gsum + b, sum);
-            if (kCount) {
-                for (int q = 0; q < 32; ++q) cnt += hc[q];
-                if (cnt) atomicAdd(p.gnum + b, cnt);
-            }
+            fx_flush_limb_totals(p.fx.lo + b, p.fx.hi + b, totals[b], totals[256 + b], totals[512 + b]);
+            if (kCount && totals[768 + b]) atomicAdd(p.gnum + b, static_cast<unsigned long long>(totals[768 + b]));
         }
     }
 };
@@ -1344,6 +1478,7 @@ struct GstepOp {
 struct RmseOp {
     struct Params { const double* G; const double* E; double* partials; };      // partials[2*cta] = {error, count} of one CTA
     static constexpr bool kUnroll = true;
+    static constexpr int kWarps = kEbWarps, kRegionBytes = kEstepTableBytes, kCtasPerSm = 2;
     static __device__ __forceinline__ void prologue(uint8_t* region, const Params& p) { fill_lane_table(region, p.G); }
     uint32_t table, lane8;
     int warps = kEbWarps;             // active consumer warps of this launch (set by the kernel)
@@ -1377,6 +1512,7 @@ struct RmseOp {
         sample(__byte_perm(v, lane8, 0x5524), e[2], ti);
         sample(__byte_perm(v, lane8, 0x5534), e[3], ti);
     }
+    __device__ __forceinline__ void after_group() {}
     __device__ __forceinline__ void end_tile(size_t, bool) { cnt_total += cnt; cnt = 0u; }
     __device__ __forceinline__ void epilogue(uint8_t* region, const Params& p) {
         double c = static_cast<double>(cnt_total);
@@ -1403,28 +1539,31 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
     int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(rc_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEbSmemBytes);
+    using Shape = StreamShape<Op>;
+    constexpr int kW = Shape::kWarps;
+    cudaError_t e = cudaFuncSetAttribute(rc_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::kSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rc_stream_kernel<Op>, kEbThreads, kEbSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rc_stream_kernel<Op>, Shape::kThreads, Shape::kSmemBytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     // Tile width (consumer warps per CTA).  A CTA works through its tiles one after the other; measured per-tile time grows like
-    // (2.6 + warps) (profiles/r02_k3_stream_tile_width_sweep.jsonl), so the width that minimises rounds x (2.6 + warps) fills the
-    // persistent CTAs best: 14 warps = 2 rounds at 1 MP (12 warps: 3 uneven rounds).  Only widths 10..14 are candidates — narrower
-    // tiles lose more to the thinner ring than they gain in balance — and an image with fewer full-width tiles than CTAs keeps 14.
+    // (2.6 + warps) for the 14-warp ops (profiles/r02_k3_stream_tile_width_sweep.jsonl), so the width that minimises
+    // rounds x (2.6 + warps) fills the persistent CTAs best: 14 warps = 2 rounds at 1 MP (12 warps: 3 uneven rounds).  Only the
+    // upper third of the widths are candidates — narrower tiles lose more to the thinner ring than they gain in balance — and an
+    // image with fewer full-width tiles than CTAs keeps the full width.
     const long long slots = static_cast<long long>(sms) * per_sm;
-    int best_w = kEbWarps;
-    if ((static_cast<long long>(a.npix) + kEbWarps * 128 - 1) / (kEbWarps * 128) > slots) {
+    int best_w = kW;
+    if ((static_cast<long long>(a.npix) + kW * 128 - 1) / (kW * 128) > slots) {
         double best_cost = -1.0;
-        for (int w = kEbWarps; w >= 10; --w) {
+        for (int w = kW; w >= kW - kW * 2 / 7; --w) {
             const long long tiles_w = (static_cast<long long>(a.npix) + w * 128 - 1) / (w * 128);
-            const double cost = static_cast<double>((tiles_w + slots - 1) / slots) * (2.6 + w);
+            const double cost = static_cast<double>((tiles_w + slots - 1) / slots) * (2.6 * kW / 14.0 + w);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
         }
     }
     if (const char* ov = getenv("MDC_STREAM_WARPS")) {      // measurement knob
         const int w = atoi(ov);
-        if (w >= 1 && w <= kEbWarps) best_w = w;
+        if (w >= 1 && w <= kW) best_w = w;
     }
     StreamArgs args = a;
     args.warps = best_w;
@@ -1440,7 +1579,7 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
         else if ((e = cudaStreamWaitEvent(stream, last_reader[dev], 0)) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbolAsync(c_exposure_t, a.t, static_cast<size_t>(a.n) * sizeof(double), 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
     }
-    rc_stream_kernel<Op><<<static_cast<unsigned>(grid), kEbThreads, kEbSmemBytes, stream>>>(args, prm);
+    rc_stream_kernel<Op><<<static_cast<unsigned>(grid), Shape::kThreads, Shape::kSmemBytes, stream>>>(args, prm);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return use_const ? cudaEventRecord(last_reader[dev], stream) : cudaSuccess;
 }
@@ -1508,27 +1647,73 @@ __global__ void __launch_bounds__(256) rc_einit_kernel(const uint8_t* __restrict
     E[k] = __ddiv_rn(s, c);
 }
 
-// G-step accumulation, main_responseCalib.cpp:290-299: GSum[b] += E[k]*t[i], GNum[b]++ for b != 255.
-// Per-CTA shared-memory histograms (fp64 atomics), flushed with one global atomic per bin per CTA.
-__global__ void __launch_bounds__(256) rc_gstep_accum_kernel(const uint8_t* __restrict__ data, int n, size_t npix, const double* __restrict__ t,
-                                                             const double* __restrict__ E, double* __restrict__ gsum, unsigned long long* __restrict__ gnum) {
-    __shared__ double s_sum[256];
-    __shared__ unsigned long long s_num[256];
-    s_sum[threadIdx.x] = 0.0; s_num[threadIdx.x] = 0ull;
-    __syncthreads();
+// largest finite |E[k]| and |t[i]| of a pass (bit patterns, see GstepScale); scale must be zeroed before the launch
+__global__ void __launch_bounds__(256) rc_gstep_scale_kernel(const double* __restrict__ E, size_t npix, const double* __restrict__ t, int n, GstepScale* __restrict__ scale) {
+    unsigned long long me = 0ull, mt = 0ull;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npix; k += stride) {
-        const double e = E[k];
+        const unsigned long long v = static_cast<unsigned long long>(__double_as_longlong(E[k])) & 0x7fffffffffffffffull;
+        if (v < 0x7ff0000000000000ull && v > me) me = v;
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long v = static_cast<unsigned long long>(__double_as_longlong(t[i])) & 0x7fffffffffffffffull;
+            if (v >= 0x7ff0000000000000ull) scale->bad_t = 1u;
+            else if (v > mt) mt = v;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long oe = __shfl_xor_sync(0xffffffffu, me, o), ot = __shfl_xor_sync(0xffffffffu, mt, o);
+        me = oe > me ? oe : me;
+        mt = ot > mt ? ot : mt;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (me) atomicMax(&scale->max_e_bits, me);
+        if (mt) atomicMax(&scale->max_t_bits, mt);
+    }
+}
+
+// G-step accumulation for image sizes the streaming kernels do not take, main_responseCalib.cpp:290-299: GSum[b] += E[k]*t[i],
+// GNum[b]++ for b != 255.  Per-CTA shared-memory sums in the same fixed-point form (here one 64-bit word + a carry word per bin,
+// updated with the compare-and-swap atomics: this kernel is the fallback, not the fast path), one 128-bit global add per bin per CTA.
+__global__ void __launch_bounds__(256) rc_gstep_accum_kernel(const uint8_t* __restrict__ data, int n, size_t npix, const double* __restrict__ t,
+                                                             const double* __restrict__ E, GstepFx fx, unsigned long long* __restrict__ gnum) {
+    __shared__ unsigned long long s_lo[256], s_num[256];
+    __shared__ int s_hi[256];
+    s_lo[threadIdx.x] = 0ull; s_hi[threadIdx.x] = 0; s_num[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int se = gstep_scale_exponent(*fx.scale);
+    const double scale = se == kFxNoScale ? 1.0 : scalbn(1.0, se);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npix; k += stride) {
+        const double e = __dmul_rn(E[k], scale);
         for (int i = 0; i < n; ++i) {
             const unsigned b = data[static_cast<size_t>(i) * npix + k];
             if (b == 255u) continue;
-            atomicAdd(&s_sum[b], __dmul_rn(e, __ldg(t + i)));
             atomicAdd(&s_num[b], 1ull);
+            const double x = __dmul_rn(e, __ldg(t + i));
+            if (!fx_in_range(x)) { atomicAdd(fx.special + b, __ddiv_rn(x, scale)); continue; }
+            const long long v = __double_as_longlong(__dadd_rn(x, kFxMagic)) - __double_as_longlong(kFxMagic);
+            const unsigned long long uv = static_cast<unsigned long long>(v);
+            const unsigned long long old = atomicAdd(&s_lo[b], uv);
+            const int delta = static_cast<int>(old + uv < old) - static_cast<int>(v < 0);      // carry out of the low word, sign extension of v
+            if (delta) atomicAdd(&s_hi[b], delta);
         }
     }
     __syncthreads();
-    atomicAdd(&gsum[threadIdx.x], s_sum[threadIdx.x]);
+    if (s_lo[threadIdx.x] | static_cast<unsigned long long>(static_cast<long long>(s_hi[threadIdx.x])))
+        fx_flush(fx.lo + threadIdx.x, fx.hi + threadIdx.x, s_lo[threadIdx.x], s_hi[threadIdx.x]);
     atomicAdd(&gnum[threadIdx.x], s_num[threadIdx.x]);
+}
+
+// gsum[b] = (hi * 2^64 + lo) * 2^-s + special[b]: the 128-bit sums back in fp64 (two roundings at most, the same on every run)
+__global__ void __launch_bounds__(256) rc_gstep_convert_kernel(GstepFx fx, double* __restrict__ gsum) {
+    const int b = threadIdx.x;
+    int s = gstep_scale_exponent(*fx.scale);
+    if (s == kFxNoScale) s = 0;
+    const double hi = __dmul_rn(static_cast<double>(static_cast<long long>(fx.hi[b])), 18446744073709551616.0);
+    const double v = __dadd_rn(hi, static_cast<double>(fx.lo[b]));
+    gsum[b] = __dadd_rn(scalbn(v, -s), fx.special[b]);
 }
 
 // G[i] = GSum[i]/GNum[i]; non-finite entries (empty bins) with i > 1 are extrapolated linearly from the two entries below, :300-304.
@@ -1617,22 +1802,35 @@ cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cud
 //               caller's gnum (which depends on the images only) is kept and only the sums are rebuilt
 //   finish      G = gsum/gnum + sequential gap extrapolation (:300-304)
 cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
-                                  bool reuse_counts, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(gsum, 0, 256 * sizeof(double), s);
+                                  bool reuse_counts, void* fx_scratch, cudaStream_t s) {
+    // fx_scratch (kGstepFxScratchBytes): scale | lo[256] | hi[256] | special[256]
+    cudaError_t e = cudaMemsetAsync(fx_scratch, 0, kGstepFxScratchBytes, s);
     if (e != cudaSuccess) return e;
+    GstepFx fx;
+    fx.scale = static_cast<GstepScale*>(fx_scratch);
+    fx.lo = reinterpret_cast<unsigned long long*>(static_cast<char*>(fx_scratch) + 64);
+    fx.hi = fx.lo + 256;
+    fx.special = reinterpret_cast<double*>(fx.hi + 256);
     const bool stream = stream_ok(data, npix);
     if (!reuse_counts) {
         e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
         if (e != cudaSuccess) return e;
     }
-    if (npix <= 0 || n <= 0) return cudaSuccess;
-    if (stream) {
-        const StreamArgs a{data, n, static_cast<uint32_t>(npix), t, kEbWarps};
-        return reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, gsum, gnum}, s)
-                            : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, gsum, gnum}, s);
+    if (npix > 0 && n > 0) {
+        if (reuse_counts && !stream) return cudaErrorNotSupported;      // the generic kernel always counts (callers check rc_counts_reusable first)
+        rc_gstep_scale_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(E, static_cast<size_t>(npix), t, n, fx.scale);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (stream) {
+            const StreamArgs a{data, n, static_cast<uint32_t>(npix), t, kEbWarps};
+            e = reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, fx, gnum}, s)
+                             : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, fx, gnum}, s);
+            if (e != cudaSuccess) return e;
+        } else {
+            rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, fx, gnum);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
     }
-    if (reuse_counts) return cudaErrorNotSupported;      // the generic kernel always counts (callers check rc_counts_reusable first)
-    rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, gsum, gnum);
+    rc_gstep_convert_kernel<<<1, 256, 0, s>>>(fx, gsum);
     return cudaGetLastError();
 }
 cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s) {
@@ -1642,8 +1840,8 @@ cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long*
 bool rc_counts_reusable(const uint8_t* data, int npix) { return stream_ok(data, npix); }
 
 cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum, double* G,
-                            bool reuse_counts, cudaStream_t s) {
-    cudaError_t e = launch_rc_gstep_accum(data, n, npix, t, E, gsum, gnum, reuse_counts && rc_counts_reusable(data, npix), s);
+                            bool reuse_counts, void* fx_scratch, cudaStream_t s) {
+    cudaError_t e = launch_rc_gstep_accum(data, n, npix, t, E, gsum, gnum, reuse_counts && rc_counts_reusable(data, npix), fx_scratch, s);
     if (e != cudaSuccess) return e;
     return launch_rc_gstep_finish(gsum, gnum, G, s);
 }

@@ -96,10 +96,12 @@ cudaError_t launch_estep(const uint8_t* data, int n, int npix, const double* t, 
 
 cudaError_t launch_rc_leak_padding(const uint8_t* in, uint8_t* out, int n, int w, int h, cudaStream_t s);
 cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cudaStream_t s);
+// fx_scratch: kGstepFxScratchBytes of device memory for the fixed-point accumulators of one pass (zeroed by the call)
+constexpr size_t kGstepFxScratchBytes = 64 + 3 * 256 * 8;
 cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
-                            double* G, bool reuse_counts, cudaStream_t s);
+                            double* G, bool reuse_counts, void* fx_scratch, cudaStream_t s);
 cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
-                                  bool reuse_counts, cudaStream_t s);
+                                  bool reuse_counts, void* fx_scratch, cudaStream_t s);
 cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s);
 bool rc_counts_reusable(const uint8_t* data, int npix);      // reuse_counts is only available on the bulk-copy streaming path
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s);

@@ -422,6 +422,55 @@ def test_response_calib_building_blocks(api, port, w, h):
     assert_bits_equal(Gc.cpu().numpy(), G2, "rescaled G")
 
 
+@pytest.mark.parametrize("npix", [96 * 64, 50 * 30 + 7], ids=["bulk_loader", "generic_kernel"])
+def test_gstep_sums_are_exact_and_repeatable(api, port, npix):
+    """The G-step sums E[k]*t[i] in 128-bit fixed point: the bits of G must not depend on the run, on the tile
+    width of the launch or on the order of the atomics, and each bin must be the correctly rounded EXACT sum of the fp64 products
+    (math.fsum) to well inside the distance between the reference's own sequential chain and that exact sum."""
+    import math
+    rng = np.random.default_rng(5)
+    n = 37
+    data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+    data[:, 11:40] = 255
+    data[:, 200:260] = 7                                   # one crowded bin: thousands of colliding atomics
+    t = rng.uniform(0.05, 20.0, n)
+    t[3] = -1.25                                           # the arithmetic has no sign assumption
+    E = np.exp(rng.uniform(-12.0, 6.0, npix))              # 8 decades of irradiance
+    ctx = api.Context(None, None, 0)
+    d, dt, dE = torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(E).cuda()
+    runs = []
+    for warps in ("", "10", "14", "3", ""):
+        if warps:
+            os.environ["MDC_STREAM_WARPS"] = warps
+        else:
+            os.environ.pop("MDC_STREAM_WARPS", None)
+        G = torch.zeros(256, dtype=torch.float64, device="cuda")
+        ctx.rc_gstep(d, dt, dE, G)
+        runs.append(G.cpu().numpy())
+    os.environ.pop("MDC_STREAM_WARPS", None)
+    for r in runs[1:]:
+        assert_bits_equal(r, runs[0], "G-step, repeated / other tile widths")
+    prod = E[None, :] * t[:, None]                         # fp64 products, rounded like the reference rounds them
+    G_ref = port.gstep(data, t, E)
+    pmax = np.abs(E).max() * np.abs(t).max()
+    worst = 0.0
+    for b in range(255):
+        m = data == b
+        cnt = int(m.sum())
+        if cnt == 0:
+            continue
+        exact = math.fsum(prod[m].tolist()) / cnt
+        # every sample is rounded to a multiple of 2^-s <= 2^-47 * pmax, so a bin's MEAN is off by at most 2^-48 * pmax = 3.6e-15 * pmax (+ the final roundings)
+        assert abs(runs[0][b] - exact) <= 4e-15 * pmax + 1e-15 * abs(exact), b
+        worst = max(worst, abs(G_ref[b] - exact) / abs(exact))
+    assert worst < 1e-10                                   # the oracle's sequential chain, for scale
+    # a NaN irradiance poisons exactly the bins its pixel has samples in, as in the reference
+    E2 = E.copy(); E2[500] = np.nan
+    G = torch.zeros(256, dtype=torch.float64, device="cuda")
+    ctx.rc_gstep(d, dt, torch.from_numpy(E2).cuda(), G)
+    assert np.array_equal(np.isnan(G.cpu().numpy()), np.isnan(port.gstep(data, t, E2)))
+
+
 def test_response_calib_loop(api, port):
     """mdc_response_calib = E-init + nits x {G-step, E-step, rescale} against the same loop composed from the oracle."""
     rng = np.random.default_rng(22)
