@@ -6,9 +6,13 @@
 //
 //   plane step (:400-446)     one thread per plane point, sequential over the images  ->  FF/FC accumulate in the reference's
 //                             order, planeColor = FC/FF is BIT-IDENTICAL; E is a sum over 10^9 doubles (order-dependent).
-//   vignette step (:458-533)  one thread per (image, plane point): bilinear scatter-add of 8 float terms into TT/CT with
-//                             global fp32 atomics.  The reference adds them in (image, point) order; any parallel order
-//                             differs in the last bits (compared to 1e-5 relative).  Then CT/TT, the maximum, the division.
+//   vignette step (:458-533)  one thread per (image, plane point): bilinear scatter-add of 8 float terms into TT/CT.  The
+//                             reference adds them in (image, point) order in fp32; no parallel order reproduces that chain,
+//                             and fp32 atomics would make the result depend on thread timing.  The terms (each rounded
+//                             exactly as the reference rounds it) are therefore added as 64-bit fixed-point integers:
+//                             the sums are exact, so they are the same bits on every run, and they differ from the
+//                             reference's chain only by the rounding error of that chain (compared to 2e-5 relative).
+//                             Then CT/TT, the maximum, the division.
 //   smoothing (:542-566)      NaN-aware 3x3 mean, ping-pong buffers, bit-identical.
 //
 // All float arithmetic is spelled out with round-to-nearest intrinsics in the reference's evaluation order (no FMA).
@@ -56,8 +60,10 @@ __device__ __forceinline__ float vc_blend(const float* __restrict__ mat, const T
     return __fadd_rn(r, __fmul_rn(t.w00, __ldg(bp)));
 }
 
-// CTA-wide reduction of (E, R) partials -> two global atomics per CTA
-__device__ __forceinline__ void vc_flush_stats(double e, double r, double* __restrict__ stats) {
+// CTA-wide reduction of (E, R) partials -> one pair per CTA in partials[]; vc_fold_stats_kernel adds the pairs in CTA order, so
+// the statistics are the same bits on every run
+constexpr int kVcMaxBlocks = 148 * 32;
+__device__ __forceinline__ void vc_flush_stats(double e, double r, double* __restrict__ partials) {
     __shared__ double se[32], sr[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -75,8 +81,20 @@ __device__ __forceinline__ void vc_flush_stats(double e, double r, double* __res
             e += __shfl_xor_sync(0xffffffffu, e, o);
             r += __shfl_xor_sync(0xffffffffu, r, o);
         }
-        if (lane == 0) { atomicAdd(stats, e); atomicAdd(stats + 1, r); }
+        if (lane == 0) { partials[2 * blockIdx.x] = e; partials[2 * blockIdx.x + 1] = r; }
     }
+}
+__global__ void __launch_bounds__(256) vc_fold_stats_kernel(const double* __restrict__ partials, int n_blocks, double* __restrict__ stats) {
+    __shared__ double se[256], sr[256];
+    const int chunk = (n_blocks + 255) / 256;      // thread i: pairs [i * chunk, (i + 1) * chunk) in order; thread 0: the 256 chunk sums in order
+    double e = 0.0, r = 0.0;
+    for (int i = threadIdx.x * chunk; i < (threadIdx.x + 1) * chunk && i < n_blocks; ++i) { e += partials[2 * i]; r += partials[2 * i + 1]; }
+    se[threadIdx.x] = e; sr[threadIdx.x] = r;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    e = r = 0.0;
+    for (int i = 0; i < 256; ++i) { e += se[i]; r += sr[i]; }
+    stats[0] = e; stats[1] = r;
 }
 
 // The reference's outlier test `abs(residual) > oth2` (:423, :481) on a double residual: with only `int abs(int)` visible to
@@ -146,13 +164,69 @@ __global__ void __launch_bounds__(256) vc_plane_kernel(const float* __restrict__
     vc_flush_stats(e_sum, r_cnt, stats);
 }
 
-// ---- vignette step: bilinear scatter of the normal equations  TT += w*cP*cP,  CT += w*cI*cP
+// ---- vignette step: bilinear scatter of the normal equations  TT += w*cP*cP,  CT += w*cI*cP, in 64-bit fixed point.
+// Every term is computed in fp32 exactly as the reference computes it, then multiplied by 2^s (exact) and rounded to an integer
+// (one DADD with 1.5 * 2^52); the integers are added with 64-bit global REDs.  s comes from three numbers measured on the
+// device (VcFx): the largest finite |planeColor| and |image| bound every term, and the largest number of plane points whose
+// bilinear footprint starts at one pixel bounds how many terms a pixel can receive (4 x that), so that neither a term (< 2^50)
+// nor a sum (< 2^62) can overflow.  A term is thus off by at most 2^-50 of the largest possible term — far below one fp32 ulp of
+// any sum that passes the reference's TT >= 1 test — and the sums do not depend on the order of the atomics.  64-bit REDs cost
+// 1.5x the fp32 ones (profiles/r02_global_atomic_probe.txt).
+struct VcFx { unsigned max_plane_bits, max_image_bits, max_count, pad; };
+constexpr double kVcMagic = 6755399441055744.0;      // 1.5 * 2^52
+__device__ __forceinline__ int vc_scale_exponent(const VcFx& fx) {
+    const double P = static_cast<double>(__uint_as_float(fx.max_plane_bits)), I = static_cast<double>(__uint_as_float(fx.max_image_bits));
+    const double term = P * (P > I ? P : I) * 1.001;                  // |w*cP*cP|, |w*cI*cP| with w in [0,1], incl. the fp32 roundings
+    if (!(term > 0.0)) return 0;
+    const double total = term * (4.0 * static_cast<double>(fx.max_count) + 4.0);
+    const int s_term = 50 - (ilogb(term) + 1), s_total = 62 - (ilogb(total) + 1);
+    const int s = s_term < s_total ? s_term : s_total;
+    return s < -1000 ? -1000 : (s > 1000 ? 1000 : s);
+}
+// largest finite |v[i]| as a float bit pattern (non-negative floats order like integers); *out must start at 0
+__global__ void __launch_bounds__(256) vc_absmax_kernel(const float* __restrict__ v, size_t n, unsigned* __restrict__ out) {
+    unsigned m = 0u;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned b = __float_as_uint(__ldg(v + i)) & 0x7fffffffu;
+        if (b < 0x7f800000u && b > m) m = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+// count[p] = number of (image, plane point) pairs whose footprint starts at pixel p; a pixel receives terms from the footprints
+// starting at it, left of it, above it and above-left of it, i.e. at most 4 x max(count)
+__global__ void __launch_bounds__(256) vc_count_kernel(const float* __restrict__ p2x, const float* __restrict__ p2y, size_t total, int wI,
+                                                       unsigned* __restrict__ count) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const float x = __ldg(p2x + idx);
+        if (isnan(x)) continue;
+        atomicAdd(count + vc_taps(x, __ldg(p2y + idx), wI).base, 1u);
+    }
+}
+__global__ void __launch_bounds__(256) vc_umax_kernel(const unsigned* __restrict__ v, size_t n, unsigned* __restrict__ out) {
+    unsigned m = 0u;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) m = v[i] > m ? v[i] : m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+__device__ __forceinline__ void vc_add(long long* acc, float term, double scale) {
+    const double y = __dadd_rn(__dmul_rn(static_cast<double>(term), scale), kVcMagic);
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(__double_as_longlong(y) - __double_as_longlong(kVcMagic)));
+}
 __global__ void __launch_bounds__(256) vc_vignette_kernel(const float* __restrict__ images, const float* __restrict__ p2x,
                                                           const float* __restrict__ p2y, size_t total, int gwgh, int wI, size_t npx,
                                                           const float* __restrict__ plane_color, const float* __restrict__ vignette,
-                                                          float* __restrict__ tt, float* __restrict__ ct, double oth2, int integer_abs,
-                                                          double* __restrict__ stats) {
+                                                          long long* __restrict__ tt, long long* __restrict__ ct, float* __restrict__ tt_special,
+                                                          float* __restrict__ ct_special, const VcFx* __restrict__ fx, double oth2, int integer_abs,
+                                                          double* __restrict__ partials) {
     double e_sum = 0.0, r_cnt = 0.0;
+    const double scale = scalbn(1.0, vc_scale_exponent(*fx));
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         const float x = __ldg(p2x + idx);
@@ -169,32 +243,41 @@ __global__ void __launch_bounds__(256) vc_vignette_kernel(const float* __restric
         const float d = __fsub_rn(cI, __fmul_rn(cP, fac));
         const double residual = static_cast<double>(__fmul_rn(d, d));
         if (vc_outlier(residual, oth2, integer_abs)) { e_sum += oth2; r_cnt += 1.0; continue; }              // :481-486
-        float* a = tt + t.base;
-        float* b = ct + t.base;
-        atomicAdd(a, __fmul_rn(__fmul_rn(t.w00, cP), cP));
-        atomicAdd(a + 1, __fmul_rn(__fmul_rn(t.w10, cP), cP));
-        atomicAdd(a + wI, __fmul_rn(__fmul_rn(t.w01, cP), cP));
-        atomicAdd(a + 1 + wI, __fmul_rn(__fmul_rn(t.w11, cP), cP));
-        atomicAdd(b, __fmul_rn(__fmul_rn(t.w00, cI), cP));
-        atomicAdd(b + 1, __fmul_rn(__fmul_rn(t.w10, cI), cP));
-        atomicAdd(b + wI, __fmul_rn(__fmul_rn(t.w01, cI), cP));
-        atomicAdd(b + 1 + wI, __fmul_rn(__fmul_rn(t.w11, cI), cP));
+        const float a00 = __fmul_rn(__fmul_rn(t.w00, cP), cP), a10 = __fmul_rn(__fmul_rn(t.w10, cP), cP);
+        const float a01 = __fmul_rn(__fmul_rn(t.w01, cP), cP), a11 = __fmul_rn(__fmul_rn(t.w11, cP), cP);
+        const float b00 = __fmul_rn(__fmul_rn(t.w00, cI), cP), b10 = __fmul_rn(__fmul_rn(t.w10, cI), cP);
+        const float b01 = __fmul_rn(__fmul_rn(t.w01, cI), cP), b11 = __fmul_rn(__fmul_rn(t.w11, cI), cP);
+        if (isfinite(cP) && isfinite(cI)) {
+            long long* a = tt + t.base;
+            long long* b = ct + t.base;
+            vc_add(a, a00, scale); vc_add(a + 1, a10, scale); vc_add(a + wI, a01, scale); vc_add(a + 1 + wI, a11, scale);
+            vc_add(b, b00, scale); vc_add(b + 1, b10, scale); vc_add(b + wI, b01, scale); vc_add(b + 1 + wI, b11, scale);
+        } else {                                                                           // an infinite colour: fp32 sums, which it turns into inf / NaN as in the reference
+            float* a = tt_special + t.base;
+            float* b = ct_special + t.base;
+            atomicAdd(a, a00); atomicAdd(a + 1, a10); atomicAdd(a + wI, a01); atomicAdd(a + 1 + wI, a11);
+            atomicAdd(b, b00); atomicAdd(b + 1, b10); atomicAdd(b + wI, b01); atomicAdd(b + 1 + wI, b11);
+        }
         if (isnan(fac)) continue;
         e_sum += residual;
         r_cnt += 1.0;
     }
-    vc_flush_stats(e_sum, r_cnt, stats);
+    vc_flush_stats(e_sum, r_cnt, partials);
 }
 
 // vignette = CT/TT where TT >= 1, NaN elsewhere; running maximum of the finite factors (:507-517)
-__global__ void __launch_bounds__(256) vc_divide_kernel(const float* __restrict__ tt, const float* __restrict__ ct, size_t npx,
+__global__ void __launch_bounds__(256) vc_divide_kernel(const long long* __restrict__ tt, const long long* __restrict__ ct, const float* __restrict__ tt_special,
+                                                        const float* __restrict__ ct_special, const VcFx* __restrict__ fx, size_t npx,
                                                         float* __restrict__ vignette, int* __restrict__ max_bits) {
     float m = 0.0f;
+    const int s = vc_scale_exponent(*fx);
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx; i += stride) {
+        const float t = __fadd_rn(static_cast<float>(scalbn(static_cast<double>(tt[i]), -s)), tt_special[i]);
+        const float c = __fadd_rn(static_cast<float>(scalbn(static_cast<double>(ct[i]), -s)), ct_special[i]);
         float v = __int_as_float(0x7fc00000);
-        if (!(tt[i] < 1.0f)) {
-            v = __fdiv_rn(ct[i], tt[i]);
+        if (!(t < 1.0f)) {
+            v = __fdiv_rn(c, t);
             if (v > m) m = v;
         }
         vignette[i] = v;
@@ -253,44 +336,81 @@ int check_problem(const char* who, mdc_ctx* c, const Problem& p, const void* a, 
     return MDC_OK;
 }
 
-// scratch layout (floats): [0, A) first accumulator, [A, 2A) second; then 2 doubles of stats and the max word
+// scratch: a 64-byte head {stats[2], max word, VcFx}, the per-CTA statistics pairs, then per pixel: TT and CT (64-bit fixed point),
+// their fp32 side accumulators, and the footprint counts
 struct Scratch {
-    float *acc0 = nullptr, *acc1 = nullptr;
-    double* stats = nullptr;
+    long long *tt = nullptr, *ct = nullptr;
+    float *tt_special = nullptr, *ct_special = nullptr;
+    unsigned* count = nullptr;
+    double *stats = nullptr, *partials = nullptr;
     int* max_bits = nullptr;
+    VcFx* fx = nullptr;
     void* base = nullptr;
+    size_t npx = 0;
 };
-int alloc_scratch(Scratch* s, size_t acc_elems) {
-    const size_t bytes = 2 * acc_elems * sizeof(float) + 64;
-    VC_CHECK(cudaMalloc(&s->base, bytes));
-    s->stats = static_cast<double*>(s->base);
-    s->max_bits = reinterpret_cast<int*>(s->stats + 2);
-    s->acc0 = reinterpret_cast<float*>(static_cast<char*>(s->base) + 64);
-    s->acc1 = s->acc0 + acc_elems;
+constexpr size_t kVcHeadBytes = 64 + 2 * kVcMaxBlocks * sizeof(double);
+int alloc_scratch(Scratch* s, size_t npx) {
+    VC_CHECK(cudaMalloc(&s->base, kVcHeadBytes + npx * (2 * sizeof(long long) + 2 * sizeof(float) + sizeof(unsigned))));
+    char* b = static_cast<char*>(s->base);
+    s->stats = reinterpret_cast<double*>(b);
+    s->max_bits = reinterpret_cast<int*>(b + 16);
+    s->fx = reinterpret_cast<VcFx*>(b + 32);
+    s->partials = reinterpret_cast<double*>(b + 64);
+    s->tt = reinterpret_cast<long long*>(b + kVcHeadBytes);
+    s->ct = s->tt + npx;
+    s->tt_special = reinterpret_cast<float*>(s->ct + npx);
+    s->ct_special = s->tt_special + npx;
+    s->count = reinterpret_cast<unsigned*>(s->ct_special + npx);
+    s->npx = npx;
     return MDC_OK;
 }
 
-int plane_step(mdc_ctx* c, const Problem& p, const float* d_vignette, float* d_plane_color, double oth2, int integer_abs, double* d_stats, cudaStream_t s) {
-    VC_CHECK(cudaMemsetAsync(d_stats, 0, 2 * sizeof(double), s));
-    vc_plane_kernel<<<vc_blocks(static_cast<size_t>(p.gwgh)), 256, 0, s>>>(p.images, p.p2x, p.p2y, p.n, p.gwgh, p.wI, static_cast<size_t>(p.wI) * p.hI,
-                                                                           d_vignette, d_plane_color, oth2, integer_abs, d_stats);
+// what the fixed-point scale needs and does not change between iterations: the largest |image| and the footprint counts
+int measure_static_bounds(mdc_ctx* c, const Problem& p, const Scratch& sc, cudaStream_t s) {
+    const size_t npx = static_cast<size_t>(p.wI) * p.hI, total = static_cast<size_t>(p.n) * p.gwgh;
+    VC_CHECK(cudaMemsetAsync(sc.fx, 0, sizeof(VcFx), s));
+    VC_CHECK(cudaMemsetAsync(sc.count, 0, npx * sizeof(unsigned), s));
+    if (total) {
+        vc_absmax_kernel<<<vc_blocks(static_cast<size_t>(p.n) * npx), 256, 0, s>>>(p.images, static_cast<size_t>(p.n) * npx, &sc.fx->max_image_bits);
+        vc_count_kernel<<<vc_blocks(total), 256, 0, s>>>(p.p2x, p.p2y, total, p.wI, sc.count);
+        vc_umax_kernel<<<vc_blocks(npx), 256, 0, s>>>(sc.count, npx, &sc.fx->max_count);
+        VC_CHECK(cudaGetLastError());
+        mdc_ctx_add_launches(c, 3);
+    }
+    return MDC_OK;
+}
+
+int plane_step(mdc_ctx* c, const Problem& p, const float* d_vignette, float* d_plane_color, double oth2, int integer_abs, double* d_partials, double* d_stats,
+               cudaStream_t s) {
+    const unsigned blocks = vc_blocks(static_cast<size_t>(p.gwgh));
+    vc_plane_kernel<<<blocks, 256, 0, s>>>(p.images, p.p2x, p.p2y, p.n, p.gwgh, p.wI, static_cast<size_t>(p.wI) * p.hI, d_vignette, d_plane_color, oth2,
+                                           integer_abs, d_partials);
+    vc_fold_stats_kernel<<<1, 256, 0, s>>>(d_partials, static_cast<int>(blocks), d_stats);
     VC_CHECK(cudaGetLastError());
-    mdc_ctx_add_launches(c, 1);
+    mdc_ctx_add_launches(c, 2);
     return MDC_OK;
 }
 
+// sc.fx->max_image_bits / max_count must be current (measure_static_bounds)
 int vignette_step(mdc_ctx* c, const Problem& p, const float* d_plane_color, float* d_vignette, double oth2, int integer_abs, const Scratch& sc, cudaStream_t s) {
     const size_t npx = static_cast<size_t>(p.wI) * p.hI, total = static_cast<size_t>(p.n) * p.gwgh;
-    VC_CHECK(cudaMemsetAsync(sc.base, 0, 64 + 2 * npx * sizeof(float), s));
+    VC_CHECK(cudaMemsetAsync(sc.stats, 0, 2 * sizeof(double) + sizeof(int), s));
+    VC_CHECK(cudaMemsetAsync(&sc.fx->max_plane_bits, 0, sizeof(unsigned), s));
+    VC_CHECK(cudaMemsetAsync(sc.tt, 0, npx * (2 * sizeof(long long) + 2 * sizeof(float)), s));
+    int launches = 3;
     if (total) {
-        vc_vignette_kernel<<<vc_blocks(total), 256, 0, s>>>(p.images, p.p2x, p.p2y, total, p.gwgh, p.wI, npx, d_plane_color, d_vignette, sc.acc0,
-                                                            sc.acc1, oth2, integer_abs, sc.stats);
+        const unsigned blocks = vc_blocks(total);
+        vc_absmax_kernel<<<vc_blocks(static_cast<size_t>(p.gwgh)), 256, 0, s>>>(d_plane_color, static_cast<size_t>(p.gwgh), &sc.fx->max_plane_bits);
+        vc_vignette_kernel<<<blocks, 256, 0, s>>>(p.images, p.p2x, p.p2y, total, p.gwgh, p.wI, npx, d_plane_color, d_vignette, sc.tt, sc.ct, sc.tt_special,
+                                                  sc.ct_special, sc.fx, oth2, integer_abs, sc.partials);
+        vc_fold_stats_kernel<<<1, 256, 0, s>>>(sc.partials, static_cast<int>(blocks), sc.stats);
         VC_CHECK(cudaGetLastError());
+        launches += 3;
     }
-    vc_divide_kernel<<<vc_blocks(npx), 256, 0, s>>>(sc.acc0, sc.acc1, npx, d_vignette, sc.max_bits);
+    vc_divide_kernel<<<vc_blocks(npx), 256, 0, s>>>(sc.tt, sc.ct, sc.tt_special, sc.ct_special, sc.fx, npx, d_vignette, sc.max_bits);
     vc_normalise_kernel<<<vc_blocks(npx), 256, 0, s>>>(d_vignette, npx, sc.max_bits);
     VC_CHECK(cudaGetLastError());
-    mdc_ctx_add_launches(c, 3);
+    mdc_ctx_add_launches(c, launches - 1);
     return MDC_OK;
 }
 
@@ -315,9 +435,9 @@ extern "C" int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float*
     if (rc != MDC_OK) return rc;
     VC_CHECK(cudaSetDevice(mdc_ctx_device_ordinal(c)));
     cudaStream_t s = static_cast<cudaStream_t>(mdc_ctx_stream_handle(c));
-    double* d_stats = nullptr;
-    VC_CHECK(cudaMalloc(&d_stats, 2 * sizeof(double)));
-    rc = plane_step(c, p, d_vignette, d_plane_color, outlier_th2, integer_abs, d_stats, s);
+    double* d_stats = nullptr;      // stats[2], then the per-CTA pairs
+    VC_CHECK(cudaMalloc(&d_stats, (2 + 2 * kVcMaxBlocks) * sizeof(double)));
+    rc = plane_step(c, p, d_vignette, d_plane_color, outlier_th2, integer_abs, d_stats + 2, d_stats, s);
     double st[2] = {0, 0};
     if (rc == MDC_OK && cudaMemcpyAsync(st, d_stats, sizeof st, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == MDC_OK) { mdc_set_error("mdc_vc_plane_step: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
@@ -335,7 +455,8 @@ extern "C" int mdc_vc_vignette_step(mdc_ctx* c, const float* d_images, const flo
     cudaStream_t s = static_cast<cudaStream_t>(mdc_ctx_stream_handle(c));
     Scratch sc;
     if ((rc = alloc_scratch(&sc, static_cast<size_t>(wI) * hI)) != MDC_OK) return rc;
-    rc = vignette_step(c, p, d_plane_color, d_vignette, outlier_th2, integer_abs, sc, s);
+    rc = measure_static_bounds(c, p, sc, s);
+    if (rc == MDC_OK) rc = vignette_step(c, p, d_plane_color, d_vignette, outlier_th2, integer_abs, sc, s);
     double st[2] = {0, 0};
     if (rc == MDC_OK && cudaMemcpyAsync(st, sc.stats, sizeof st, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == MDC_OK) { mdc_set_error("mdc_vc_vignette_step: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
@@ -372,11 +493,12 @@ extern "C" int mdc_vignette_calib(mdc_ctx* c, const float* d_images, const float
     if ((rc = alloc_scratch(&sc, npx)) != MDC_OK) return rc;
     double* d_pstats = nullptr;
     if (cudaMalloc(&d_pstats, 2 * sizeof(double)) != cudaSuccess) { cudaFree(sc.base); mdc_set_error("mdc_vignette_calib: out of device memory"); return MDC_ERR_CUDA; }
+    rc = measure_static_bounds(c, p, sc, s);      // images and maps do not change inside the loop
     for (int it = 0; it < max_iterations && rc == MDC_OK; ++it) {
         double oth2 = static_cast<double>(outlier_th) * outlier_th;           // :397-398 (int arithmetic in the reference)
         if (it < max_iterations / 2) oth2 = 10000.0 * 10000.0;
         double ps[2] = {0, 0}, vs[2] = {0, 0};
-        rc = plane_step(c, p, d_vignette, d_plane_color, oth2, integer_abs, d_pstats, s);
+        rc = plane_step(c, p, d_vignette, d_plane_color, oth2, integer_abs, sc.partials, d_pstats, s);
         if (rc == MDC_OK && cudaMemcpyAsync(ps, d_pstats, sizeof ps, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
         if (rc == MDC_OK) rc = vignette_step(c, p, d_plane_color, d_vignette, oth2, integer_abs, sc, s);
         if (rc == MDC_OK && cudaMemcpyAsync(vs, sc.stats, sizeof vs, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = MDC_ERR_CUDA;
@@ -387,7 +509,7 @@ extern "C" int mdc_vignette_calib(mdc_ctx* c, const float* d_images, const float
         if (log_host) { log_host[4 * it] = ps[0]; log_host[4 * it + 1] = ps[1]; log_host[4 * it + 2] = vs[0]; log_host[4 * it + 3] = vs[1]; }
     }
     if (rc == MDC_OK && d_smoothed) {
-        rc = smooth(c, d_vignette, wI, hI, 4, d_smoothed, sc.acc0, s);
+        rc = smooth(c, d_vignette, wI, hI, 4, d_smoothed, sc.tt_special, s);
         if (cudaStreamSynchronize(s) != cudaSuccess && rc == MDC_OK) { mdc_set_error("mdc_vignette_calib: %s", cudaGetErrorString(cudaGetLastError())); rc = MDC_ERR_CUDA; }
     }
     cudaFree(d_pstats);

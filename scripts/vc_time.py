@@ -41,8 +41,14 @@ def main():
     vig_ms = timed(lambda: ctx.vc_vignette_step(images, p2x, p2y, gw, gh, wI, hI, plane, vig, 10000 * 10000))
     smooth_ms = timed(lambda: ctx.vc_smooth(vig, wI, hI, 4))
     samples = n * gw * gh
+    pc2, v2 = plane.clone(), vig.clone()
+    ctx.vignette_calib(images, p2x, p2y, gw, gh, wI, hI, 1, 15, pc2, v2, True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ctx.vignette_calib(images, p2x, p2y, gw, gh, wI, hI, 4, 15, pc2, v2, True)
+    torch.cuda.synchronize()
+    loop_ms = (time.perf_counter() - t0) * 1e3 / 4      # incl. the one-off bounds pass and the final smoothing
     print(json.dumps({"n": n, "plane_points": gw * gh, "visible_fraction": visible, "plane_step_ms": plane_ms, "vignette_step_ms": vig_ms,
-                      "smooth4_ms": smooth_ms, "plane_gsamples_per_s": samples / plane_ms / 1e6, "vignette_gsamples_per_s": samples / vig_ms / 1e6,
+                      "smooth4_ms": smooth_ms, "loop_ms_per_iteration": loop_ms, "plane_gsamples_per_s": samples / plane_ms / 1e6, "vignette_gsamples_per_s": samples / vig_ms / 1e6,
                       "map_bytes_gbs_plane": samples * 8 / plane_ms / 1e6}), flush=True)
 
 
