@@ -148,6 +148,23 @@ def config_dict(batch=256):
                          "CPU arm: per-thread outputs + shared inputs exceed the last-level cache"}
 
 
+def cpu_quota_cores():
+    """CPU time the container may use per wall-clock second (cgroup CFS quota / period), or None if unlimited / unknown.  The GPU boxes of
+    this pool give a 1-GPU job 16 CPUs' worth although 128 hardware threads are visible: more busy threads than that only get throttled."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2
+            q, per = f.read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:      # cgroup v1
+            q, per = float(f.read()), float(g.read())
+        return None if q <= 0 else q / per
+    except (OSError, ValueError):
+        return None
+
+
 class CpuReference:
     """The reference's own per-frame code on the host cores (oracle/_ref = /root/reference/src/*.cpp compiled unmodified), or the
     plain-C restatement when that build is absent.  Two figures:
@@ -160,6 +177,7 @@ class CpuReference:
         from mono_dataset_code_b200 import synthetic as S
         self.frames = S.frames(16, IN_W, IN_H)
         self.cores = os.cpu_count() or 1
+        self.quota = cpu_quota_cores()
         self.pool = None
         if loader.ref_available():
             self.kind = "reference"
@@ -169,10 +187,15 @@ class CpuReference:
             self.photo = R.photo(files["pcalib"], files["vignette"], IN_W, IN_H)
             assert self.fov.valid and self.photo.valid_vignette
             # The reference's loop does not scale to every hardware thread: beyond a few dozen workers the private
-            # float images (2 x 5 MB per thread) evict each other and throughput FALLS (profiles/r02_cpu_ref_scaling.jsonl).
+            # float images (2 x 5 MB per thread) evict each other and throughput FALLS (profiles/r02_cpu_ref_scaling.jsonl),
+            # and the GPU boxes cap the container at 16 CPUs per GPU (cgroup quota) although 128 threads are visible.
             # The CPU arm therefore runs at the best worker count / placement of a short sweep — its fastest configuration.
             self.sweep = []
-            cands = [(threads, "0")] if threads else [(t, sp) for t in sorted({8, 16, 32, 64, self.cores}) if t <= self.cores for sp in ("0", "1")]
+            counts = {8, 16, 32, 64, self.cores}
+            if self.quota:                 # busy threads beyond the container's CPU quota only get throttled: sweep up to the quota
+                q = max(1, int(self.quota))
+                counts = {max(1, q // 4), max(1, q // 2), q}
+            cands = [(threads, "0")] if threads else [(t, sp) for t in sorted(counts) if t <= self.cores for sp in ("0", "1")]
             best = None
             for t, spread in cands:
                 os.environ["MDC_REF_SPREAD"] = spread
@@ -219,7 +242,8 @@ class CpuReference:
 
     def describe(self):
         return (f"{self.threads} pinned threads" + (f" ({self.placement}) on {self.numa_nodes} NUMA node(s), tables + inputs replicated per node" if self.numa_nodes else "")
-                + f" = the fastest of a sweep over worker counts on this {self.cores}-thread host; private buffers first-touched by their thread; "
+                + f" = the fastest of a sweep over worker counts on this {self.cores}-thread host"
+                + (f" (container CPU quota: {self.quota:g} CPUs)" if self.quota else "") + "; private buffers first-touched by their thread; "
                 "timed inside the library; decode/alloc excluded")
 
     def close(self):
@@ -238,7 +262,7 @@ def cpu_baseline(files):
         s += b
     out = {"value": n / s, "unit": "frames/s", "cores": ref.threads, "kind": ref.kind,
            "sample": f"{n} frames of {IN_W}x{IN_H} (16 distinct, cycled), 5 steps of {fpt} per thread; " + ref.describe(),
-           "single_thread": one, "thread_sweep": getattr(ref, "sweep", None)}
+           "single_thread": one, "thread_sweep": getattr(ref, "sweep", None), "cpu_quota_cores": ref.quota, "hardware_threads": ref.cores}
     ref.close()
     return out
 
@@ -287,7 +311,7 @@ def run_reference_arm(args):
             "run_config": {"frames_per_step": per_step, "threads": ref.threads, "numa_nodes": ref.numa_nodes},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.threads, "kind": ref.kind,
                              "sample": f"{per_step} frames/step x {args.steps} steps ({fpt} per thread and step); " + ref.describe(),
-                             "single_thread": one},
+                             "single_thread": one, "cpu_quota_cores": ref.quota, "hardware_threads": ref.cores},
             "as_shipped_single_thread": one, "thread_sweep": getattr(ref, "sweep", None),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -484,6 +508,9 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
         dist.all_gather_object(nodes, numa)
     same_node = sum(1 for x in nodes if x.get("node") == numa.get("node"))
     threads = max(1, len(os.sched_getaffinity(0)) // max(1, same_node))
+    quota = cpu_quota_cores()
+    if quota:                              # busy threads beyond the container's CPU quota only get throttled (and make every timing noisy)
+        threads = max(1, min(threads, int(quota // world)))
     n_px = W * H
     h_out = C.c_void_p()
     _lib.check(_lib.lib.mdc_host_alloc(C.byref(h_out), CALL * n_px * 4), "mdc_host_alloc")
@@ -559,6 +586,7 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
             "decode_inclusive": {"value": total / dec_s, "unit": "frames/s", "seconds": dec_s, "decode_threads_per_rank": threads,
                                  "decode_thread_sweep": sweep, "host_decode_only_frames_per_s_rank0": decode_only,
                                  "d2h_bytes_per_frame": n_px * 4, "numa": nodes, "jpeg_mean_bytes": meta["jpeg_mean_bytes"],
+                                 "cpu_quota_cores": cpu_quota_cores(),
                                  "path": "mdc_seq_prepare: zip read + JPEG decode (host) -> pinned -> H2D -> K1 -> D2H, chunks double-buffered"},
             "device_resident": {"value": total / res_s, "unit": "frames/s", "seconds": res_s, "alg_gbs": alg / res_s / 1e9,
                                 "frames_per_launch": B, "launches_per_rank": launches}}

@@ -223,11 +223,14 @@ int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int count, unsigned
  *   i.e. the reference's era; also how the unmodified program builds against this repo's oracle headers); 0 = fabs(residual).
  * ===================================================================================== */
 /* "optimize planeColor" (:400-446): d_plane_color is read (residual test) and overwritten with sum(color*fac)/sum(fac*fac),
- * NaN where sum(fac*fac) < 1.  Bit-identical to the reference.  stats_host = {E, R} (E: fp64 sum, order-dependent). */
+ * NaN where sum(fac*fac) < 1.  Bit-identical to the reference.  stats_host = {E, R} (E: fp64 sum in a fixed order that is not the
+ * reference's: rounding-level, but the same bits on every run). */
 int mdc_vc_plane_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
                       const float* d_vignette, float* d_plane_color, double outlier_th2, int integer_abs, double stats_host[2]);
 /* "optimize vignette" (:458-523) including the normalisation to maximum factor 1: d_vignette is read and overwritten.
- * The bilinear scatter-add runs on fp32 atomics, so sums match the reference's sequential ones to rounding only. */
+ * The reference adds the scattered fp32 terms one after the other in fp32; here the same terms are added exactly (64-bit fixed
+ * point), so the result differs from the reference by the rounding error of its own chain only (<= 2e-5 relative in the tests)
+ * and is the same bits on every run. */
 int mdc_vc_vignette_step(mdc_ctx* c, const float* d_images, const float* d_p2x, const float* d_p2y, int n, int gw, int gh, int wI, int hI,
                          const float* d_plane_color, float* d_vignette, double outlier_th2, int integer_abs, double stats_host[2]);
 /* "dilate & smoothe" (:542-566): `iterations` rounds (the reference: 4) of the NaN-aware 3x3 mean.  Bit-identical. */
@@ -248,9 +251,12 @@ int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* 
  * image-major, t = [n] f64 exposure times, G = [256] f64, E = [npix] f64):
  *   mdc_rc_leak_padding  3x3 dilation of saturated interior pixels, `iterations` rounds, in place   main_responseCalib.cpp:212-236  bit-exact
  *   mdc_rc_einit         E = per-pixel mean over the n images                                          :249-259                       bit-exact
- *   mdc_rc_gstep         G[b] = sum(E[k]*t[i]) / count over samples with value b != 255, gaps extrapolated  :286-304   rounding-level (sum order)
+ *   mdc_rc_gstep         G[b] = sum(E[k]*t[i]) / count over samples with value b != 255, gaps extrapolated  :286-304   rounding-level: the products are
+ *                        rounded as in the reference and then summed EXACTLY (fixed point), where the reference has one fp64 chain;
+ *                        order-independent, so the same bits on every run and for every launch geometry
  *   mdc_rc_rescale       factor = 255/G[255]; E *= factor; G *= factor; *factor_host = factor           :350-355                       bit-exact
  *   mdc_rc_rmse          out_host = {1e5*sqrt(mean((G[b]-t*E)^2 * 1e-10)), count}                       :50-69                         rounding-level
+ *                        (the reference sums in long double); residuals, finite test and count exact; same bits on every run
  *   mdc_response_calib   the optimisation loop of main(): E := mean, then nits x {G-step, E-step, rescale}, rmse after
  *                        each half-step; log_host (may be NULL) receives nits x 4 doubles {rmse_G, rmse_E, rmse_rescaled, count}. */
 int mdc_rc_leak_padding(mdc_ctx* c, uint8_t* d_data, int n, int w, int h, int iterations, mdc_stream stream);

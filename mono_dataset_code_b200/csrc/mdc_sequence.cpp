@@ -18,6 +18,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <string>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -271,6 +272,20 @@ extern "C" int mdc_seq_read_gray8(const mdc_seq* s, int id, uint8_t* out, size_t
     return MDC_OK;
 }
 
+// threads = 0: as many decode threads as the process may keep busy — the CPUs it is allowed to run on, capped by the container's
+// CPU-time quota (cgroup v2 cpu.max) where there is one: more busy threads than the quota only get throttled
+static int default_decode_threads() {
+    int n = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::max(1, std::min(n, CPU_COUNT(&set)));
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        long long quota = 0, period = 0;
+        if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) n = std::max(1, std::min<int>(n, static_cast<int>(quota / period)));
+        fclose(f);
+    }
+    return n;
+}
+
 // getImage(id, ...) for ids [first, first+count): decode ahead on `threads` host threads, prepare on the GPU chunk by chunk.
 extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int count, unsigned flags, float* const* h_out_levels, int levels,
                                int threads) {
@@ -287,7 +302,7 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     std::vector<size_t> level_px(static_cast<size_t>(levels));
     for (int l = 0; l < levels; ++l)      // level l of getImage's result: (w >> l) x (h >> l), mdc_prepare_batch
         level_px[static_cast<size_t>(l)] = static_cast<size_t>((rectify ? out_w : in_w) >> l) * static_cast<size_t>((rectify ? out_h : in_h) >> l);
-    if (threads < 1) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    if (threads < 1) threads = default_decode_threads();
     // several frames per decode thread and chunk: decode times vary from frame to frame, and a chunk is as slow as its slowest thread
     const int chunk = std::min(256, std::max(32, 4 * threads));
     std::lock_guard<std::mutex> feed_lock(s->feed_mutex);
