@@ -270,8 +270,20 @@ class Context:
 
     @staticmethod
     def _stream(t):
+        """torch's current stream on the tensor's device as an mdc_stream.  The default stream has handle 0, which the C ABI reads as
+        "the context's own stream, synchronised before returning"; torch callers mean the (legacy) default stream itself — other
+        work they enqueue there, e.g. the wait torch.distributed puts behind an all-reduce, must order with ours — so it is passed
+        by its explicit handle cudaStreamLegacy."""
         import torch
-        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        h = torch.cuda.current_stream(t.device).cuda_stream
+        return C.c_void_p(h if h else 0x1)
+
+    @staticmethod
+    def _drain(t):
+        """Entry points without a stream argument run on the context's own stream and return when they are done; what torch has queued
+        on its current stream for their inputs must be finished first."""
+        import torch
+        torch.cuda.current_stream(t.device).synchronize()
 
     # ---- device-resident operators (CUDA tensors, asynchronous on torch's current stream)
     def prepare_batch(self, frames, flags: int, out_levels):
@@ -319,15 +331,13 @@ class Context:
                                C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), self._stream(data)), "mdc_rc_gstep")
 
     def rc_rescale(self, E, G) -> float:
-        import torch
-        torch.cuda.current_stream(E.device).synchronize()
+        self._drain(E)
         f = C.c_double()
         check(lib.mdc_rc_rescale(self._h, E.shape[0], C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), C.byref(f)), "mdc_rc_rescale")
         return f.value
 
     def rc_rmse(self, data, t, G, E):
-        import torch
-        torch.cuda.current_stream(data.device).synchronize()
+        self._drain(data)
         out = (C.c_double * 2)()
         check(lib.mdc_rc_rmse(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
                               C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), out), "mdc_rc_rmse")
@@ -350,8 +360,7 @@ class Context:
 
     def response_calib(self, data, t, nits, E, G):
         """The optimisation loop of responseCalib's main(); returns the per-iteration log [nits, 4]."""
-        import torch
-        torch.cuda.current_stream(data.device).synchronize()
+        self._drain(data)
         log = np.zeros((max(nits, 1), 4), np.float64)
         check(lib.mdc_response_calib(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()), nits,
                                      C.c_void_p(E.data_ptr()), C.c_void_p(G.data_ptr()), log.ctypes.data_as(C.POINTER(C.c_double))),
@@ -369,9 +378,9 @@ class Context:
 
     def vc_plane_step(self, images, p2x, p2y, gw, gh, wI, hI, vignette, plane_color, oth2, integer_abs=True):
         """plane_color is updated in place; returns (E, R)."""
+        self._drain(images)
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
-        torch.cuda.current_stream(images.device).synchronize()
         st = (C.c_double * 2)()
         check(lib.mdc_vc_plane_step(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,
                                     C.c_void_p(vignette.data_ptr()), C.c_void_p(plane_color.data_ptr()), float(oth2), int(integer_abs), st), "mdc_vc_plane_step")
@@ -379,26 +388,26 @@ class Context:
 
     def vc_vignette_step(self, images, p2x, p2y, gw, gh, wI, hI, plane_color, vignette, oth2, integer_abs=True):
         """vignette is updated in place (normalised to maximum 1); returns (E, R)."""
+        self._drain(images)
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
-        torch.cuda.current_stream(images.device).synchronize()
         st = (C.c_double * 2)()
         check(lib.mdc_vc_vignette_step(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,
                                        C.c_void_p(plane_color.data_ptr()), C.c_void_p(vignette.data_ptr()), float(oth2), int(integer_abs), st), "mdc_vc_vignette_step")
         return st[0], st[1]
 
     def vc_smooth(self, vignette, wI, hI, iterations=4):
+        self._drain(vignette)
         import torch
-        torch.cuda.current_stream(vignette.device).synchronize()
         out = torch.empty_like(vignette)
         check(lib.mdc_vc_smooth(self._h, C.c_void_p(vignette.data_ptr()), wI, hI, iterations, C.c_void_p(out.data_ptr())), "mdc_vc_smooth")
         return out
 
     def vignette_calib(self, images, p2x, p2y, gw, gh, wI, hI, max_iterations, outlier_th, plane_color, vignette, integer_abs=True):
         """The reference's optimisation loop; plane_color / vignette updated in place.  Returns (smoothed vignette, log [its, 4])."""
+        self._drain(images)
         import torch
         n = self._vc_dims(images, p2x, p2y, gw, gh, wI, hI)
-        torch.cuda.current_stream(images.device).synchronize()
         smoothed = torch.empty_like(vignette)
         log = np.zeros((max(max_iterations, 1), 4), np.float64)
         check(lib.mdc_vignette_calib(self._h, C.c_void_p(images.data_ptr()), C.c_void_p(p2x.data_ptr()), C.c_void_p(p2y.data_ptr()), n, gw, gh, wI, hI,

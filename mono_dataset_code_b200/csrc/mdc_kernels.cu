@@ -1574,6 +1574,7 @@ struct RmseOp {
     }
 };
 
+static cudaEvent_t g_exposure_reader[64] = {};      // per device: recorded behind the last pass that read c_exposure_t
 template <class Op>
 static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params& prm, cudaStream_t stream, int* grid_out = nullptr) {
     int dev = 0, sms = 148, per_sm = 0;
@@ -1612,7 +1613,7 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
     if (grid > tiles) grid = tiles;
     if (grid_out) *grid_out = static_cast<int>(grid);
     // exposure times -> constant memory (device-to-device, on this stream), behind the last pass that read the symbol
-    static cudaEvent_t last_reader[64] = {};
+    cudaEvent_t* last_reader = g_exposure_reader;      // one event per device, shared by the three ops (they share the symbol)
     const bool use_const = a.n <= kEbMaxN && dev >= 0 && dev < 64;
     if (use_const) {
         if (!last_reader[dev] && (e = cudaEventCreateWithFlags(&last_reader[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
