@@ -18,6 +18,9 @@
 #include <vector>
 
 #include "mdc_internal.h"
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -30,6 +33,21 @@ struct HuffTable {
     // canonical decoding tables (T.81 Annex F.2.2.3) + a prefix table for the short codes
     int mincode[17], maxcode[18], valptr[17];
     uint16_t look[1 << kLookBits];      // (code length << 8) | symbol, 0 = longer than kLookBits
+    // AC tables: where code + magnitude bits fit the look-up window and the value fits 8 bits, one look-up yields the whole
+    // coefficient: (value << 8) | (run << 4) | total bits; 0 = take the general path
+    int16_t fast_ac[1 << kLookBits];
+    void build_fast_ac() {
+        for (int i = 0; i < (1 << kLookBits); ++i) {
+            fast_ac[i] = 0;
+            const int e = look[i];
+            if (!e) continue;
+            const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
+            if (!mag || len + mag > kLookBits) continue;
+            int v = ((i << len) & ((1 << kLookBits) - 1)) >> (kLookBits - mag);      // the magnitude bits that follow the code
+            if (v < (1 << (mag - 1))) v += 1 - (1 << mag);                             // T.81 F.2.2.1 EXTEND
+            if (v >= -128 && v <= 127) fast_ac[i] = static_cast<int16_t>(v * 256 + run * 16 + len + mag);
+        }
+    }
     // false = over-subscribed table (more codes of some length than the prefix code space has left; libjpeg's
     // JERR_BAD_HUFF_TABLE).  Must be checked before look[] is filled: such a table would index past its end.
     bool build() {
@@ -62,6 +80,19 @@ struct BitReader {
     bool hit_marker = false;
     // entropy-coded bytes: 0xFF 0x00 is a stuffed 0xFF, 0xFF followed by anything else is a marker (zero bits from then on)
     void fill() {
+        if (!hit_marker && end - p >= 8) {      // eight plain bytes ahead (no 0xFF among them): take as many whole bytes as fit at once
+            uint64_t v;
+            memcpy(&v, p, 8);
+            const uint64_t x = ~v;
+            if (!((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull)) {
+                const int bytes = (64 - n) >> 3;
+                // bits of a partly fitting next byte come along below the counted ones; the next fill ORs the same byte over them
+                acc |= __builtin_bswap64(v) >> n;
+                p += bytes;
+                n += 8 * bytes;
+                return;
+            }
+        }
         while (n <= 56) {
             uint64_t b = 0;
             if (!hit_marker && p < end) {
@@ -171,6 +202,90 @@ void idct_block(const int32_t coef[64], uint8_t* out, size_t stride) {
     }
 }
 
+// ---- the same transform with AVX2: eight columns (pass 1) resp. eight rows (pass 2) per instruction, 32-bit lanes.  Dequantised
+// coefficients of a valid stream fit 16 bits, so no lane can overflow and the results equal the 64-bit scalar code bit for bit
+// (and what libjpeg-turbo's SIMD returns); only corrupt streams can tell the two apart.  Chosen at run time (cpu_has_avx2).
+#if defined(__x86_64__) && defined(__GNUC__)
+#define MDC_JPEG_AVX2 1
+#define AVX2_FN __attribute__((target("avx2"), always_inline)) inline
+typedef __m256i V8;
+AVX2_FN V8 vmul(V8 a, int c) { return _mm256_mullo_epi32(a, _mm256_set1_epi32(c)); }
+AVX2_FN V8 vadd(V8 a, V8 b) { return _mm256_add_epi32(a, b); }
+AVX2_FN V8 vsub(V8 a, V8 b) { return _mm256_sub_epi32(a, b); }
+struct ButterflyV { V8 e0, e1, e2, e3, o0, o1, o2, o3; };
+AVX2_FN ButterflyV idct_1d_v(V8 c0, V8 c1, V8 c2, V8 c3, V8 c4, V8 c5, V8 c6, V8 c7) {
+    ButterflyV r;
+    V8 z1 = vmul(vadd(c2, c6), static_cast<int>(F_0_541196100));
+    const V8 t2 = vadd(z1, vmul(c6, -static_cast<int>(F_1_847759065))), t3 = vadd(z1, vmul(c2, static_cast<int>(F_0_765366865)));
+    const V8 t0 = _mm256_slli_epi32(vadd(c0, c4), kConstBits), t1 = _mm256_slli_epi32(vsub(c0, c4), kConstBits);
+    r.e0 = vadd(t0, t3); r.e3 = vsub(t0, t3); r.e1 = vadd(t1, t2); r.e2 = vsub(t1, t2);
+    V8 a0 = c7, a1 = c5, a2 = c3, a3 = c1;
+    z1 = vadd(a0, a3);
+    V8 z2 = vadd(a1, a2), z3 = vadd(a0, a2), z4 = vadd(a1, a3);
+    const V8 z5 = vmul(vadd(z3, z4), static_cast<int>(F_1_175875602));
+    a0 = vmul(a0, static_cast<int>(F_0_298631336)); a1 = vmul(a1, static_cast<int>(F_2_053119869));
+    a2 = vmul(a2, static_cast<int>(F_3_072711026)); a3 = vmul(a3, static_cast<int>(F_1_501321110));
+    z1 = vmul(z1, -static_cast<int>(F_0_899976223)); z2 = vmul(z2, -static_cast<int>(F_2_562915447));
+    z3 = vadd(vmul(z3, -static_cast<int>(F_1_961570560)), z5); z4 = vadd(vmul(z4, -static_cast<int>(F_0_390180644)), z5);
+    r.o0 = vadd(vadd(a0, z1), z3); r.o1 = vadd(vadd(a1, z2), z4); r.o2 = vadd(vadd(a2, z2), z3); r.o3 = vadd(vadd(a3, z1), z4);
+    return r;
+}
+template <int kShift> AVX2_FN V8 vdescale(V8 x) { return _mm256_srai_epi32(vadd(x, _mm256_set1_epi32(1 << (kShift - 1))), kShift); }
+// rows r0..r7 of an 8x8 int32 matrix -> its columns
+AVX2_FN void transpose8(V8& r0, V8& r1, V8& r2, V8& r3, V8& r4, V8& r5, V8& r6, V8& r7) {
+    const V8 a0 = _mm256_unpacklo_epi32(r0, r1), a1 = _mm256_unpackhi_epi32(r0, r1), a2 = _mm256_unpacklo_epi32(r2, r3), a3 = _mm256_unpackhi_epi32(r2, r3);
+    const V8 a4 = _mm256_unpacklo_epi32(r4, r5), a5 = _mm256_unpackhi_epi32(r4, r5), a6 = _mm256_unpacklo_epi32(r6, r7), a7 = _mm256_unpackhi_epi32(r6, r7);
+    const V8 b0 = _mm256_unpacklo_epi64(a0, a2), b1 = _mm256_unpackhi_epi64(a0, a2), b2 = _mm256_unpacklo_epi64(a1, a3), b3 = _mm256_unpackhi_epi64(a1, a3);
+    const V8 b4 = _mm256_unpacklo_epi64(a4, a6), b5 = _mm256_unpackhi_epi64(a4, a6), b6 = _mm256_unpacklo_epi64(a5, a7), b7 = _mm256_unpackhi_epi64(a5, a7);
+    r0 = _mm256_permute2x128_si256(b0, b4, 0x20); r1 = _mm256_permute2x128_si256(b1, b5, 0x20);
+    r2 = _mm256_permute2x128_si256(b2, b6, 0x20); r3 = _mm256_permute2x128_si256(b3, b7, 0x20);
+    r4 = _mm256_permute2x128_si256(b0, b4, 0x31); r5 = _mm256_permute2x128_si256(b1, b5, 0x31);
+    r6 = _mm256_permute2x128_si256(b2, b6, 0x31); r7 = _mm256_permute2x128_si256(b3, b7, 0x31);
+}
+__attribute__((target("avx2"))) void idct_block_avx2(const int32_t* coef, uint8_t* out, size_t stride) {
+    const V8* c = reinterpret_cast<const V8*>(coef);      // 32-byte aligned by the caller; row r = lanes (columns) of one vector
+    // pass 1: columns
+    ButterflyV b = idct_1d_v(_mm256_load_si256(c), _mm256_load_si256(c + 1), _mm256_load_si256(c + 2), _mm256_load_si256(c + 3),
+                             _mm256_load_si256(c + 4), _mm256_load_si256(c + 5), _mm256_load_si256(c + 6), _mm256_load_si256(c + 7));
+    constexpr int s1 = kConstBits - kPass1Bits;
+    V8 w0 = vdescale<s1>(vadd(b.e0, b.o3)), w7 = vdescale<s1>(vsub(b.e0, b.o3)), w1 = vdescale<s1>(vadd(b.e1, b.o2)), w6 = vdescale<s1>(vsub(b.e1, b.o2));
+    V8 w2 = vdescale<s1>(vadd(b.e2, b.o1)), w5 = vdescale<s1>(vsub(b.e2, b.o1)), w3 = vdescale<s1>(vadd(b.e3, b.o0)), w4 = vdescale<s1>(vsub(b.e3, b.o0));
+    // pass 2: rows — lanes become rows
+    transpose8(w0, w1, w2, w3, w4, w5, w6, w7);
+    b = idct_1d_v(w0, w1, w2, w3, w4, w5, w6, w7);
+    constexpr int s2 = kConstBits + kPass1Bits + 3;
+    const V8 bias = _mm256_set1_epi32(128);
+    const V8 o0 = vadd(vdescale<s2>(vadd(b.e0, b.o3)), bias), o7 = vadd(vdescale<s2>(vsub(b.e0, b.o3)), bias);
+    const V8 o1 = vadd(vdescale<s2>(vadd(b.e1, b.o2)), bias), o6 = vadd(vdescale<s2>(vsub(b.e1, b.o2)), bias);
+    const V8 o2 = vadd(vdescale<s2>(vadd(b.e2, b.o1)), bias), o5 = vadd(vdescale<s2>(vsub(b.e2, b.o1)), bias);
+    const V8 o3 = vadd(vdescale<s2>(vadd(b.e3, b.o0)), bias), o4 = vadd(vdescale<s2>(vsub(b.e3, b.o0)), bias);
+    // o_k: lane = row, value = sample k of that row.  Saturating packs clamp to 0..255; per 128-bit half the bytes come out as
+    // [k0: r0-3][k1: r0-3][k2: r0-3][k3: r0-3] and have to be regrouped by row
+    const V8 p0123 = _mm256_packus_epi16(_mm256_packs_epi32(o0, o1), _mm256_packs_epi32(o2, o3));
+    const V8 p4567 = _mm256_packus_epi16(_mm256_packs_epi32(o4, o5), _mm256_packs_epi32(o6, o7));
+    const V8 by_row = _mm256_setr_epi8(0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15, 0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15);
+    const V8 q0 = _mm256_shuffle_epi8(p0123, by_row), q1 = _mm256_shuffle_epi8(p4567, by_row);      // dword j of a half = samples 0-3 (q0) / 4-7 (q1) of row j
+    const V8 rows01 = _mm256_unpacklo_epi32(q0, q1), rows23 = _mm256_unpackhi_epi32(q0, q1);         // low half: rows 0,1 / 2,3; high half: rows 4,5 / 6,7
+    const __m128i lo01 = _mm256_castsi256_si128(rows01), lo23 = _mm256_castsi256_si128(rows23);
+    const __m128i hi45 = _mm256_extracti128_si256(rows01, 1), hi67 = _mm256_extracti128_si256(rows23, 1);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out), lo01);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + stride), _mm_unpackhi_epi64(lo01, lo01));
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 2 * stride), lo23);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 3 * stride), _mm_unpackhi_epi64(lo23, lo23));
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 4 * stride), hi45);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 5 * stride), _mm_unpackhi_epi64(hi45, hi45));
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 6 * stride), hi67);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 7 * stride), _mm_unpackhi_epi64(hi67, hi67));
+}
+const bool cpu_has_avx2 = [] { __builtin_cpu_init(); return __builtin_cpu_supports("avx2") != 0; }();
+#endif
+
+// a block whose AC coefficients are all zero: every sample is the rounded DC term (what both passes' shortcuts give)
+inline void idct_dc_only(int32_t dc, uint8_t* out, size_t stride) {
+    const uint8_t v = clamp_sample(descale(wide(dc) * (1 << kPass1Bits), kPass1Bits + 3));
+    for (int r = 0; r < 8; ++r) memset(out + r * stride, v, 8);
+}
+
 inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 
 }  // namespace
@@ -226,6 +341,7 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                 i += total;
                 t.defined = t.build();
                 if (!t.defined) return fail("bad Huffman table (over-subscribed code lengths)");
+                if (tc) t.build_fast_ac();
             }
         } else if (marker == 0xc0 || marker == 0xc1) {         // SOF0 / SOF1 (Huffman, sequential)
             if (seg_len < 6) return fail("bad frame header");
@@ -284,7 +400,9 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
             static thread_local std::vector<uint8_t> plane;
             plane.resize(pw * ph);      // every block of the padded plane is written by the loop below
             BitReader br{d + pos, d + n};
-            int32_t coef[64];
+            alignas(32) int32_t coef[64] = {0};      // all zero between blocks: a block clears what it wrote
+            int32_t qzz[64];                         // luminance quantisation steps in zig-zag (= stream) order
+            for (int k = 0; k < 64; ++k) qzz[k] = quant[Y.tq][kZigZag[k]];
             int until_restart = restart_interval;
             for (int my = 0; my < mcus_y; ++my)
                 for (int mx = 0; mx < mcus_x; ++mx) {
@@ -308,10 +426,21 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                                 if (t < 0 || t > 15) return fail("corrupt JPEG data (DC)");
                                 // libjpeg stores coefficients as 16-bit JCOEF: the running DC value wraps there (only corrupt data gets that far)
                                 comp.pred = static_cast<int16_t>(static_cast<uint32_t>(comp.pred) + static_cast<uint32_t>(extend(br.bits(t), t)));
-                                if (c == 0) { memset(coef, 0, sizeof coef); coef[0] = comp.pred * static_cast<int32_t>(quant[Y.tq][0]); }
+                                if (c == 0) coef[0] = comp.pred * qzz[0];
+                                bool any_ac = false;
                                 // AC
+                                const HuffTable& act = ac[comp.ta];
                                 for (int k = 1; k < 64;) {
-                                    const int rs = decode_symbol(br, ac[comp.ta]);
+                                    const int fa = act.fast_ac[br.peek(kLookBits)];
+                                    if (fa) {                      // code + magnitude in one look-up
+                                        k += (fa >> 4) & 15;
+                                        if (k > 63) return fail("corrupt JPEG data (run past the block)");
+                                        br.skip(fa & 15);
+                                        if (c == 0) { coef[kZigZag[k]] = (fa >> 8) * qzz[k]; any_ac = true; }
+                                        ++k;
+                                        continue;
+                                    }
+                                    const int rs = decode_symbol(br, act);
                                     if (rs < 0) return fail("corrupt JPEG data (AC)");
                                     const int r = rs >> 4, s = rs & 15;
                                     if (s == 0) {
@@ -322,12 +451,23 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                                     k += r;
                                     if (k > 63) return fail("corrupt JPEG data (run past the block)");
                                     const int v = extend(br.bits(s), s);
-                                    if (c == 0) coef[kZigZag[k]] = v * static_cast<int32_t>(quant[Y.tq][kZigZag[k]]);
+                                    if (c == 0) { coef[kZigZag[k]] = v * qzz[k]; any_ac = true; }
                                     ++k;
                                 }
                                 if (c == 0) {
                                     const size_t x0 = (static_cast<size_t>(mx) * yh + bx) * 8, y0 = (static_cast<size_t>(my) * yv + by) * 8;
-                                    idct_block(coef, plane.data() + y0 * pw + x0, pw);
+                                    uint8_t* dst = plane.data() + y0 * pw + x0;
+                                    if (!any_ac) {
+                                        idct_dc_only(coef[0], dst, pw);
+                                        coef[0] = 0;
+                                    } else {
+#ifdef MDC_JPEG_AVX2
+                                        if (cpu_has_avx2) idct_block_avx2(coef, dst, pw);
+                                        else
+#endif
+                                            idct_block(coef, dst, pw);
+                                        memset(coef, 0, sizeof coef);
+                                    }
                                 }
                             }
                     }
