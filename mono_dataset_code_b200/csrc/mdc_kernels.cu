@@ -1178,7 +1178,11 @@ __device__ __forceinline__ void stream_produce(const StreamArgs& a, uint32_t n_t
         const uint32_t bytes = a.npix - k0 < tile_px ? a.npix - k0 : tile_px;      // multiple of 16 (npix is)
         const uint8_t* src = a.data + k0;
         for (int g = 0; g < n_groups; ++g, ++it) {
-            if (it >= kEbStages) mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
+            if (it >= kEbStages) {
+                mbar_wait_backoff(bar_empty + 8u * s, ph ^ 1u);
+                // the consumers read this stage through the generic proxy, the copy below writes it through the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
             const int planes = a.n - g * kEbPlanes < kEbPlanes ? a.n - g * kEbPlanes : kEbPlanes;
             mbar_expect_tx(bar_full + 8u * s, static_cast<uint32_t>(planes) * bytes);
             const uint32_t dst = stages + s * static_cast<uint32_t>(Shape::kStageBytes);
@@ -1362,8 +1366,8 @@ struct GstepFx {
 // value at the same moment): three limb planes and, in the first pass, a count plane (kCount = false: the caller already holds
 // GNum — it depends on the images only, so the optimisation loop computes it once).  One PRMT + one LEA build each address.
 // A slot receives at most 4 x 28 adds per exposure, i.e. a limb could overflow after 2^15 / 112 = 292 exposures; every 160
-// exposures each warp therefore folds its share of the (plane, value) rows into 64-bit totals: it reads a slot, subtracts what it
-// read with another ATOMS.ADD — which commutes with the adds of the other warps, so no barrier is needed — and sums the 32 slots
+// exposures each warp therefore folds its share of the (plane, value) rows into 64-bit totals: it takes a slot's value with an
+// atomic exchange against zero — the adds of the other warps go on around it, so no barrier is needed — and sums the 32 slots
 // with REDUX.  The ring lets warps drift apart by at most 24 exposures, so a slot sees at most 4 x 28 x (160 + 48) = 23 296 adds
 // between folds.  At the end the three totals of a bin are combined into one 128-bit number and added to the global accumulators.
 constexpr int kGstepWarps = 28;
@@ -1451,8 +1455,7 @@ struct GstepOp {
 #pragma unroll 2
         for (int r = warp; r < kPlanes * 256; r += warps) {
             unsigned* slot = reinterpret_cast<unsigned*>(hist + r * 128) + lane;
-            const unsigned cur = *reinterpret_cast<volatile unsigned*>(slot);
-            if (cur) atomicAdd(slot, 0u - cur);
+            const unsigned cur = atomicExch(slot, 0u);      // read and clear in one atomic: nothing another warp adds can be lost
             long long sum;
             if ((r >> 8) == 2) {            // the signed limb
                 const int c = static_cast<int>(cur);
@@ -1589,18 +1592,16 @@ static cudaError_t launch_stream(const StreamArgs& a, const typename Op::Params&
     if (per_sm < 1) per_sm = 1;
     // Tile width (consumer warps per CTA).  A CTA works through its tiles one after the other; measured per-tile time grows like
     // (2.6 + warps) for the 14-warp ops (profiles/r02_k3_stream_tile_width_sweep.jsonl), so the width that minimises
-    // rounds x (2.6 + warps) fills the persistent CTAs best: 14 warps = 2 rounds at 1 MP (12 warps: 3 uneven rounds).  Only the
-    // upper third of the widths are candidates — narrower tiles lose more to the thinner ring than they gain in balance — and an
-    // image with fewer full-width tiles than CTAs keeps the full width.
+    // rounds x (2.6 + warps) fills the persistent CTAs best: 14 warps = 2 rounds at 1 MP (12 warps: 3 uneven rounds), and a slice of
+    // 125 k pixels (1 MP pixel-sharded over 8 GPUs) runs as 245 tiles of 4 warps on all SMs instead of 70 full-width tiles on a
+    // quarter of them.  Ties go to the wider tile (fewer, longer bulk copies).
     const long long slots = static_cast<long long>(sms) * per_sm;
     int best_w = kW;
-    if ((static_cast<long long>(a.npix) + kW * 128 - 1) / (kW * 128) > slots) {
-        double best_cost = -1.0;
-        for (int w = kW; w >= kW - kW * 2 / 7; --w) {
-            const long long tiles_w = (static_cast<long long>(a.npix) + w * 128 - 1) / (w * 128);
-            const double cost = static_cast<double>((tiles_w + slots - 1) / slots) * (2.6 * kW / 14.0 + w);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
-        }
+    double best_cost = -1.0;
+    for (int w = kW; w >= 1; --w) {
+        const long long tiles_w = (static_cast<long long>(a.npix) + w * 128 - 1) / (w * 128);
+        const double cost = static_cast<double>((tiles_w + slots - 1) / slots) * (2.6 * kW / 14.0 + w);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
     }
     if (const char* ov = getenv("MDC_STREAM_WARPS")) {      // measurement knob
         const int w = atoi(ov);

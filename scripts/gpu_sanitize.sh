@@ -3,7 +3,7 @@
 # rmse: bulk-copy ring and generic loaders), device distortCoordinates and the vignetteCalib kernels: memcheck, racecheck, synccheck.
 set -u
 mkdir -p gpurun_out
-cat > /tmp/san.py <<'PY'
+cat > gpurun_out/san.py <<'PY'
 import sys, tempfile, numpy as np, torch
 sys.path.insert(0, '.')
 from mono_dataset_code_b200 import api, synthetic as S
@@ -18,7 +18,7 @@ for tma in (1, 0):
         out = prep.prepare_device(fr, True, True, True, True, levels=lv)
 torch.cuda.synchronize()
 ctx = api.Context(None, None, 0)
-for n, npix in ((21, 1536 * 3 + 48), (9, 1001)):          # bulk-copy ring (3 full tiles + a partial one), generic loader
+for n, npix in ((21, 1536 * 3 + 48), (200, 3584 * 2 + 256), (9, 1001)):      # bulk-copy ring (full tiles + a partial one; 200 exposures: the G-step folds its limb histograms mid-run), generic loader
     data = torch.randint(0, 256, (n, npix), dtype=torch.uint8, device="cuda")
     t = torch.linspace(0.1, 2, n, dtype=torch.float64, device="cuda")
     G = torch.linspace(0, 255, 256, dtype=torch.float64, device="cuda")
@@ -38,6 +38,6 @@ torch.cuda.synchronize()
 print("done")
 PY
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 10 python /tmp/san.py > gpurun_out/sanitize_$tool.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --print-limit 10 python gpurun_out/san.py > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error|error" gpurun_out/sanitize_$tool.log | grep -v "^Input\|Failed to read" | head -8
 done

@@ -471,6 +471,44 @@ def test_gstep_sums_are_exact_and_repeatable(api, port, npix):
     assert np.array_equal(np.isnan(G.cpu().numpy()), np.isnan(port.gstep(data, t, E2)))
 
 
+def test_streaming_ring_reused_many_times(api, port):
+    """300 exposures = 38 plane groups through the 3-stage bulk-copy ring of the calibrator's streaming kernels: every stage is refilled a
+    dozen times per tile while the consumers are still a group or two behind, and the G-step folds its limb histograms in mid-run.
+    E must be the oracle's bits, G exact, rmse the oracle's count, on every one of several runs (compute-sanitizer's racecheck cannot
+    follow the empty-barrier hand-over of a 1-D bulk copy and reports it as a hazard; this is the functional check of that hand-over)."""
+    import math
+    rng = np.random.default_rng(31)
+    n, npix = 300, 1792 * 3 + 128
+    data = rng.integers(0, 256, (n, npix), dtype=np.uint8)
+    data[:, 5:25] = 255
+    t = rng.uniform(0.05, 20.0, n)
+    G = np.sort(rng.uniform(0.0, 255.0, 256))
+    ctx = api.Context(None, None, 0)
+    d, dt, dG = torch.from_numpy(data).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(G).cuda()
+    E_ref = port.estep(data, t, G)
+    r_ref = port.rmse(data, t, G, E_ref)
+    first = None
+    for _ in range(4):
+        E = torch.zeros(npix, dtype=torch.float64, device="cuda")
+        ctx.estep(d, dt, dG, E)
+        assert_bits_equal(E.cpu().numpy(), E_ref, "E-step over a reused ring")
+        G2 = torch.zeros(256, dtype=torch.float64, device="cuda")
+        ctx.rc_gstep(d, dt, E, G2)
+        r = ctx.rc_rmse(d, dt, dG, E)
+        assert r[1] == r_ref[1] and abs(r[0] - r_ref[0]) <= 1e-9 * abs(r_ref[0])
+        if first is None:
+            first = (G2.cpu().numpy(), r)
+        else:
+            assert_bits_equal(G2.cpu().numpy(), first[0], "G-step over a reused ring, repeated")
+            assert r == first[1]
+    prod = E_ref[None, :] * t[:, None]
+    pmax = np.nanmax(np.abs(E_ref)) * np.abs(t).max()
+    for b in range(0, 255, 17):
+        m = (data == b) & np.isfinite(prod)
+        exact = math.fsum(prod[m].tolist()) / int((data == b).sum())
+        assert abs(first[0][b] - exact) <= 4e-15 * pmax + 1e-15 * abs(exact), b
+
+
 def test_response_calib_loop(api, port):
     """mdc_response_calib = E-init + nits x {G-step, E-step, rescale} against the same loop composed from the oracle."""
     rng = np.random.default_rng(22)
