@@ -7,9 +7,9 @@ cd "$(dirname "$0")/.."
 S="python scripts/ncu_summary.py"
 $S gpurun_out/prof_k1.ncu-rep profiles/r02_k1_ncu_summary.csv --traffic profiles/k1_traffic.json --frames 256 --bytes-per-frame 6553600 \
    --label "K1 fused_prepare_kernel<tma,vig,nopyr,3>, 256 C2 frames, scripts/gpu_prof.sh round 2"
-$S gpurun_out/prof_k1_pyr.ncu-rep profiles/r02_k1_pyramid_ncu_summary.csv --launch 0 --traffic gpurun_out/c3_a.json --frames 256 --bytes-per-frame 8294400 \
+$S gpurun_out/prof_k1_pyr.ncu-rep profiles/r02_k1_pyramid_ncu_summary.csv --launch 1 --traffic gpurun_out/c3_a.json --frames 256 --bytes-per-frame 8294400 \
    --label "K1 pyramid variant fused_prepare_kernel<tma,vig,pyr,2> (levels 0-2), 256 C2 frames"
-$S gpurun_out/prof_k1_pyr.ncu-rep profiles/r02_k2_pyr_down2_ncu_summary.csv --launch 1 --traffic gpurun_out/c3_b.json --frames 256 --bytes-per-frame 8294400 \
+$S gpurun_out/prof_k1_pyr.ncu-rep profiles/r02_k2_pyr_down2_ncu_summary.csv --launch 0 --traffic gpurun_out/c3_b.json --frames 256 --bytes-per-frame 8294400 \
    --label "K2 pyr_down2_kernel (levels 3-4 from level 2), 256 C2 frames"
 python - <<'PY'
 import json
@@ -24,6 +24,7 @@ doc.update({"kernel": a["kernel"] + " + " + b["kernel"].replace("void ", ""), "d
 json.dump(doc, open("profiles/c3_pyramid_traffic.json", "w"), indent=1)
 print("wrote profiles/c3_pyramid_traffic.json")
 PY
+# (the two captured launches of the pyramid step arrive as pyr_down2 of one step, then the fused kernel of the next)
 # rc_stream_kernel launches captured from scripts/estep_time.py: row 0 = E-step, rows 1-4 = G-step (count plane), rows 5-6 = rmse
 $S gpurun_out/prof_calib.ncu-rep profiles/r02_k3_estep_ncu_summary.csv --launch 0 --traffic profiles/c5_estep_traffic.json --frames 1 --bytes-per-frame 1008000000 \
    --label "rc_stream_kernel<EstepOp>, n=1000 x 1 MP, scripts/gpu_prof.sh round 2"
