@@ -13,6 +13,7 @@
 //     description (ITU-T T.81 for the entropy coding); tests/test_jpeg_decoder.py compares the result with cv2's decoder on
 //     grey and colour files of several qualities, sampling modes and restart intervals, byte for byte.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -277,7 +278,12 @@ __attribute__((target("avx2"))) void idct_block_avx2(const int32_t* coef, uint8_
     _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 6 * stride), hi67);
     _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 7 * stride), _mm_unpackhi_epi64(hi67, hi67));
 }
-const bool cpu_has_avx2 = [] { __builtin_cpu_init(); return __builtin_cpu_supports("avx2") != 0; }();
+// MDC_JPEG_SCALAR=1 forces the scalar transform (tests compare both against OpenCV's decoder)
+const bool cpu_has_avx2 = [] {
+    __builtin_cpu_init();
+    const char* e = getenv("MDC_JPEG_SCALAR");
+    return __builtin_cpu_supports("avx2") != 0 && !(e && e[0] == '1');
+}();
 #endif
 
 // a block whose AC coefficients are all zero: every sample is the rounded DC term (what both passes' shortcuts give)

@@ -137,3 +137,28 @@ def test_oversubscribed_huffman_table_is_rejected(tmp_path):
             assert got is None and b"Huffman" in _lib.lib.mdc_last_error()
         else:       # 255 codes of length 9 fit the code space: a legal (if useless) table, decoded or rejected later without a crash
             assert got is None or got.shape == img.shape
+
+
+def test_scalar_and_avx2_transforms_agree_with_opencv(tmp_path):
+    """The inverse DCT exists twice (AVX2, chosen at run time, and the portable 64-bit scalar code).  Whatever this machine picks is
+    what the tests above exercise; here a child process forces the scalar one (MDC_JPEG_SCALAR=1) and both must return OpenCV's bytes."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(4)
+    blobs, expect = [], []
+    for kind, quality in CASES:
+        img = scene(rng, 120, 200, kind)
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality])
+        assert ok
+        blobs.append(enc.tobytes())
+        expect.append(cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+    seq = sequence_of(tmp_path, blobs)
+    for i, exp in enumerate(expect):
+        assert np.array_equal(seq.getImageRaw_internal(i), exp)
+    np.save(tmp_path / "expect.npy", np.stack(expect))
+    child = ("import sys, numpy as np; sys.path.insert(0, %r); from mono_dataset_code_b200 import api; "
+             "s = api.Sequence(%r); e = np.load(%r); "
+             "bad = [i for i in range(len(e)) if not np.array_equal(s.getImageRaw_internal(i), e[i])]; print('BAD', bad); sys.exit(1 if bad else 0)"
+             % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path), str(tmp_path / "expect.npy")))
+    r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, MDC_JPEG_SCALAR="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
