@@ -409,14 +409,17 @@ def sharded_estep_leg(args, ctx, comm, dev, rank, world, peak, barrier):
         b.record(); torch.cuda.synchronize()
         return max_over_ranks(a.elapsed_time(b) / reps, dev, world)
     est_ms = ms_of(lambda: ctx.estep(data, t_exp, G_tab, E))
-    gsum = torch.zeros(256, dtype=torch.float64, device=dev)
+    scale4, limbs = torch.zeros(4, dtype=torch.int64, device=dev), torch.zeros(768, dtype=torch.int64, device=dev)
+    special = torch.zeros(256, dtype=torch.float64, device=dev)
     gnum = torch.zeros(256, dtype=torch.int64, device=dev)
     G_new = torch.zeros_like(G_tab)
 
-    def gstep():
-        ctx.rc_gstep_accumulate(data, t_exp, E, gsum, gnum, False)
-        dist.all_reduce(gsum); dist.all_reduce(gnum)
-        ctx.rc_gstep_finish(gsum, gnum, G_new)
+    def gstep():      # sums exact across ranks: scale (MAX), integer limbs + side sums + counts (SUM), finish
+        ctx.rc_gstep_scale(E, t_exp, scale4)
+        dist.all_reduce(scale4, op=dist.ReduceOp.MAX)
+        ctx.rc_gstep_accumulate_exact(data, t_exp, E, scale4, limbs, special, gnum, False)
+        dist.all_reduce(limbs); dist.all_reduce(special); dist.all_reduce(gnum)
+        ctx.rc_gstep_finish_exact(scale4, limbs, special, gnum, G_new)
     g_ms = ms_of(gstep, 3)
     acc = torch.zeros(2, dtype=torch.float64, device=dev)
 
@@ -449,7 +452,7 @@ def sharded_estep_leg(args, ctx, comm, dev, rank, world, peak, barrier):
     return {"ms_per_pass": est_ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (est_ms * 1e-3) / 1e9,
             "frac_of_hbm_peak": alg / (est_ms * 1e-3) / 1e9 / (peak * world), "workload": "n=1000 x 1 MP u8 -> f64 E[1 MP]",
             "sharding": f"pixel-sharded over {world} ranks ({hi - lo} pixels on rank 0), strong scaling", "gstep_ms": g_ms, "rmse_ms": r_ms,
-            "loop_iteration_ms": loop_ms, "loop": how, "collectives_per_iteration": "1 x allreduce(256 f64) [+256 u64 once], 3 x allreduce(2 f64)",
+            "loop_iteration_ms": loop_ms, "loop": how, "collectives_per_iteration": "G-step: allreduce MAX(4 u64), SUM(768 i64), SUM(256 f64) [+ SUM(256 u64) once]; 3 x allreduce SUM(2 f64) for rmse",
             "G_identical_on_all_ranks": same}
 
 

@@ -279,6 +279,20 @@ int mdc_rc_gstep_accumulate(mdc_ctx* c, const uint8_t* d_data, int n, int npix, 
 int mdc_rc_gstep_finish(mdc_ctx* c, const double* d_gsum256, const unsigned long long* d_gnum256, double* d_G, mdc_stream stream);
 int mdc_rc_rmse_accumulate(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_G, const double* d_E,
                            double* d_acc2, mdc_stream stream);
+/* The G-step of a pixel-sharded run with sums that are exact ACROSS ranks, so that G (and therefore E) comes out bit-identical for
+ * any number of ranks, 1 included (mdc_rc_gstep / mdc_response_calib compute the same bits).  The per-rank sums of
+ * mdc_rc_gstep_accumulate are exact integers that are rounded to fp64 before the all-reduce; here they travel as integers:
+ *   mdc_rc_gstep_scale             d_scale4 (4 x u64) = bit patterns of the largest finite |E|, |t| of this rank's pixels and a flag
+ *                                  for non-finite exposure times — all-reduce(MAX) so that every rank scales alike, then
+ *   mdc_rc_gstep_accumulate_exact  d_limbs768 (3 x 256 int64: each bin's 128-bit fixed-point sum as three 43-bit limbs),
+ *                                  d_special256 (fp64 sums of non-finite products) and d_gnum256 as above — all-reduce(SUM) each, then
+ *   mdc_rc_gstep_finish_exact      G from the summed limbs: limbs -> 128-bit integer -> fp64 -> / gnum, gaps extrapolated (:300-304). */
+int mdc_rc_gstep_scale(mdc_ctx* c, const double* d_E, int npix, const double* d_t, int n, unsigned long long* d_scale4, mdc_stream stream);
+int mdc_rc_gstep_accumulate_exact(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E,
+                                  const unsigned long long* d_scale4, long long* d_limbs768, double* d_special256,
+                                  unsigned long long* d_gnum256, int reuse_counts, mdc_stream stream);
+int mdc_rc_gstep_finish_exact(mdc_ctx* c, const unsigned long long* d_scale4, const long long* d_limbs768, const double* d_special256,
+                              const unsigned long long* d_gnum256, double* d_G, mdc_stream stream);
 
 /* -------------------------------------------------------------------------------------
  * Host-buffer entry points (what the compat classes call): H2D copy, kernels, D2H copy.

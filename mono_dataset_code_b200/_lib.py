@@ -86,6 +86,9 @@ SIGNATURES = {
     "mdc_response_calib": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(C.c_double)]),
     "mdc_rc_gstep_accumulate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "mdc_rc_gstep_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mdc_rc_gstep_scale": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "mdc_rc_gstep_accumulate_exact": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mdc_rc_gstep_finish_exact": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdc_rc_rmse_accumulate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mdc_unmap_u8_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint]),
     "mdc_undistort_u8_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),

@@ -353,6 +353,21 @@ class Context:
         check(lib.mdc_rc_gstep_finish(self._h, C.c_void_p(gsum.data_ptr()), C.c_void_p(gnum.data_ptr()), C.c_void_p(G.data_ptr()),
                                       self._stream(G)), "mdc_rc_gstep_finish")
 
+    # the G-step with sums that are exact across ranks: scale4 i64[4] (all-reduce MAX), limbs i64[768] + special f64[256] (all-reduce SUM)
+    def rc_gstep_scale(self, E, t, scale4):
+        check(lib.mdc_rc_gstep_scale(self._h, C.c_void_p(E.data_ptr()), E.shape[0], C.c_void_p(t.data_ptr()), t.shape[0],
+                                     C.c_void_p(scale4.data_ptr()), self._stream(E)), "mdc_rc_gstep_scale")
+
+    def rc_gstep_accumulate_exact(self, data, t, E, scale4, limbs, special, gnum, reuse_counts=False):
+        check(lib.mdc_rc_gstep_accumulate_exact(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
+                                                C.c_void_p(E.data_ptr()), C.c_void_p(scale4.data_ptr()), C.c_void_p(limbs.data_ptr()),
+                                                C.c_void_p(special.data_ptr()), C.c_void_p(gnum.data_ptr()), int(bool(reuse_counts)),
+                                                self._stream(data)), "mdc_rc_gstep_accumulate_exact")
+
+    def rc_gstep_finish_exact(self, scale4, limbs, special, gnum, G):
+        check(lib.mdc_rc_gstep_finish_exact(self._h, C.c_void_p(scale4.data_ptr()), C.c_void_p(limbs.data_ptr()), C.c_void_p(special.data_ptr()),
+                                            C.c_void_p(gnum.data_ptr()), C.c_void_p(G.data_ptr()), self._stream(G)), "mdc_rc_gstep_finish_exact")
+
     def rc_rmse_accumulate(self, data, t, G, E, acc):
         check(lib.mdc_rc_rmse_accumulate(self._h, C.c_void_p(data.data_ptr()), data.shape[0], data.shape[1], C.c_void_p(t.data_ptr()),
                                          C.c_void_p(G.data_ptr()), C.c_void_p(E.data_ptr()), C.c_void_p(acc.data_ptr()), self._stream(data)),

@@ -988,6 +988,41 @@ extern "C" int mdc_rc_gstep_accumulate(mdc_ctx* c, const uint8_t* d_data, int n,
     c->launches += (npix > 0 && n > 0) ? 3 : 1;      // scale, accumulate, convert
     return finish(c, stream, s);
 }
+// ---- the same G-step with sums that are exact ACROSS ranks (include/mdc_b200.h)
+extern "C" int mdc_rc_gstep_scale(mdc_ctx* c, const double* d_E, int npix, const double* d_t, int n, unsigned long long* d_scale4, mdc_stream stream) {
+    if (!c || !d_scale4 || n < 0 || npix < 0 || (npix > 0 && n > 0 && (!d_E || !d_t))) { mdc_set_error("mdc_rc_gstep_scale: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_rc_gstep_scale(d_E, npix, d_t, n, d_scale4, s));
+    c->launches += (npix > 0 && n > 0) ? 1 : 0;
+    return finish(c, stream, s);
+}
+extern "C" int mdc_rc_gstep_accumulate_exact(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* d_t, const double* d_E,
+                                             const unsigned long long* d_scale4, long long* d_limbs768, double* d_special256,
+                                             unsigned long long* d_gnum256, int reuse_counts, mdc_stream stream) {
+    if (!c || !d_t || !d_scale4 || !d_limbs768 || !d_special256 || !d_gnum256 || n < 0 || npix < 0 || (npix > 0 && n > 0 && (!d_data || !d_E))) {
+        mdc_set_error("mdc_rc_gstep_accumulate_exact: bad argument");
+        return MDC_ERR_INVALID_ARG;
+    }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if (reuse_counts && npix > 0 && n > 0 && !rc_counts_reusable(d_data, npix)) {
+        mdc_set_error("mdc_rc_gstep_accumulate_exact: reuse_counts needs a 16-byte aligned slice of a multiple of 16 pixels");
+        return MDC_ERR_UNSUPPORTED;
+    }
+    CU_CHECK(launch_rc_gstep_accum_exact(d_data, n, npix, d_t, d_E, d_scale4, d_limbs768, d_special256, d_gnum256, reuse_counts != 0, c->d_rc + kRcFxOffset, s));
+    c->launches += (npix > 0 && n > 0) ? 2 : 1;      // histogram pass, split
+    return finish(c, stream, s);
+}
+extern "C" int mdc_rc_gstep_finish_exact(mdc_ctx* c, const unsigned long long* d_scale4, const long long* d_limbs768, const double* d_special256,
+                                         const unsigned long long* d_gnum256, double* d_G, mdc_stream stream) {
+    if (!c || !d_scale4 || !d_limbs768 || !d_special256 || !d_gnum256 || !d_G) { mdc_set_error("mdc_rc_gstep_finish_exact: bad argument"); return MDC_ERR_INVALID_ARG; }
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    CU_CHECK(launch_rc_gstep_finish_exact(d_scale4, d_limbs768, d_special256, d_gnum256, c->d_rc, d_G, s));      // d_rc[0..255]: the joined sums
+    c->launches += 2;
+    return finish(c, stream, s);
+}
 extern "C" int mdc_rc_gstep_finish(mdc_ctx* c, const double* d_gsum256, const unsigned long long* d_gnum256, double* d_G, mdc_stream stream) {
     if (!c || !d_gsum256 || !d_gnum256 || !d_G) { mdc_set_error("mdc_rc_gstep_finish: bad argument"); return MDC_ERR_INVALID_ARG; }
     CU_CHECK(cudaSetDevice(c->device));

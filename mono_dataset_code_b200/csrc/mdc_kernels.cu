@@ -1314,7 +1314,9 @@ struct EstepOp {
 // into 64-bit totals long before a limb can overflow.
 constexpr double kFxMagic = 6755399441055744.0;      // 1.5 * 2^52
 constexpr double kFxLimit = 281474976710656.0;       // 2^48: scaled products stay below it
-struct GstepScale { unsigned long long max_e_bits, max_t_bits; unsigned bad_t; };      // bit patterns of max finite |E[k]|, |t[i]| (non-negative doubles order like integers); bad_t: a non-finite exposure time exists
+// bit patterns of max finite |E[k]|, |t[i]| (non-negative doubles order like integers); bad_t != 0: a non-finite exposure time exists.
+// Four u64 words, so that the ranks of a pixel-sharded run can agree on one scale with a single all-reduce(MAX).
+struct GstepScale { unsigned long long max_e_bits, max_t_bits, bad_t, reserved; };
 
 // power of two 2^s with |E*t| * 2^s < 2^48 for all finite samples; kFxNoScale if no such bound exists (the largest product overflows
 // or an exposure time is not finite): every sample is then range-checked on its own
@@ -1700,7 +1702,7 @@ __global__ void __launch_bounds__(256) rc_gstep_scale_kernel(const double* __res
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const unsigned long long v = static_cast<unsigned long long>(__double_as_longlong(t[i])) & 0x7fffffffffffffffull;
-            if (v >= 0x7ff0000000000000ull) scale->bad_t = 1u;
+            if (v >= 0x7ff0000000000000ull) scale->bad_t = 1ull;
             else if (v > mt) mt = v;
         }
 #pragma unroll
@@ -1749,13 +1751,34 @@ __global__ void __launch_bounds__(256) rc_gstep_accum_kernel(const uint8_t* __re
 }
 
 // gsum[b] = (hi * 2^64 + lo) * 2^-s + special[b]: the 128-bit sums back in fp64 (two roundings at most, the same on every run)
+__device__ __forceinline__ double fx_to_double(unsigned long long lo, unsigned long long hi, const GstepScale& scale, double special) {
+    int s = gstep_scale_exponent(scale);
+    if (s == kFxNoScale) s = 0;
+    const double h = __dmul_rn(static_cast<double>(static_cast<long long>(hi)), 18446744073709551616.0);
+    return __dadd_rn(scalbn(__dadd_rn(h, static_cast<double>(lo)), -s), special);
+}
 __global__ void __launch_bounds__(256) rc_gstep_convert_kernel(GstepFx fx, double* __restrict__ gsum) {
     const int b = threadIdx.x;
-    int s = gstep_scale_exponent(*fx.scale);
-    if (s == kFxNoScale) s = 0;
-    const double hi = __dmul_rn(static_cast<double>(static_cast<long long>(fx.hi[b])), 18446744073709551616.0);
-    const double v = __dadd_rn(hi, static_cast<double>(fx.lo[b]));
-    gsum[b] = __dadd_rn(scalbn(v, -s), fx.special[b]);
+    gsum[b] = fx_to_double(fx.lo[b], fx.hi[b], *fx.scale, fx.special[b]);
+}
+// Pixel-sharded runs add the ranks' sums as integers, so that G does not depend on the number of ranks: each 128-bit sum travels as
+// three signed limbs of 43 bits (limbs[b], limbs[256 + b], limbs[512 + b]), which an all-reduce(SUM) over any realistic number of
+// ranks cannot overflow, and is put together again afterwards.
+constexpr int kFxLimbBits = 43;
+__global__ void __launch_bounds__(256) rc_gstep_split_kernel(const unsigned long long* __restrict__ lo, const unsigned long long* __restrict__ hi,
+                                                             long long* __restrict__ limbs) {
+    const int b = threadIdx.x;
+    const __int128 v = (static_cast<__int128>(static_cast<long long>(hi[b])) << 64) | static_cast<__int128>(lo[b]);
+    const long long mask = (1ll << kFxLimbBits) - 1;
+    limbs[b] = static_cast<long long>(v) & mask;
+    limbs[256 + b] = static_cast<long long>(v >> kFxLimbBits) & mask;
+    limbs[512 + b] = static_cast<long long>(v >> (2 * kFxLimbBits));      // arithmetic shift: carries the sign
+}
+__global__ void __launch_bounds__(256) rc_gstep_join_kernel(const long long* __restrict__ limbs, const double* __restrict__ special,
+                                                            const GstepScale* __restrict__ scale, double* __restrict__ gsum) {
+    const int b = threadIdx.x;
+    const __int128 v = static_cast<__int128>(limbs[b]) + (static_cast<__int128>(limbs[256 + b]) << kFxLimbBits) + (static_cast<__int128>(limbs[512 + b]) << (2 * kFxLimbBits));
+    gsum[b] = fx_to_double(static_cast<unsigned long long>(v), static_cast<unsigned long long>(static_cast<long long>(v >> 64)), *scale, special[b]);
 }
 
 // G[i] = GSum[i]/GNum[i]; non-finite entries (empty bins) with i > 1 are extrapolated linearly from the two entries below, :300-304.
@@ -1843,36 +1866,64 @@ cudaError_t launch_rc_einit(const uint8_t* data, int n, int npix, double* E, cud
 //   accumulate  gsum[b] = sum E[k]*t[i], gnum[b] = count over THIS pixel range (main_responseCalib.cpp:290-299); with reuse_counts the
 //               caller's gnum (which depends on the images only) is kept and only the sums are rebuilt
 //   finish      G = gsum/gnum + sequential gap extrapolation (:300-304)
-cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
-                                  bool reuse_counts, void* fx_scratch, cudaStream_t s) {
-    // fx_scratch (kGstepFxScratchBytes): scale | lo[256] | hi[256] | special[256]
-    cudaError_t e = cudaMemsetAsync(fx_scratch, 0, kGstepFxScratchBytes, s);
-    if (e != cudaSuccess) return e;
+// fx_scratch (kGstepFxScratchBytes): scale | lo[256] | hi[256] | special[256]
+static GstepFx fx_of(void* fx_scratch) {
     GstepFx fx;
     fx.scale = static_cast<GstepScale*>(fx_scratch);
     fx.lo = reinterpret_cast<unsigned long long*>(static_cast<char*>(fx_scratch) + 64);
     fx.hi = fx.lo + 256;
     fx.special = reinterpret_cast<double*>(fx.hi + 256);
+    return fx;
+}
+// largest finite |E|, |t| of this pixel range -> scale4 (GstepScale as four u64 words)
+cudaError_t launch_rc_gstep_scale(const double* E, int npix, const double* t, int n, void* scale4, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(scale4, 0, sizeof(GstepScale), s);
+    if (e != cudaSuccess || npix <= 0 || n <= 0) return e;
+    rc_gstep_scale_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(E, static_cast<size_t>(npix), t, n, static_cast<GstepScale*>(scale4));
+    return cudaGetLastError();
+}
+// the histogram pass itself: fx.scale must hold the scale (of this range, or agreed between ranks); lo / hi / special are rebuilt
+static cudaError_t gstep_histogram(const uint8_t* data, int n, int npix, const double* t, const double* E, const GstepFx& fx, unsigned long long* gnum,
+                                   bool reuse_counts, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(fx.lo, 0, 2 * 256 * sizeof(unsigned long long), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fx.special, 0, 256 * sizeof(double), s);
+    if (e == cudaSuccess && !reuse_counts) e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess || npix <= 0 || n <= 0) return e;
     const bool stream = stream_ok(data, npix);
-    if (!reuse_counts) {
-        e = cudaMemsetAsync(gnum, 0, 256 * sizeof(unsigned long long), s);
-        if (e != cudaSuccess) return e;
+    if (reuse_counts && !stream) return cudaErrorNotSupported;      // the generic kernel always counts (callers check rc_counts_reusable first)
+    if (stream) {
+        const StreamArgs a{data, n, static_cast<uint32_t>(npix), t, kEbWarps};
+        return reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, fx, gnum}, s)
+                            : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, fx, gnum}, s);
     }
-    if (npix > 0 && n > 0) {
-        if (reuse_counts && !stream) return cudaErrorNotSupported;      // the generic kernel always counts (callers check rc_counts_reusable first)
-        rc_gstep_scale_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(E, static_cast<size_t>(npix), t, n, fx.scale);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (stream) {
-            const StreamArgs a{data, n, static_cast<uint32_t>(npix), t, kEbWarps};
-            e = reuse_counts ? launch_stream<GstepOp<false>>(a, GstepOp<false>::Params{E, fx, gnum}, s)
-                             : launch_stream<GstepOp<true>>(a, GstepOp<true>::Params{E, fx, gnum}, s);
-            if (e != cudaSuccess) return e;
-        } else {
-            rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, fx, gnum);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        }
-    }
+    rc_gstep_accum_kernel<<<rc_blocks(static_cast<size_t>(npix)), 256, 0, s>>>(data, n, static_cast<size_t>(npix), t, E, fx, gnum);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
+                                  bool reuse_counts, void* fx_scratch, cudaStream_t s) {
+    const GstepFx fx = fx_of(fx_scratch);
+    cudaError_t e = launch_rc_gstep_scale(E, npix, t, n, fx.scale, s);
+    if (e == cudaSuccess) e = gstep_histogram(data, n, npix, t, E, fx, gnum, reuse_counts, s);
+    if (e != cudaSuccess) return e;
     rc_gstep_convert_kernel<<<1, 256, 0, s>>>(fx, gsum);
+    return cudaGetLastError();
+}
+// the same pass for one rank of a pixel-sharded run: the scale comes from the caller (all-reduced MAX of launch_rc_gstep_scale's result),
+// the sums leave as integer limbs (limbs768, all-reduce SUM) + special256 (fp64, all-reduce SUM) — see rc_gstep_split_kernel
+cudaError_t launch_rc_gstep_accum_exact(const uint8_t* data, int n, int npix, const double* t, const double* E, const void* scale4, long long* limbs768,
+                                        double* special256, unsigned long long* gnum, bool reuse_counts, void* fx_scratch, cudaStream_t s) {
+    GstepFx fx = fx_of(fx_scratch);
+    fx.scale = const_cast<GstepScale*>(static_cast<const GstepScale*>(scale4));
+    fx.special = special256;
+    cudaError_t e = gstep_histogram(data, n, npix, t, E, fx, gnum, reuse_counts, s);
+    if (e != cudaSuccess) return e;
+    rc_gstep_split_kernel<<<1, 256, 0, s>>>(fx.lo, fx.hi, limbs768);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_gstep_finish_exact(const void* scale4, const long long* limbs768, const double* special256, const unsigned long long* gnum,
+                                         double* gsum_scratch, double* G, cudaStream_t s) {
+    rc_gstep_join_kernel<<<1, 256, 0, s>>>(limbs768, special256, static_cast<const GstepScale*>(scale4), gsum_scratch);
+    rc_gstep_finish_kernel<<<1, 256, 0, s>>>(gsum_scratch, gnum, G);
     return cudaGetLastError();
 }
 cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s) {

@@ -103,6 +103,13 @@ cudaError_t launch_rc_gstep(const uint8_t* data, int n, int npix, const double* 
 cudaError_t launch_rc_gstep_accum(const uint8_t* data, int n, int npix, const double* t, const double* E, double* gsum, unsigned long long* gnum,
                                   bool reuse_counts, void* fx_scratch, cudaStream_t s);
 cudaError_t launch_rc_gstep_finish(const double* gsum, const unsigned long long* gnum, double* G, cudaStream_t s);
+// the G-step of one rank of a pixel-sharded run, with sums that are exact across ranks: scale (four u64 words; all-reduce MAX) ->
+// accumulate (limbs768: 3 x 256 int64, special256: 256 fp64, both all-reduce SUM) -> finish.  See mdc_kernels.cu.
+cudaError_t launch_rc_gstep_scale(const double* E, int npix, const double* t, int n, void* scale4, cudaStream_t s);
+cudaError_t launch_rc_gstep_accum_exact(const uint8_t* data, int n, int npix, const double* t, const double* E, const void* scale4, long long* limbs768,
+                                        double* special256, unsigned long long* gnum, bool reuse_counts, void* fx_scratch, cudaStream_t s);
+cudaError_t launch_rc_gstep_finish_exact(const void* scale4, const long long* limbs768, const double* special256, const unsigned long long* gnum,
+                                         double* gsum_scratch, double* G, cudaStream_t s);
 bool rc_counts_reusable(const uint8_t* data, int npix);      // reuse_counts is only available on the bulk-copy streaming path
 cudaError_t launch_rc_rescale(int npix, double* E, double* G, double* factor, cudaStream_t s);
 constexpr int kRmsePartialPairs = 2048;      // rmse: capacity of the per-CTA partial scratch ({error, count} pairs)

@@ -94,8 +94,9 @@ extern "C" int mdc_nccl_version(void) { int v = 0; ncclGetVersion(&v); return v;
 
 // ---------------------------------------------------------------- pixel-sharded responseCalib
 // main(), main_responseCalib.cpp:281-362, with the image stack split by pixel range: every pass is per-pixel work on the local
-// slice; the G-step's 2 x 256 accumulators (:290-299) and rmse's {error, count} pair (:50-69) are summed across ranks with
-// ncclAllReduce — 4 KB and 16 bytes per call, latency-bound on NVLink — and then finished identically on every rank.
+// slice; the G-step's sums (:290-299) are added across ranks as integers — one all-reduce(MAX) of the scale inputs, then
+// all-reduce(SUM) of 768 int64 limbs, 256 fp64 side sums and, once, 256 counts — so that G and E are bit-identical for any number of
+// ranks; rmse's {error, count} pair (:50-69) is summed as fp64.  All of it is latency-bound on NVLink (<= 6 KB per call).
 extern "C" int mdc_response_calib_sharded(mdc_ctx* c, void* nccl_comm, int device, const uint8_t* d_data_local, int n, int npix_local,
                                           const double* d_t, int nits, double* d_E_local, double* d_G, double* log_host) {
     if (!c || !nccl_comm || !d_t || !d_G || n < 1 || npix_local < 0 || nits < 0) return MDC_ERR_INVALID_ARG;
@@ -103,11 +104,13 @@ extern "C" int mdc_response_calib_sharded(mdc_ctx* c, void* nccl_comm, int devic
     NC_CHECK(cudaSetDevice(device) == cudaSuccess, MDC_ERR_CUDA);
     cudaStream_t s;
     NC_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess, MDC_ERR_CUDA);
-    double* scratch = nullptr;                                   // gsum[256] | gnum[256] (u64) | acc[2]
-    NC_CHECK(cudaMalloc(&scratch, (256 + 256 + 2) * sizeof(double)) == cudaSuccess, MDC_ERR_CUDA);
-    double* gsum = scratch;
+    double* scratch = nullptr;                                   // special[256] | gnum[256] (u64) | acc[2] | scale[4] (u64) | limbs[768] (i64)
+    NC_CHECK(cudaMalloc(&scratch, (256 + 256 + 2 + 4 + 768) * sizeof(double)) == cudaSuccess, MDC_ERR_CUDA);
+    double* special = scratch;
     unsigned long long* gnum = reinterpret_cast<unsigned long long*>(scratch + 256);
     double* acc = scratch + 512;
+    unsigned long long* scale = reinterpret_cast<unsigned long long*>(scratch + 514);
+    long long* limbs = reinterpret_cast<long long*>(scratch + 518);
     int rc = MDC_OK;
     auto rmse = [&](double out[2]) -> int {
         int r = mdc_rc_rmse_accumulate(c, d_data_local, n, npix_local, d_t, d_G, d_E_local, acc, s);
@@ -136,11 +139,15 @@ extern "C" int mdc_response_calib_sharded(mdc_ctx* c, void* nccl_comm, int devic
     for (int it = 0; it < nits && rc == MDC_OK; ++it) {
         double r[2], row[4] = {0, 0, 0, 0};
         const bool reuse = it > 0 && reusable;
-        rc = mdc_rc_gstep_accumulate(c, d_data_local, n, npix_local, d_t, d_E_local, gsum, gnum, reuse ? 1 : 0, s);
+        // G-step with sums that are exact across ranks: one scale for all (MAX), integer limbs + fp64 side sums (SUM)
+        if ((rc = mdc_rc_gstep_scale(c, d_E_local, npix_local, d_t, n, scale, s)) != MDC_OK) break;
+        if (ncclAllReduce(scale, scale, 4, ncclUint64, ncclMax, comm, s) != ncclSuccess) { rc = MDC_ERR_CUDA; break; }
+        rc = mdc_rc_gstep_accumulate_exact(c, d_data_local, n, npix_local, d_t, d_E_local, scale, limbs, special, gnum, reuse ? 1 : 0, s);
         if (rc != MDC_OK) break;
-        if (ncclAllReduce(gsum, gsum, 256, ncclDouble, ncclSum, comm, s) != ncclSuccess) { rc = MDC_ERR_CUDA; break; }
+        if (ncclAllReduce(limbs, limbs, 768, ncclInt64, ncclSum, comm, s) != ncclSuccess) { rc = MDC_ERR_CUDA; break; }
+        if (ncclAllReduce(special, special, 256, ncclDouble, ncclSum, comm, s) != ncclSuccess) { rc = MDC_ERR_CUDA; break; }
         if (!reuse && ncclAllReduce(gnum, gnum, 256, ncclUint64, ncclSum, comm, s) != ncclSuccess) { rc = MDC_ERR_CUDA; break; }
-        if ((rc = mdc_rc_gstep_finish(c, gsum, gnum, d_G, s)) != MDC_OK) break;
+        if ((rc = mdc_rc_gstep_finish_exact(c, scale, limbs, special, gnum, d_G, s)) != MDC_OK) break;
         if ((rc = rmse(r)) != MDC_OK) break;
         row[0] = r[0];
         if (npix_local > 0 && (rc = mdc_estep(c, d_data_local, n, npix_local, d_t, d_G, d_E_local, s)) != MDC_OK) break;

@@ -74,7 +74,9 @@ def response_calib_sharded(ops, data_local, t, nits, E_local, G, group=None):
     import torch.distributed as dist
 
     dev = data_local.device
-    gsum = torch.zeros(256, dtype=torch.float64, device=dev)
+    scale4 = torch.zeros(4, dtype=torch.int64, device=dev)        # bit patterns of max |E|, max |t|, bad-t flag: all-reduce MAX
+    limbs = torch.zeros(768, dtype=torch.int64, device=dev)       # the bins' fixed-point sums as 3 x 43-bit limbs: all-reduce SUM
+    special = torch.zeros(256, dtype=torch.float64, device=dev)   # fp64 sums of non-finite products: all-reduce SUM
     gnum = torch.zeros(256, dtype=torch.int64, device=dev)
     acc = torch.zeros(2, dtype=torch.float64, device=dev)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -85,9 +87,9 @@ def response_calib_sharded(ops, data_local, t, nits, E_local, G, group=None):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         reusable = bool(flag.item())
 
-    def all_reduce(x):
+    def all_reduce(x, op=None):
         if distributed:
-            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(x, op=op or dist.ReduceOp.SUM, group=group)
 
     def rmse():
         ops.rc_rmse_accumulate(data_local, t, G, E_local, acc)
@@ -100,11 +102,15 @@ def response_calib_sharded(ops, data_local, t, nits, E_local, G, group=None):
     log = np.zeros((nits, 4), np.float64)
     for it in range(nits):
         reuse = it > 0 and reusable
-        ops.rc_gstep_accumulate(data_local, t, E_local, gsum, gnum, reuse)
-        all_reduce(gsum)
+        # G-step with sums that are exact across ranks (G, and with it E, does not depend on the number of ranks)
+        ops.rc_gstep_scale(E_local, t, scale4)
+        all_reduce(scale4, dist.ReduceOp.MAX if distributed else None)
+        ops.rc_gstep_accumulate_exact(data_local, t, E_local, scale4, limbs, special, gnum, reuse)
+        all_reduce(limbs)
+        all_reduce(special)
         if not reuse:
             all_reduce(gnum)
-        ops.rc_gstep_finish(gsum, gnum, G)
+        ops.rc_gstep_finish_exact(scale4, limbs, special, gnum, G)
         log[it, 0] = rmse()[0]
         ops.estep(data_local, t, G, E_local)
         log[it, 1] = rmse()[0]

@@ -9,6 +9,7 @@ import os
 import numpy as np
 import pytest
 
+import gstep_fixed_point_spec as fx_spec
 import pyramid_spec
 from conftest import CALIBS, BIG_CALIBS, ROOT, assert_bits_equal
 from mono_dataset_code_b200 import synthetic as S
@@ -450,6 +451,7 @@ def test_gstep_sums_are_exact_and_repeatable(api, port, npix):
     os.environ.pop("MDC_STREAM_WARPS", None)
     for r in runs[1:]:
         assert_bits_equal(r, runs[0], "G-step, repeated / other tile widths")
+    assert_bits_equal(runs[0], fx_spec.gstep(data, t, E), "G-step vs the numpy specification of the fixed-point sums")
     prod = E[None, :] * t[:, None]                         # fp64 products, rounded like the reference rounds them
     G_ref = port.gstep(data, t, E)
     pmax = np.abs(E).max() * np.abs(t).max()
@@ -469,6 +471,7 @@ def test_gstep_sums_are_exact_and_repeatable(api, port, npix):
     G = torch.zeros(256, dtype=torch.float64, device="cuda")
     ctx.rc_gstep(d, dt, torch.from_numpy(E2).cuda(), G)
     assert np.array_equal(np.isnan(G.cpu().numpy()), np.isnan(port.gstep(data, t, E2)))
+    assert_bits_equal(G.cpu().numpy(), fx_spec.gstep(data, t, E2), "G-step with a NaN irradiance vs the specification")
 
 
 def test_streaming_ring_reused_many_times(api, port):
@@ -618,6 +621,22 @@ def test_pixel_sharded_calibrator_partials_one_gpu(api, port, npix, split):
         tot_num += gnum
     G = torch.zeros(256, dtype=torch.float64, device=dev)
     ctx.rc_gstep_finish(tot_sum, tot_num, G)
+    # the same through the rank-count-independent protocol: one scale for both slices (MAX), integer limbs summed -> the unsharded bits
+    scale4, s4 = torch.zeros(4, dtype=torch.int64, device=dev), torch.zeros(4, dtype=torch.int64, device=dev)
+    for s, E in zip(slices, Es):
+        ctx.rc_gstep_scale(E, dt, s4)
+        scale4 = torch.maximum(scale4, s4)
+    limbs, special, gn = (torch.zeros(768, dtype=torch.int64, device=dev), torch.zeros(256, dtype=torch.float64, device=dev),
+                          torch.zeros(256, dtype=torch.int64, device=dev))
+    tot_l, tot_s, tot_n = torch.zeros_like(limbs), torch.zeros_like(special), torch.zeros_like(gn)
+    for s, E in zip(slices, Es):
+        ctx.rc_gstep_accumulate_exact(s, dt, E, scale4, limbs, special, gn, False)
+        tot_l += limbs; tot_s += special; tot_n += gn
+    Gx = torch.zeros(256, dtype=torch.float64, device=dev)
+    ctx.rc_gstep_finish_exact(scale4, tot_l, tot_s, tot_n, Gx)
+    G_whole = torch.zeros(256, dtype=torch.float64, device=dev)
+    ctx.rc_gstep(torch.from_numpy(data).to(dev), dt, torch.cat(Es), G_whole)
+    assert_bits_equal(Gx.cpu().numpy(), G_whole.cpu().numpy(), "G from two slices (exact protocol) vs the unsharded G-step")
     G_ref = port.gstep(data, t, E_ref)
     g = G.cpu().numpy()
     assert np.array_equal(np.isnan(g), np.isnan(G_ref))
@@ -678,7 +697,7 @@ def _sharded_calib_worker(rank, world, port_no, data_path, out_dir, nits):
 
 
 def test_pixel_sharded_calibrator_two_gpus_nccl(api, port, tmp_path):
-    """SURVEY.md §8e row 2 on two GPUs: both ranks end with the same G, equal (<= 1e-10) to the single-GPU loop, through the Python
+    """SURVEY.md §8e row 2 on two GPUs: both ranks end with the same G and E, bit-identical to the single-GPU loop, through the Python
     host loop (torch.distributed NCCL all-reduce) and through the native C++ loop (ncclAllReduce in libmdc_b200_nccl.so)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -701,8 +720,9 @@ def test_pixel_sharded_calibrator_two_gpus_nccl(api, port, tmp_path):
     log1 = ctx.response_calib(d, dt, nits, E1, G1)
     for tag in ("py", "cc"):
         assert np.array_equal(a["G_" + tag], b["G_" + tag], equal_nan=True), tag
-        np.testing.assert_allclose(a["G_" + tag], G1.cpu().numpy(), rtol=1e-10, equal_nan=True)
-        np.testing.assert_allclose(np.concatenate([a["E_" + tag], b["E_" + tag]]), E1.cpu().numpy(), rtol=1e-10, equal_nan=True)
+        # exact integer sums across ranks: not "close", identical
+        assert_bits_equal(a["G_" + tag], G1.cpu().numpy(), f"G on 2 GPUs ({tag}) vs 1 GPU")
+        assert_bits_equal(np.concatenate([a["E_" + tag], b["E_" + tag]]), E1.cpu().numpy(), f"E on 2 GPUs ({tag}) vs 1 GPU")
         np.testing.assert_allclose(a["log_" + tag], log1, rtol=1e-9)
         assert np.array_equal(a["log_" + tag], b["log_" + tag])
 

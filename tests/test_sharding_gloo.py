@@ -7,6 +7,7 @@ import sys
 import numpy as np
 import pytest
 
+import gstep_fixed_point_spec as fx
 from conftest import ROOT
 from mono_dataset_code_b200 import sharding
 
@@ -70,23 +71,22 @@ class NumpyCalibOps:
     def rc_einit(self, data, E):
         E.copy_(__import__("torch").from_numpy(self.port.einit(data.numpy())))
 
-    def rc_gstep_accumulate(self, data, t, E, gsum, gnum, reuse_counts):
+    # the G-step in fixed point, from the numpy specification of what the CUDA kernels compute (tests/gstep_fixed_point_spec.py)
+    def rc_gstep_scale(self, E, t, scale4):
         import torch
-        d = data.numpy()
-        keep = d != 255
-        w = (E.numpy()[None, :] * t.numpy()[:, None])[keep]
-        gsum.copy_(torch.from_numpy(np.bincount(d[keep].ravel(), weights=w.ravel(), minlength=256)[:256]))
-        if not reuse_counts:
-            gnum.copy_(torch.from_numpy(np.bincount(d[keep].ravel(), minlength=256)[:256].astype(np.int64)))
+        scale4.copy_(torch.from_numpy(fx.scale_words(E.numpy(), t.numpy())))
 
-    def rc_gstep_finish(self, gsum, gnum, G):
+    def rc_gstep_accumulate_exact(self, data, t, E, scale4, limbs, special, gnum, reuse_counts):
         import torch
-        with np.errstate(divide="ignore", invalid="ignore"):
-            g = gsum.numpy() / gnum.numpy().astype(np.float64)
-        for i in range(2, 256):                         # main_responseCalib.cpp:300-304, sequential
-            if not np.isfinite(g[i]):
-                g[i] = g[i - 1] + (g[i - 1] - g[i - 2])
-        G.copy_(torch.from_numpy(g))
+        l, sp, cnt = fx.accumulate(data.numpy(), t.numpy(), E.numpy(), scale4.numpy())
+        limbs.copy_(torch.from_numpy(l))
+        special.copy_(torch.from_numpy(sp))
+        if not reuse_counts:
+            gnum.copy_(torch.from_numpy(cnt))
+
+    def rc_gstep_finish_exact(self, scale4, limbs, special, gnum, G):
+        import torch
+        G.copy_(torch.from_numpy(fx.finish(scale4.numpy(), limbs.numpy(), special.numpy(), gnum.numpy())))
 
     def estep(self, data, t, G, E):
         E.copy_(__import__("torch").from_numpy(self.port.estep(data.numpy(), t.numpy(), G.numpy())))
@@ -105,6 +105,7 @@ class NumpyCalibOps:
 
 def _calib_worker(rank, world, port_no, data_path, out_dir, nits):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
     from mono_dataset_code_b200 import sharding as sh
@@ -154,6 +155,12 @@ def test_pixel_sharded_response_calib_world2_gloo(port, tmp_path):
         port.rescale(E, G)
         exp_log[it, 2:] = port.rmse(data, t, G, E)
     got_E = np.concatenate([a["E"], b["E"]])
+    # exact sums across ranks: the same loop on ONE rank (no process group) gives the same bits of G and E
+    import torch
+    E1, G1 = torch.zeros(npix, dtype=torch.float64), torch.zeros(256, dtype=torch.float64)
+    from oracle import loader
+    sharding.response_calib_sharded(NumpyCalibOps(loader.PortOracle()), torch.from_numpy(data), torch.from_numpy(t), nits, E1, G1)
+    assert np.array_equal(a["G"], G1.numpy(), equal_nan=True) and np.array_equal(got_E, E1.numpy(), equal_nan=True)
     np.testing.assert_allclose(a["G"], G, rtol=1e-10, atol=0)
     np.testing.assert_allclose(got_E, E, rtol=1e-10, atol=0, equal_nan=True)
     assert np.isnan(got_E[17]) and np.isnan(E[17])
