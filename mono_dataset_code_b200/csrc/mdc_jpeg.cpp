@@ -26,6 +26,7 @@
 namespace {
 
 constexpr int kLookBits = 9;      // Huffman codes up to this length are resolved by one table look-up
+constexpr int kFastBits = 10;     // window of the combined code + magnitude look-up of the AC tables
 
 struct HuffTable {
     bool defined = false;
@@ -34,23 +35,34 @@ struct HuffTable {
     // canonical decoding tables (T.81 Annex F.2.2.3) + a prefix table for the short codes
     int mincode[17], maxcode[18], valptr[17];
     uint16_t look[1 << kLookBits];      // (code length << 8) | symbol, 0 = longer than kLookBits
-    // AC tables: where code + magnitude bits fit the look-up window and the value fits 8 bits, one look-up yields the whole
-    // coefficient: (value << 8) | (run << 4) | total bits; 0 = take the general path
-    int16_t fast_ac[1 << kLookBits];
-    void build_fast_ac() {
-        for (int i = 0; i < (1 << kLookBits); ++i) {
-            fast_ac[i] = 0;
-            const int e = look[i];
-            if (!e) continue;
-            const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
-            if (!mag || len + mag > kLookBits) continue;
-            int v = ((i << len) & ((1 << kLookBits) - 1)) >> (kLookBits - mag);      // the magnitude bits that follow the code
-            if (v < (1 << (mag - 1))) v += 1 - (1 << mag);                             // T.81 F.2.2.1 EXTEND
-            if (v >= -128 && v <= 127) fast_ac[i] = static_cast<int16_t>(v * 256 + run * 16 + len + mag);
+    // AC tables: a kFastBits-wide window resolves in one look-up every code that fits it TOGETHER with its magnitude bits, and the
+    // two symbols without magnitude bits: entry = (value << 16) | (kind << 9) | (run << 5) | total bits consumed;
+    // kind 0 = not covered (general path), 1 = coefficient, 2 = end of block, 3 = run of 16 zeros
+    int32_t fast[1 << kFastBits];
+    void build_fast() {
+        memset(fast, 0, sizeof fast);
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+            for (int i = 0; i < bits[l]; ++i, ++code, ++k) {
+                if (l > kFastBits) continue;
+                const int run = vals[k] >> 4, mag = vals[k] & 15, spare = kFastBits - l;
+                for (int suffix = 0; suffix < (1 << spare); ++suffix) {
+                    int32_t e = 0;
+                    if (mag == 0) {
+                        e = ((run == 15 ? 3 : 2) << 9) | l;            // anything but ZRL ends the block, like the general path
+                    } else if (mag <= spare) {
+                        int v = suffix >> (spare - mag);                // the magnitude bits that follow the code
+                        if (v < (1 << (mag - 1))) v += 1 - (1 << mag);  // T.81 F.2.2.1 EXTEND
+                        e = (v * 65536) | (1 << 9) | (run << 5) | (l + mag);
+                    }
+                    fast[(code << spare) | suffix] = e;
+                }
+            }
+            code <<= 1;
         }
     }
     // false = over-subscribed table (more codes of some length than the prefix code space has left; libjpeg's
-    // JERR_BAD_HUFF_TABLE).  Must be checked before look[] is filled: such a table would index past its end.
+    // JERR_BAD_HUFF_TABLE).  Must be checked before look[] / fast[] are filled: such a table would index past their end.
     bool build() {
         int code = 0, k = 0;
         memset(look, 0, sizeof look);
@@ -139,6 +151,53 @@ inline int extend(int v, int t) { return (t && v < (1 << (t - 1))) ? v - (1 << t
 
 const uint8_t kZigZag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                              35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// One block: DC difference, then AC coefficients until end of block.  kStore = false for components that are only skipped (chroma of a
+// colour file): same bits consumed, nothing written.  The bit reader is copied into a local so that its state lives in registers (a
+// coefficient store could alias `n` otherwise); at least 32 bits are made available before every symbol — more than the longest
+// code + magnitude — so nothing below checks the fill level again.  Returns < 0 on corrupt data, else 1 if an AC coefficient was stored.
+enum { kBlockBadDc = -1, kBlockBadAc = -2, kBlockBadRun = -3 };
+template <bool kStore>
+inline int decode_block(BitReader& reader, const HuffTable& dct, const HuffTable& act, int& pred, int32_t* coef, const int32_t* qzz) {
+    BitReader br = reader;
+    if (br.n < 32) br.fill();
+    const int t = decode_symbol(br, dct);
+    if (t < 0 || t > 15) return kBlockBadDc;
+    // libjpeg stores coefficients as 16-bit JCOEF: the running DC value wraps there (only corrupt data gets that far)
+    pred = static_cast<int16_t>(static_cast<uint32_t>(pred) + static_cast<uint32_t>(extend(br.bits(t), t)));
+    if (kStore) coef[0] = pred * qzz[0];
+    int any_ac = 0;
+    for (int k = 1; k < 64;) {
+        if (br.n < 32) br.fill();
+        const int32_t fe = act.fast[br.acc >> (64 - kFastBits)];
+        const int kind = (fe >> 9) & 3;
+        if (kind == 1) {                       // code + magnitude in one look-up
+            k += (fe >> 5) & 15;
+            if (k > 63) return kBlockBadRun;
+            br.skip(fe & 31);
+            if (kStore) { coef[kZigZag[k]] = (fe >> 16) * qzz[k]; any_ac = 1; }
+            ++k;
+            continue;
+        }
+        if (kind == 2) { br.skip(fe & 31); break; }
+        if (kind == 3) { br.skip(fe & 31); k += 16; continue; }
+        const int rs = decode_symbol(br, act);
+        if (rs < 0) return kBlockBadAc;
+        const int r = rs >> 4, sz = rs & 15;
+        if (sz == 0) {
+            if (r != 15) break;                // EOB
+            k += 16;
+            continue;
+        }
+        k += r;
+        if (k > 63) return kBlockBadRun;
+        const int v = extend(br.bits(sz), sz);
+        if (kStore) { coef[kZigZag[k]] = v * qzz[k]; any_ac = 1; }
+        ++k;
+    }
+    reader = br;
+    return any_ac;
+}
 
 // ---- inverse DCT, accurate integer method (13-bit constants, 2 guard bits between the passes)
 // Temporaries are 64-bit like libjpeg's (its JLONG is `long`), so no input — not even a corrupt one — can overflow.
@@ -347,7 +406,7 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                 i += total;
                 t.defined = t.build();
                 if (!t.defined) return fail("bad Huffman table (over-subscribed code lengths)");
-                if (tc) t.build_fast_ac();
+                if (tc) t.build_fast();
             }
         } else if (marker == 0xc0 || marker == 0xc1) {         // SOF0 / SOF1 (Huffman, sequential)
             if (seg_len < 6) return fail("bad frame header");
@@ -431,39 +490,10 @@ bool mdc_decode_jpeg_gray(const std::vector<uint8_t>& file, const std::string& n
                         const int bh = single ? 1 : comp.h, bv = single ? 1 : comp.v;
                         for (int by = 0; by < bv; ++by)
                             for (int bx = 0; bx < bh; ++bx) {
-                                // DC
-                                const int t = decode_symbol(br, dc[comp.td]);
-                                if (t < 0 || t > 15) return fail("corrupt JPEG data (DC)");
-                                // libjpeg stores coefficients as 16-bit JCOEF: the running DC value wraps there (only corrupt data gets that far)
-                                comp.pred = static_cast<int16_t>(static_cast<uint32_t>(comp.pred) + static_cast<uint32_t>(extend(br.bits(t), t)));
-                                if (c == 0) coef[0] = comp.pred * qzz[0];
-                                bool any_ac = false;
-                                // AC
-                                const HuffTable& act = ac[comp.ta];
-                                for (int k = 1; k < 64;) {
-                                    const int fa = act.fast_ac[br.peek(kLookBits)];
-                                    if (fa) {                      // code + magnitude in one look-up
-                                        k += (fa >> 4) & 15;
-                                        if (k > 63) return fail("corrupt JPEG data (run past the block)");
-                                        br.skip(fa & 15);
-                                        if (c == 0) { coef[kZigZag[k]] = (fa >> 8) * qzz[k]; any_ac = true; }
-                                        ++k;
-                                        continue;
-                                    }
-                                    const int rs = decode_symbol(br, act);
-                                    if (rs < 0) return fail("corrupt JPEG data (AC)");
-                                    const int r = rs >> 4, s = rs & 15;
-                                    if (s == 0) {
-                                        if (r != 15) break;      // EOB
-                                        k += 16;
-                                        continue;
-                                    }
-                                    k += r;
-                                    if (k > 63) return fail("corrupt JPEG data (run past the block)");
-                                    const int v = extend(br.bits(s), s);
-                                    if (c == 0) { coef[kZigZag[k]] = v * qzz[k]; any_ac = true; }
-                                    ++k;
-                                }
+                                const int rc = c == 0 ? decode_block<true>(br, dc[comp.td], ac[comp.ta], comp.pred, coef, qzz)
+                                                      : decode_block<false>(br, dc[comp.td], ac[comp.ta], comp.pred, nullptr, qzz);
+                                if (rc < 0) return fail(rc == kBlockBadDc ? "corrupt JPEG data (DC)" : rc == kBlockBadAc ? "corrupt JPEG data (AC)" : "corrupt JPEG data (run past the block)");
+                                const bool any_ac = rc != 0;
                                 if (c == 0) {
                                     const size_t x0 = (static_cast<size_t>(mx) * yh + bx) * 8, y0 = (static_cast<size_t>(my) * yv + by) * 8;
                                     uint8_t* dst = plane.data() + y0 * pw + x0;
