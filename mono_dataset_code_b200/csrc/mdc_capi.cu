@@ -96,7 +96,6 @@ struct mdc_ctx {
     // streams + host pipeline scratch
     cudaStream_t stream = nullptr;
     cudaStream_t pipe_stream[kHostPipeDepth] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_done[kHostPipeDepth] = {nullptr, nullptr, nullptr};      // blocking-sync events: long waits sleep instead of spinning
     uint8_t* pipe_in[kHostPipeDepth] = {nullptr, nullptr, nullptr};
     float* pipe_out[kHostPipeDepth] = {nullptr, nullptr, nullptr};
     size_t pipe_in_bytes = 0, pipe_out_bytes = 0;
@@ -728,7 +727,6 @@ extern "C" void mdc_ctx_destroy(mdc_ctx* c) {
     if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     for (int s = 0; s < kHostPipeDepth; ++s) {
         if (c->pipe_stream[s]) { cudaStreamSynchronize(c->pipe_stream[s]); cudaStreamDestroy(c->pipe_stream[s]); }
-        if (c->pipe_done[s]) cudaEventDestroy(c->pipe_done[s]);
         cudaFree(c->pipe_in[s]); cudaFree(c->pipe_out[s]);
     }
     cudaFree(c->scratch_a); cudaFree(c->scratch_b);
@@ -1218,23 +1216,10 @@ extern "C" int mdc_prepare_batch_host(mdc_ctx* c, const uint8_t* frames, int n_f
     }
     // On any failure the copies of earlier chunks into the caller's buffers may still be in flight on the other pipe streams:
     // drain all of them before returning, so the caller can free or reuse its buffers.
-    // A call with many frames waits for milliseconds: it sleeps on blocking-sync events, so that the waiting thread does not burn one
-    // of the CPUs the decode threads of a sequence feed are rationed (cgroup quotas); short calls spin, which costs ~20 us less.
-    const bool sleep_wait = n_frames >= 32;
     auto drain = [&]() {
         cudaError_t first = cudaSuccess;
-        for (int s = 0; s < kHostPipeDepth; ++s) {
-            if (!c->pipe_stream[s]) continue;
-            cudaError_t e = cudaSuccess;
-            if (sleep_wait && !c->pipe_done[s]) e = cudaEventCreateWithFlags(&c->pipe_done[s], cudaEventBlockingSync | cudaEventDisableTiming);
-            if (sleep_wait && e == cudaSuccess) {
-                e = cudaEventRecord(c->pipe_done[s], c->pipe_stream[s]);
-                if (e == cudaSuccess) e = cudaEventSynchronize(c->pipe_done[s]);
-            } else {
-                e = cudaStreamSynchronize(c->pipe_stream[s]);
-            }
-            if (first == cudaSuccess) first = e;
-        }
+        for (int s = 0; s < kHostPipeDepth; ++s)
+            if (c->pipe_stream[s]) { const cudaError_t e = cudaStreamSynchronize(c->pipe_stream[s]); if (first == cudaSuccess) first = e; }
         return first;
     };
     int k = 0, rc = MDC_OK;
