@@ -467,7 +467,7 @@ def sequence_leg(args, dev, rank, world, local, numa, barrier):
     import torch.distributed as dist
     import cv2
     from mono_dataset_code_b200 import _lib, api, sharding, synthetic as S
-    W, H, K, UNIQUE, CALL = 1920, 1080, 1024, 128, 256      # zip entries, distinct JPEG payloads among them, frames per mdc_seq_prepare call
+    W, H, K, UNIQUE, CALL = 1920, 1080, 1024, 128, 512      # zip entries, distinct JPEG payloads among them, frames per mdc_seq_prepare call
     root = os.path.join(tempfile.gettempdir(), f"mdc_c4_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}")
     if rank == 0:
         os.makedirs(root, exist_ok=True)

@@ -10,6 +10,7 @@
 // The zip reader handles what `zip` / Python's zipfile / the TUM archives produce: stored and deflated entries, no encryption,
 // no zip64 (archives < 4 GB, < 65535 entries), CRC-32 verified.
 #include <algorithm>
+#include <atomic>
 #include <exception>
 #include <cstdio>
 #include <cstring>
@@ -303,8 +304,10 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     for (int l = 0; l < levels; ++l)      // level l of getImage's result: (w >> l) x (h >> l), mdc_prepare_batch
         level_px[static_cast<size_t>(l)] = static_cast<size_t>((rectify ? out_w : in_w) >> l) * static_cast<size_t>((rectify ? out_h : in_h) >> l);
     if (threads < 1) threads = default_decode_threads();
-    // several frames per decode thread and chunk: decode times vary from frame to frame, and a chunk is as slow as its slowest thread
-    const int chunk = std::min(256, std::max(32, 4 * threads));
+    // a chunk is what the GPU side takes at a time: two frames per decode thread (handed out dynamically, so a slow frame or a
+    // descheduled thread does not hold the chunk up), small enough that the un-overlapped head (first decode) and tail (last
+    // H2D / K1 / D2H) of a call stay short
+    const int chunk = std::min(256, std::max(16, 2 * threads));
     std::lock_guard<std::mutex> feed_lock(s->feed_mutex);
     const size_t need = static_cast<size_t>(chunk) * n_in;
     if (s->stage_bytes < need) {
@@ -320,18 +323,20 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
     }
     void* const stage[2] = {s->stage[0], s->stage[1]};
 
-    // Decode pool: `threads` workers live for the whole call.  Worker t decodes frames t, t+threads, ... of chunk k into stage[k & 1],
-    // then moves on to chunk k+1 as soon as the GPU side has released that chunk's buffer (chunk k-1 consumed), so decode of chunk k+1
-    // overlaps H2D / K1 / D2H of chunk k, and nobody creates threads or multi-megabyte buffers per frame.
+    // Decode pool: `threads` workers live for the whole call.  The workers take the frames of chunk k one by one (an atomic counter per
+    // chunk) and decode them into stage[k & 1], then move on to chunk k+1 as soon as the GPU side has released that chunk's buffer
+    // (chunk k-1 consumed), so decode of chunk k+1 overlaps H2D / K1 / D2H of chunk k, and nobody creates multi-megabyte buffers per frame.
     const int n_chunks = (count + chunk - 1) / chunk;
     const int workers = std::min(threads, std::min(count, chunk));
     std::mutex mu;
     std::condition_variable cv;
     std::vector<int> decoded(static_cast<size_t>(n_chunks), 0);      // workers finished with chunk k
+    std::vector<std::atomic<int>> next_frame(static_cast<size_t>(n_chunks));      // next frame of chunk k nobody has taken yet
+    for (auto& a : next_frame) a.store(0, std::memory_order_relaxed);
     int released = 1;                 // chunks whose buffer may be written: 0 .. released (stage[0] and stage[1] are free at the start)
     bool abort = false;
     std::string first_error;
-    auto worker = [&](int t) {
+    auto worker = [&](int) {
         std::vector<uint8_t> px;
         for (int k = 0; k < n_chunks; ++k) {
             {
@@ -342,7 +347,7 @@ extern "C" int mdc_seq_prepare(mdc_ctx* c, const mdc_seq* s, int first, int coun
             const int f0 = k * chunk, n = std::min(chunk, count - f0);
             uint8_t* dst = static_cast<uint8_t*>(stage[k & 1]);
             std::string err;
-            for (int i = t; i < n && err.empty(); i += workers) {
+            for (int i; err.empty() && (i = next_frame[static_cast<size_t>(k)].fetch_add(1, std::memory_order_relaxed)) < n;) {
                 int w = 0, h = 0;
                 if (!read_gray8(s, first + f0 + i, &px, &w, &h)) err = mdc_last_error();
                 else if (w != in_w || h != in_h) {      // BenchmarkDatasetReader.h:194-199
