@@ -253,7 +253,9 @@ int mdc_estep(mdc_ctx* c, const uint8_t* d_data, int n, int npix, const double* 
  *   mdc_rc_einit         E = per-pixel mean over the n images                                          :249-259                       bit-exact
  *   mdc_rc_gstep         G[b] = sum(E[k]*t[i]) / count over samples with value b != 255, gaps extrapolated  :286-304   rounding-level: the products are
  *                        rounded as in the reference and then summed EXACTLY (fixed point), where the reference has one fp64 chain;
- *                        order-independent, so the same bits on every run and for every launch geometry
+ *                        order-independent, so the same bits on every run and for every launch geometry.  (The fixed-point scale
+ *                        comes from the largest finite |E| and |t|; if an exposure time is not finite, or that largest product
+ *                        overflows, there is no common scale and the finite products are summed at unit resolution — garbage in.)
  *   mdc_rc_rescale       factor = 255/G[255]; E *= factor; G *= factor; *factor_host = factor           :350-355                       bit-exact
  *   mdc_rc_rmse          out_host = {1e5*sqrt(mean((G[b]-t*E)^2 * 1e-10)), count}                       :50-69                         rounding-level
  *                        (the reference sums in long double); residuals, finite test and count exact; same bits on every run
