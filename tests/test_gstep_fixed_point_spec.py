@@ -70,7 +70,7 @@ def test_special_values_follow_the_reference(port, case):
         E[::7] *= 1e200
         E[1::7] *= 1e-200
     else:
-        E *= 1e-300
+        E *= 1e-250                                      # (the scale exponent is clamped to +-1000: products below 2^-950 would lose bits)
     with np.errstate(invalid="ignore", over="ignore"):
         G, G_ref = fx.gstep(data, t, E), port.gstep(data, t, E)
     assert np.array_equal(np.isnan(G), np.isnan(G_ref))
@@ -80,7 +80,8 @@ def test_special_values_follow_the_reference(port, case):
         # A non-finite exposure time leaves no common scale (include/mdc_b200.h): the bins it does not touch are summed at unit
         # resolution — each product rounded to an integer — which is what the kernels do, too.  Garbage in, coarse out; never wrong
         # about which bins are infinite.
-        assert np.max(np.abs(G[m] - G_ref[m])) <= 0.5
+        direct = np.array([(data == b).any() and not (data[2] == b).any() for b in range(255)] + [False])      # bins with samples, none from image 2
+        assert direct.sum() > 20 and np.max(np.abs(G[direct] - G_ref[direct])) <= 0.5      # (the other finite entries are extrapolations, :300-304)
         return
     # one scale for all bins: a sample is resolved to 2^-48 of the largest product, so that is the error bound of a bin's mean — bins
     # whose products are all 2^48 times smaller than the largest one (only in "huge_range") come out as 0
