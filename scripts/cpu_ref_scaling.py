@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""How the reference's per-frame path scales over the host threads of this box (bench.py's CPU arm uses all of them):
-frames/s at 1, 8, 16, 32, 64, all threads, pinned and unpinned.  One JSON line each."""
+"""How the reference's per-frame path scales over the host threads of this box: frames/s at 1, 8, 16, 32, 64, all threads, pinned and
+unpinned.  One JSON line each.  (This is the measurement that showed the peak at 16-32 workers — the boxes' 16-CPU cgroup quota —
+after which bench.py's CPU arm started to sweep the worker count instead of using every hardware thread.)"""
 import json
 import os
 import sys
