@@ -29,9 +29,11 @@ int mdc_nccl_version(void);
 
 /* responseCalib's optimisation loop (main_responseCalib.cpp:281-362) PIXEL-SHARDED over the ranks of `nccl_comm`:
  * d_data_local = this rank's slice of every image, [n][npix_local] u8 (slices of a multiple of 16 pixels keep the fast streaming
- * kernels); d_E_local [npix_local]; d_G [256] is replicated — identical on every rank on return.  Per iteration: one ncclAllReduce of
- * 256 doubles (+ 256 u64 counts in the first iteration) for the G-step and three of 2 doubles for the rmse evaluations; E-step, E-init
- * and rescale are collective-free.  log_host as in mdc_response_calib (global rmse / count).  Same call on every rank. */
+ * kernels); d_E_local [npix_local]; d_G [256] is replicated.  The G-step's sums cross the ranks as integers (mdc_rc_gstep_scale /
+ * _accumulate_exact / _finish_exact, include/mdc_b200.h): per iteration ncclAllReduce MAX of 4 u64, SUM of 768 int64 and of 256 fp64
+ * (+ 256 u64 counts in the first iteration), so d_G and d_E_local hold the same bits for ANY number of ranks, mdc_response_calib's
+ * included; the three rmse evaluations all-reduce 2 doubles each; E-step, E-init and rescale are collective-free.  log_host as in
+ * mdc_response_calib (global rmse / count).  Same call on every rank. */
 int mdc_response_calib_sharded(mdc_ctx* c, void* nccl_comm, int device, const uint8_t* d_data_local, int n, int npix_local,
                                const double* d_t, int nits, double* d_E_local, double* d_G, double* log_host);
 
