@@ -162,3 +162,33 @@ def test_scalar_and_avx2_transforms_agree_with_opencv(tmp_path):
              % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path), str(tmp_path / "expect.npy")))
     r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, MDC_JPEG_SCALAR="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_random_sizes_qualities_and_modes_match_opencv(tmp_path):
+    """Property-style sweep (seeded): random sizes incl. non-multiples of the MCU, qualities 1..100, grey / colour with every sampling mode,
+    optimised Huffman tables, restart intervals, progressive rejected — every accepted file decodes to OpenCV's bytes."""
+    rng = np.random.default_rng(2024)
+    sampling = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+                "411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440} if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR") else {}
+    blobs, expect = [], []
+    for _ in range(60):
+        w, h = int(rng.integers(1, 200)), int(rng.integers(1, 160))
+        kind = ("smooth", "noise", "edges", "ramp")[int(rng.integers(0, 4))]
+        img = scene(rng, h, w, kind)
+        params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(1, 101))]
+        if rng.random() < 0.3:
+            params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+        if rng.random() < 0.3:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 9))]
+        if sampling and rng.random() < 0.5:
+            img = np.stack([img, np.roll(img, 3, 1), 255 - img], axis=2)      # a colour file, read as grey
+            params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, list(sampling.values())[int(rng.integers(0, len(sampling)))]]
+        ok, enc = cv2.imencode(".jpg", img, params)
+        assert ok
+        blobs.append(enc.tobytes())
+        expect.append(cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+    seq = sequence_of(tmp_path, blobs)
+    for i, exp in enumerate(expect):
+        got = seq.getImageRaw_internal(i)
+        assert got is not None, f"file {i} rejected"
+        assert got.shape == exp.shape and np.array_equal(got, exp), f"file {i}: {np.count_nonzero(got != exp)} pixels differ"
