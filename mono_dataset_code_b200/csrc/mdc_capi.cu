@@ -682,6 +682,10 @@ extern "C" int mdc_ctx_create_from_device_tables(int device, int in_w, int in_h,
     if (!out) { mdc_set_error("mdc_ctx_create_from_device_tables: out is NULL"); return MDC_ERR_INVALID_ARG; }
     *out = nullptr;
     if (in_w < 2 || in_h < 2) { mdc_set_error("bad input size"); return MDC_ERR_INVALID_ARG; }
+    if (static_cast<long long>(in_w) * in_h > (1LL << 28) || (d_remap_x && (out_w < 1 || out_h < 1 || static_cast<long long>(out_w) * out_h > (1LL << 28)))) {
+        mdc_set_error("image larger than 2^28 pixels");      // same limit as the table builders and the image decoders
+        return MDC_ERR_INVALID_ARG;
+    }
     if ((d_remap_x == nullptr) != (d_remap_y == nullptr)) { mdc_set_error("remap tables must come as a pair"); return MDC_ERR_INVALID_ARG; }
     mdc_ctx* c = new mdc_ctx();
     int rc = ctx_common_init(c, device);

@@ -211,6 +211,10 @@ void mdc_fov_build(mdc_fov* f, int mode, const float out_calib_in[5]) {
     fill_K(f->k_org, f->in_calib, W, H);
 }
 
+// Sizes come from files: everything allocated from them (remap tables, vignette maps, device buffers) stays below 2^28 pixels per image,
+// the limit the image decoders use too, so that a crafted header cannot make an allocation throw across the C ABI.
+static bool size_ok(int w, int h) { return static_cast<long long>(w) * h <= (1LL << 28); }
+
 // -------------------------------------------------------------- FOV model: C entry points
 static int fov_from_file(const char* path, int float_math, mdc_fov** out) {
     if (!out) { mdc_set_error("mdc_fov_create: out is NULL"); return MDC_ERR_INVALID_ARG; }
@@ -265,6 +269,10 @@ static int fov_from_file(const char* path, int float_math, mdc_fov** out) {
         mdc_set_error("camera calibration %s: non-positive image size", path);
         return MDC_ERR_FORMAT;
     }
+    if (!size_ok(f->in_w, f->in_h) || !size_ok(f->out_w, f->out_h)) {      // the tables below are allocated from these numbers
+        mdc_set_error("camera calibration %s: image larger than 2^28 pixels", path);
+        return MDC_ERR_FORMAT;
+    }
     f->valid = true;
     mdc_fov_build(f, mode, oc);
     return MDC_OK;
@@ -279,7 +287,7 @@ extern "C" int mdc_fov_create_from_params(const float in_calib[5], int in_w, int
                                           const float out_calib[5], int out_w, int out_h, int float_math,
                                           mdc_fov** out) {
     if (!out || !in_calib) { mdc_set_error("mdc_fov_create_from_params: NULL argument"); return MDC_ERR_INVALID_ARG; }
-    if (in_w < 2 || in_h < 2 || out_w < 1 || out_h < 1) { mdc_set_error("mdc_fov_create_from_params: bad size"); return MDC_ERR_INVALID_ARG; }
+    if (in_w < 2 || in_h < 2 || out_w < 1 || out_h < 1 || !size_ok(in_w, in_h) || !size_ok(out_w, out_h)) { mdc_set_error("mdc_fov_create_from_params: bad size"); return MDC_ERR_INVALID_ARG; }
     if (mode == MDC_FOV_EXPLICIT && !out_calib) { mdc_set_error("mdc_fov_create_from_params: explicit mode needs out_calib"); return MDC_ERR_INVALID_ARG; }
     mdc_fov* f = new mdc_fov();
     f->float_math = float_math ? 1 : 0;
@@ -410,7 +418,7 @@ extern "C" int mdc_photo_create(const char* pcalib_txt, const char* vignette_ima
         return MDC_ERR_FORMAT;
     }
     if (!mdc_photo_set_gamma(p, raw.data())) { mdc_set_error("%s: response not strictly increasing", calib.c_str()); return MDC_ERR_FORMAT; }
-    if (w < 1 || h < 1) { mdc_set_error("photometric calibration: bad image size %d x %d", w, h); return MDC_ERR_INVALID_ARG; }
+    if (w < 1 || h < 1 || !size_ok(w, h)) { mdc_set_error("photometric calibration: bad image size %d x %d", w, h); return MDC_ERR_INVALID_ARG; }
 
     printf("Reading Vignette Image from %s\n", vig.c_str());
     p->vmap.assign(static_cast<size_t>(w) * h, 0.0f);
@@ -435,7 +443,7 @@ extern "C" int mdc_photo_create_from_arrays(const float* ginv_raw256, const void
     *out = p;
     if (!ginv_raw256 || !vignette_pixels) { mdc_set_error("photometric calibration: missing table"); return MDC_ERR_INVALID_OBJECT; }
     if (!mdc_photo_set_gamma(p, ginv_raw256)) { mdc_set_error("response not strictly increasing"); return MDC_ERR_FORMAT; }
-    if (w < 1 || h < 1) { mdc_set_error("photometric calibration: bad image size"); return MDC_ERR_INVALID_ARG; }
+    if (w < 1 || h < 1 || !size_ok(w, h)) { mdc_set_error("photometric calibration: bad image size"); return MDC_ERR_INVALID_ARG; }
     p->vmap.assign(static_cast<size_t>(w) * h, 0.0f);
     p->vinv.assign(static_cast<size_t>(w) * h, 0.0f);
     if (rows != h || cols != w || (depth != 8 && depth != 16)) {

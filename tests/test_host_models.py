@@ -84,6 +84,12 @@ def test_invalid_camera_files(tmp_path, capfd):
     u = api.UndistorterFOV(str(tmp_path / "missing.txt"))
     assert not u.isValid() and u.status == 2
     assert "Failed to read camera calibration" in capfd.readouterr().out
+    # sizes from the file drive allocations: absurd ones are refused instead of letting an allocation throw across the C ABI
+    for text in ["0.3 0.4 0.5 0.5 0.9\n640 480\ncrop\n2000000000 2000000000\n", "0.3 0.4 0.5 0.5 0.9\n2000000000 2000000000\ncrop\n640 480\n",
+                 "0.3 0.4 0.5 0.5 0.9\n640 480\ncrop\n65536 65536\n"]:
+        cam.write_text(text)
+        u = api.UndistorterFOV(str(cam))
+        assert not u.isValid() and u.status == 3, text      # MDC_ERR_FORMAT
 
 
 @pytest.mark.parametrize("depth", [8, 16])
